@@ -1,0 +1,95 @@
+/* tbk.h -- C ABI of libtbk.so, the B200-native evaluator for the TBmodels k-space hot path.
+ *
+ * The reference (Z2PackDev/TBmodels v1.4.4) is pure Python and has no FFI seam; the boundary this
+ * library sits behind is the pair of methods
+ *     Model.hamilton(self, k, convention=2)      reference src/tbmodels/_tb_model.py:1076-1132
+ *     Model.eigenval(self, k)                    reference src/tbmodels/_tb_model.py:1134-1150
+ * plus the state they read: Model.hop (:206-218, half-set semantics from _reduce_hop :247-279),
+ * Model.pos (:186-191), Model.size, Model.dim.  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = OK, non-zero = error (TBK_E_*); the message for the last
+ *     error on the calling thread is tbk_last_error().  No C++ exceptions cross the boundary.
+ *   - plain pointers and sizes only; complex128 arrays are interleaved (re, im) doubles, row-major.
+ *   - a handle is immutable after creation (re-create it when the model's hoppings change) and owns its
+ *     device scratch; use one handle per GPU and one in-flight call per handle.
+ *   - "_host" entry points take HOST pointers and run a chunked H2D -> kernels -> D2H pipeline on private
+ *     streams (pinned buffers from tbk_host_alloc overlap fully; pageable memory works, slower); the plain
+ *     entry points take DEVICE pointers, enqueue on the caller's stream and return without synchronising.
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails.
+ */
+#ifndef TBK_H
+#define TBK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBK_OK 0
+#define TBK_E_INVALID 1     /* bad argument (null pointer, size, convention, dimension) */
+#define TBK_E_CUDA 2        /* CUDA runtime / launch failure */
+#define TBK_E_UNSUPPORTED 3 /* model outside the supported envelope (dim > 8) */
+#define TBK_E_NOCONV 4      /* QL iteration did not converge for some matrix */
+
+typedef struct tbk_model tbk_model;
+
+/* Library version (major * 100 + minor). */
+int tbk_version(void);
+/* Message describing the last error on this thread ("" if none). */
+const char* tbk_last_error(void);
+
+/* Pack a model onto GPU `device`.
+ *   R    [n_R][dim]            int32   keys of Model.hop, in dict order            (_tb_model.py:1111)
+ *   hop  [n_R][n_orb][n_orb]   c128    dense values of Model.hop; the R = 0 entry holds HALF the on-site
+ *                                      block, exactly as the reference stores it     (:218, :268)
+ *   pos  [n_orb][dim]          f64     Model.pos (reduced coordinates)              (:186-191)
+ * All three are HOST pointers, copied during the call.  n_R may be 0 (H == 0). */
+int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double* hop, const double* pos,
+                     int device, tbk_model** out);
+int tbk_model_destroy(tbk_model* m);
+/* path: 0 = fused thread-per-k kernel (N <= 8), 1 = DMMA GEMM + batched tridiagonal/QL eigensolver. */
+int tbk_model_info(const tbk_model* m, int* n_orb, int* dim, int* n_R, int* path);
+
+/* Model.hamilton for a batch (replaces _tb_model.py:1109-1128).
+ *   k_dev   [n_k][dim]            f64   device
+ *   out_dev [n_k][n_orb][n_orb]   c128  device
+ *   convention  1 or 2 (anything else -> TBK_E_INVALID; the Python layer raises ValueError first, :1097-1102) */
+int tbk_hamilton(tbk_model* m, const double* k_dev, int64_t n_k, int convention, double* out_dev, void* stream);
+/* Model.eigenval for a batch (replaces _tb_model.py:1147-1149): convention-2 H(k), eigenvalues ascending.
+ *   out_dev [n_k][n_orb] f64 device */
+int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* stream);
+
+/* Same two operations with HOST buffers (copies inside, synchronous on return). */
+int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host);
+int tbk_eigenval_host(tbk_model* m, const double* k_host, int64_t n_k, double* out_host);
+
+/* Synchronise the handle's device and report deferred errors (QL non-convergence) of the device-pointer calls. */
+int tbk_model_check(tbk_model* m);
+/* Number of kernels launched through this handle so far. */
+int64_t tbk_launch_count(const tbk_model* m);
+/* Bytes of device scratch currently held by the handle. */
+int64_t tbk_workspace_bytes(const tbk_model* m);
+
+/* Page-locked host memory for the _host entry points. */
+int tbk_host_alloc(void** p, size_t bytes);
+int tbk_host_free(void* p);
+
+/* Measured FP64 peaks of the current device, TFLOP/s (kind 0: DMMA mma.sync.m8n8k4.f64, 1: DFMA). < 0 on error. */
+double tbk_measure_fp64_peak(int kind, int iters);
+
+/* ---- host-side debug entry points: run the exact scalar code of the kernels on the CPU (tests only) ---- */
+/* In-place eigenvalues of a real symmetric tridiagonal matrix; d[n], e[n] (e[n-1] scratch). Returns #failures. */
+int tbk_host_tridiag_ql(int n, double* d, double* e);
+/* Packed Hermitian (n*n doubles, destroyed) -> d[n], e[n]. */
+int tbk_host_hetrd(int n, double* hp, double* d, double* e);
+/* Hermitian-split weights W[2*n_R][n_orb*n_orb] the kernels consume, from hop[n_R][n_orb][n_orb] c128. */
+int tbk_host_pack_weights(int n_orb, int n_R, const double* hop, double* W);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBK_H */

@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE ONLY -- import the unmodified reference ``tbmodels`` from /root/reference.
+
+This module is part of the parity oracle: only ``tests/``, ``oracle/make_golden.py`` and the
+``cpu_baseline`` leg of ``bench.py`` may use anything under ``oracle/``.  The product package
+``tbmodels_b200`` never imports it.
+
+``/root/reference`` exists only in the build container (never on the GPU box), so everything that
+goes through this shim is either a ``-m "not gpu"`` test that skips when the tree is absent, or the
+golden-vector generator whose outputs are committed under ``tests/golden/``.
+
+The reference (v1.4.4) does not import on this image as-is; the hot path itself needs only numpy and
+scipy.  The shims:
+
+* ``importlib.metadata.version("tbmodels")`` -> "1.4.4"       (src/tbmodels/__init__.py:7)
+* stub ``h5py`` and ``fsc.hdf5_io`` modules                     (src/tbmodels/_tb_model.py:21,26; io.py:10-11)
+* ``np.complex_`` / ``np.float_`` aliases removed in numpy 2    (src/tbmodels/_tb_model.py:1131,1150)
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.metadata
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("TBK_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "tbmodels"))
+
+
+def _install_stubs() -> None:
+    if not hasattr(np, "complex_"):
+        np.complex_ = np.complex128  # type: ignore[attr-defined]
+    if not hasattr(np, "float_"):
+        np.float_ = np.float64  # type: ignore[attr-defined]
+
+    orig_version = importlib.metadata.version
+
+    def version(name):  # noqa: D401
+        if name == "tbmodels":
+            return "1.4.4"
+        return orig_version(name)
+
+    importlib.metadata.version = version  # type: ignore[assignment]
+
+    if "h5py" not in sys.modules:
+        try:
+            importlib.import_module("h5py")
+        except ImportError:
+            h5 = types.ModuleType("h5py")
+            h5.File = object  # type: ignore[attr-defined]
+            h5.Group = object  # type: ignore[attr-defined]
+            sys.modules["h5py"] = h5
+    if "fsc.hdf5_io" not in sys.modules:
+        try:
+            importlib.import_module("fsc.hdf5_io")
+        except ImportError:
+            fsc = types.ModuleType("fsc")
+            hio = types.ModuleType("fsc.hdf5_io")
+
+            class HDF5Enabled:  # plain base class, no behaviour needed on the hot path
+                pass
+
+            class SimpleHDF5Mapping(HDF5Enabled):
+                pass
+
+            def subscribe_hdf5(*_a, **_k):
+                return lambda cls: cls
+
+            def _unavailable(*_a, **_k):
+                raise RuntimeError("fsc.hdf5_io is stubbed: HDF5 I/O is not available in this container")
+
+            hio.HDF5Enabled = HDF5Enabled
+            hio.SimpleHDF5Mapping = SimpleHDF5Mapping
+            hio.subscribe_hdf5 = subscribe_hdf5
+            hio.save = _unavailable
+            hio.load = _unavailable
+            hio.to_hdf5 = _unavailable
+            hio.from_hdf5 = _unavailable
+            hio.to_hdf5_file = _unavailable
+            hio.from_hdf5_file = _unavailable
+            fsc.hdf5_io = hio
+            sys.modules["fsc"] = fsc
+            sys.modules["fsc.hdf5_io"] = hio
+
+
+def import_reference():
+    """Return the reference ``tbmodels`` module (unmodified sources, shimmed imports)."""
+    if "tbmodels" in sys.modules:
+        return sys.modules["tbmodels"]
+    if not reference_available():
+        raise ImportError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    src = os.path.join(REFERENCE_ROOT, "src")
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return importlib.import_module("tbmodels")

@@ -1,0 +1,119 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy/scipy) of the TBmodels k-space hot path.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function here against
+(a) outputs of the unmodified reference run in the build container (``tests/golden/*.npz``, made by
+``oracle/make_golden.py``), (b) the reference's own known-answer file
+``tests/samples/cli_eigenvals/silicon_eigenvals.hdf5`` (values committed in
+``tests/golden/silicon_cli_eigenvals.npz``) and (c) the reference's regression goldens
+``tests/regression_data/test_hamilton|test_eigenval`` (subset committed in
+``tests/golden/ref_regression.npz``).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product package ``tbmodels_b200`` must never import it.
+
+The functions operate on the *packed* form of a model (what ``tbmodels_b200.pack_model`` produces):
+
+* ``R``   int   [n_R, dim]      -- the keys of ``Model.hop`` (half set: first non-zero component > 0, or 0)
+* ``hop`` c128  [n_R, N, N]     -- the dense values of ``Model.hop`` (R = 0 entry is HALF the on-site block,
+                                   reference src/tbmodels/_tb_model.py:218,268)
+* ``pos`` f64   [N, dim]        -- ``Model.pos``
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as la
+
+
+def hamilton(R, hop, pos, k, convention=2):
+    """Restates ``Model.hamilton`` (reference src/tbmodels/_tb_model.py:1076-1132) operation by operation.
+
+    Same loop order over the stored R vectors, same ``exp(2j*pi*dot(k, R))`` phase (argument rounded in
+    f64 before the exponential, :1118), same ``H += H^dagger`` (:1123) and the orbital-position phases for
+    ``convention == 1`` only (:1124-1128).
+    """
+    if convention not in [1, 2]:  # :1097-1102
+        raise ValueError(
+            "Invalid value '{}' for 'convention': must be either '1' or '2'".format(convention)
+        )
+    R = np.asarray(R)
+    hop = np.asarray(hop)
+    pos = np.asarray(pos)
+    size = pos.shape[0]
+    k_array = np.array(k, ndmin=1)  # :1103
+    if k_array.ndim == 1:
+        single_point = True
+        k_array = k_array.reshape((1, -1))
+    else:
+        single_point = False
+    H = np.zeros((k_array.shape[0], size, size), dtype=complex)  # :1109
+    tmp_array = np.empty_like(H)
+    for r_vec, mat in zip(R, hop):  # :1111-1122
+        np.multiply(
+            np.exp(2j * np.pi * np.dot(k_array, r_vec)).reshape((-1, 1, 1)),
+            mat[np.newaxis, :, :],
+            out=tmp_array,
+        )
+        H += tmp_array
+    H += H.conjugate().transpose((0, 2, 1))  # :1123
+    if convention == 1:  # :1124-1128
+        pos_exponential = np.array(
+            [[np.exp(2j * np.pi * np.dot(k_array, p)) for p in pos]]
+        ).transpose((2, 0, 1))
+        H = pos_exponential.conjugate().transpose((0, 2, 1)) * H * pos_exponential
+    if single_point:  # :1130-1132
+        return H[0]
+    return H
+
+
+def eigenval(R, hop, pos, k):
+    """Restates ``Model.eigenval`` (reference src/tbmodels/_tb_model.py:1134-1150).
+
+    ``hamilton`` with the default convention 2, then one ``scipy.linalg.eigvalsh`` (LAPACK, lower
+    triangle, ascending) per k-point in a Python loop; returns a list of arrays for a k-list and a single
+    array for a single k-point.
+    """
+    hamiltonians = hamilton(R, hop, pos, k)
+    if hamiltonians.ndim == 3:
+        return [la.eigvalsh(ham) for ham in hamiltonians]
+    return la.eigvalsh(hamiltonians)
+
+
+def eigenval_array(R, hop, pos, k, chunk=4096):
+    """``eigenval`` for a k-list, chunked so the two [n_k, N, N] temporaries of the reference stay small.
+
+    Returns one ``[n_k, N]`` array.  Chunking does not change any number (every k-point is independent,
+    reference :1109-1132); it only bounds memory, which the reference cannot do at the benchmark sizes.
+    """
+    k = np.asarray(k, dtype=float)
+    assert k.ndim == 2
+    size = np.asarray(pos).shape[0]
+    out = np.empty((k.shape[0], size))
+    for start in range(0, k.shape[0], chunk):
+        ev = eigenval(R, hop, pos, k[start : start + chunk])
+        if len(ev):
+            out[start : start + chunk] = np.asarray(ev)
+    return out
+
+
+def hamilton_longdouble(R, hop, pos, k, convention=2):
+    """Same formula evaluated with 80-bit phases (argument reduced exactly); used only to show which of two
+    f64 implementations is closer to the exact answer when they disagree at the 1e-15 level."""
+    R = np.asarray(R)
+    hop = np.asarray(hop)
+    pos = np.asarray(pos, dtype=np.longdouble)
+    k_array = np.array(k, ndmin=2, dtype=np.longdouble)
+    size = pos.shape[0]
+    H = np.zeros((k_array.shape[0], size, size), dtype=np.clongdouble)
+    pi_l = np.longdouble("3.14159265358979323846264338327950288")
+    for r_vec, mat in zip(R, hop):
+        x = k_array @ r_vec.astype(np.longdouble)
+        x = x - np.rint(x)
+        ph = np.cos(2 * pi_l * x) + 1j * np.sin(2 * pi_l * x)
+        H += ph.reshape((-1, 1, 1)) * mat[None].astype(np.clongdouble)
+    H = H + H.conjugate().transpose((0, 2, 1))
+    if convention == 1:
+        x = k_array @ pos.T  # [nk, N]
+        x = x - np.rint(x)
+        pe = np.cos(2 * pi_l * x) + 1j * np.sin(2 * pi_l * x)
+        H = pe.conjugate()[:, :, None] * H * pe[:, None, :]
+    return H

@@ -1,0 +1,234 @@
+"""Device evaluator: the object that owns a ``tbk_model`` handle and mirrors the reference call contract.
+
+``Evaluator.hamilton`` / ``Evaluator.eigenval`` reproduce the argument handling and return types of
+``Model.hamilton`` / ``Model.eigenval`` (reference src/tbmodels/_tb_model.py:1076-1150):
+
+* ``convention not in [1, 2]`` -> ``ValueError`` with the reference's message, before any device work (:1097-1102);
+* ``np.array(k, ndmin=1)``; a 1-D (or scalar) k is a single point and the leading axis is squeezed from the
+  result (:1103-1108, :1130-1132);
+* ``eigenval`` of a k-list returns a Python ``list`` of ``[N]`` arrays, of a single point one ``[N]`` array
+  (:1148-1150).  The list elements are views of one ``[n_k, N]`` buffer (``eigenval_array`` returns it whole).
+
+Everything numerical happens in libtbk.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _capi
+from ._pack import PackedModel
+
+
+def _check_convention(convention) -> None:
+    if convention not in [1, 2]:
+        raise ValueError(
+            "Invalid value '{}' for 'convention': must be either '1' or '2'".format(convention)
+        )
+
+
+def _normalise_k(k, dim: int):
+    """Reference semantics of ``k_array = np.array(k, ndmin=1)`` + single-point reshape (:1103-1108)."""
+    k_array = np.array(k, ndmin=1)
+    if k_array.ndim == 1:
+        single_point = True
+        k_array = k_array.reshape((1, -1))
+    else:
+        single_point = False
+    if k_array.ndim != 2:
+        raise ValueError(f"k must be a k-point or a list of k-points, got an array of shape {k_array.shape}")
+    if k_array.shape[1] != dim:
+        # the reference fails inside np.dot(k_array, R) with a ValueError as well
+        raise ValueError(
+            f"shapes {k_array.shape} and ({dim},) not aligned: k-points must have {dim} component(s)"
+        )
+    if k_array.dtype.kind not in "fiub":
+        raise TypeError(f"k-points must be real numbers, got dtype {k_array.dtype}")
+    return np.ascontiguousarray(k_array, dtype=np.float64), single_point
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """Uninitialised page-locked numpy array (fast path of the host entry points); freed with the array."""
+    lib = _capi.load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    nbytes = max(n * dtype.itemsize, 1)
+    ptr = C.c_void_p()
+    _capi.check(lib.tbk_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    weakref.finalize(buf, lib.tbk_host_free, ptr.value)
+    return arr
+
+
+class Evaluator:
+    """GPU-resident copy of one packed model plus the launch plumbing."""
+
+    def __init__(self, packed: PackedModel, device=None):
+        self._lib = _capi.load()
+        self.packed = packed
+        self.size = packed.size
+        self.dim = packed.dim
+        if device is None:
+            device = _default_device()
+        self.device = int(device)
+        handle = C.c_void_p()
+        _capi.check(
+            self._lib.tbk_model_create(
+                packed.dim,
+                packed.size,
+                packed.n_R,
+                packed.R.ctypes.data_as(C.c_void_p),
+                packed.hop.ctypes.data_as(C.c_void_p),
+                packed.pos.ctypes.data_as(C.c_void_p),
+                self.device,
+                C.byref(handle),
+            )
+        )
+        self._handle = handle
+        self._finalizer = weakref.finalize(self, self._lib.tbk_model_destroy, handle)
+
+    # ------------------------------------------------------------------ info
+    @property
+    def path(self) -> str:
+        p = C.c_int()
+        _capi.check(self._lib.tbk_model_info(self._handle, None, None, None, C.byref(p)))
+        return "fused-small" if p.value == 0 else "gemm+tridiag-ql"
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.tbk_launch_count(self._handle))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._lib.tbk_workspace_bytes(self._handle))
+
+    def close(self) -> None:
+        self._finalizer()
+
+    def check(self) -> None:
+        """Synchronise and raise if a device-pointer call hit a deferred error (QL non-convergence)."""
+        _capi.check(self._lib.tbk_model_check(self._handle))
+
+    # ------------------------------------------------------------------ host buffers (reference contract)
+    def hamilton(self, k, convention=2, out=None):
+        _check_convention(convention)
+        k_array, single_point = _normalise_k(k, self.dim)
+        n_k = k_array.shape[0]
+        shape = (n_k, self.size, self.size)
+        if out is None:
+            out = np.empty(shape, dtype=np.complex128)
+        elif out.shape != shape or out.dtype != np.complex128 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous complex128 array of shape %r" % (shape,))
+        _capi.check(
+            self._lib.tbk_hamilton_host(
+                self._handle,
+                k_array.ctypes.data_as(C.c_void_p),
+                n_k,
+                int(convention),
+                out.ctypes.data_as(C.c_void_p),
+            )
+        )
+        if single_point:
+            return out[0]
+        return out
+
+    def eigenval_array(self, k, out=None) -> np.ndarray:
+        """Eigenvalues of a k-list as one ``[n_k, N]`` array (no per-k Python objects)."""
+        k_array, _ = _normalise_k(k, self.dim)
+        n_k = k_array.shape[0]
+        shape = (n_k, self.size)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %r" % (shape,))
+        _capi.check(
+            self._lib.tbk_eigenval_host(
+                self._handle, k_array.ctypes.data_as(C.c_void_p), n_k, out.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return out
+
+    def eigenval(self, k):
+        k_array, single_point = _normalise_k(k, self.dim)
+        res = self.eigenval_array(k_array)
+        if single_point:
+            return res[0]
+        return list(res)
+
+    # ------------------------------------------------------------------ device buffers (torch tensors as allocators)
+    def _stream(self):
+        import torch
+
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_k_dev(self, k_dev):
+        import torch
+
+        if not (isinstance(k_dev, torch.Tensor) and k_dev.is_cuda):
+            raise TypeError("k_dev must be a CUDA torch.Tensor")
+        if k_dev.device.index != self.device:
+            raise ValueError(f"k_dev lives on {k_dev.device}, the evaluator on cuda:{self.device}")
+        if k_dev.dtype != torch.float64 or k_dev.ndim != 2 or k_dev.shape[1] != self.dim:
+            raise ValueError(f"k_dev must be float64 [n_k, {self.dim}]")
+        return k_dev.contiguous()
+
+    def hamilton_device(self, k_dev, convention=2, out=None):
+        """``[n_k, dim]`` float64 CUDA tensor -> ``[n_k, N, N]`` complex128 CUDA tensor, asynchronous."""
+        import torch
+
+        _check_convention(convention)
+        k_dev = self._check_k_dev(k_dev)
+        n_k = k_dev.shape[0]
+        if out is None:
+            out = torch.empty((n_k, self.size, self.size), dtype=torch.complex128, device=k_dev.device)
+        elif tuple(out.shape) != (n_k, self.size, self.size) or out.dtype != torch.complex128 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous complex128 tensor [n_k, N, N]")
+        _capi.check(
+            self._lib.tbk_hamilton(
+                self._handle, C.c_void_p(k_dev.data_ptr()), n_k, int(convention), C.c_void_p(out.data_ptr()),
+                self._stream(),
+            )
+        )
+        return out
+
+    def eigenval_device(self, k_dev, out=None):
+        """``[n_k, dim]`` float64 CUDA tensor -> ``[n_k, N]`` float64 CUDA tensor (ascending), asynchronous."""
+        import torch
+
+        k_dev = self._check_k_dev(k_dev)
+        n_k = k_dev.shape[0]
+        if out is None:
+            out = torch.empty((n_k, self.size), dtype=torch.float64, device=k_dev.device)
+        elif tuple(out.shape) != (n_k, self.size) or out.dtype != torch.float64 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float64 tensor [n_k, N]")
+        _capi.check(
+            self._lib.tbk_eigenval(
+                self._handle, C.c_void_p(k_dev.data_ptr()), n_k, C.c_void_p(out.data_ptr()), self._stream()
+            )
+        )
+        return out
+
+
+def _default_device() -> int:
+    """LOCAL_RANK under torchrun (one process per GPU), else device 0."""
+    import os
+
+    try:
+        return int(os.environ.get("TBK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    except ValueError:
+        return 0
+
+
+def fp64_peaks(iters: int = 4000) -> dict:
+    """Measured FP64 peaks of the current device in TFLOP/s: ``{"dmma": .., "dfma": ..}``."""
+    lib = _capi.load()
+    out = {}
+    for name, kind in (("dmma", 0), ("dfma", 1)):
+        v = float(lib.tbk_measure_fp64_peak(kind, iters))
+        if v < 0:
+            raise _capi.TbkError(_capi.TBK_E_CUDA, "FP64 peak micro-benchmark failed (no CUDA device?)")
+        out[name] = v
+    return out

@@ -1,0 +1,74 @@
+"""Host-side mirror of the slice of ``tbmodels.Model`` that the k-space hot path touches.
+
+``KModel`` carries exactly the state ``Model.hamilton`` / ``Model.eigenval`` read -- ``hop`` (half-set dict),
+``pos``, ``size``, ``dim`` (reference src/tbmodels/_tb_model.py:186-218) -- and exposes the same two methods
+with the same signatures, return types and error behaviour (:1076-1150), evaluated on the GPU.
+
+It exists so that (a) the accelerated path can be used and tested on machines where the reference package
+is not installed (the GPU box), and (b) a ``tbmodels.Model`` can be handed over with
+``KModel.from_model(model)``.  Model construction / file formats / model algebra stay in the reference.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._evaluator import Evaluator
+from ._pack import PackedModel, hop_dict, pack_arrays, pack_model
+
+
+class KModel:
+    """Duck-type of ``tbmodels.Model`` restricted to the k-space evaluation path."""
+
+    def __init__(self, *, hop, pos, size=None, dim=None, device=None):
+        pos = np.array(pos, dtype=float)
+        self.size = int(size) if size is not None else pos.shape[0]
+        self.dim = int(dim) if dim is not None else pos.shape[1]
+        self.pos = pos.reshape(self.size, self.dim)
+        self.hop = {tuple(int(x) for x in R): np.array(mat, dtype=complex) for R, mat in hop.items()}
+        self.uc = None
+        self.occ = None
+        self._device = device
+        self._cache = None  # (digest, Evaluator); never pickled
+
+    # -- constructors ------------------------------------------------------------------------------
+    @classmethod
+    def from_packed(cls, packed: PackedModel, device=None) -> "KModel":
+        return cls(hop=hop_dict(packed), pos=packed.pos, size=packed.size, dim=packed.dim, device=device)
+
+    @classmethod
+    def from_arrays(cls, R, hop, pos, device=None) -> "KModel":
+        return cls.from_packed(pack_arrays(R, hop, pos), device=device)
+
+    @classmethod
+    def from_model(cls, model, device=None) -> "KModel":
+        """Snapshot of a ``tbmodels.Model`` (or anything with hop / pos / size / dim)."""
+        return cls.from_packed(pack_model(model), device=device)
+
+    # -- pickling: device handles never enter the pickled state (reference tests/test_pickle.py) -------
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_cache"] = None
+        return state
+
+    # -- evaluation --------------------------------------------------------------------------------
+    def evaluator(self) -> Evaluator:
+        """Device copy of the current hoppings; re-packed when ``hop`` / ``pos`` were mutated."""
+        packed = pack_model(self)
+        digest = packed.digest()
+        if self._cache is None or self._cache[0] != digest:
+            if self._cache is not None:
+                self._cache[1].close()
+            self._cache = (digest, Evaluator(packed, device=self._device))
+        return self._cache[1]
+
+    def hamilton(self, k, convention=2):
+        """Same contract as ``tbmodels.Model.hamilton`` (reference :1076-1132)."""
+        if convention not in [1, 2]:
+            raise ValueError(
+                "Invalid value '{}' for 'convention': must be either '1' or '2'".format(convention)
+            )
+        return self.evaluator().hamilton(k, convention=convention)
+
+    def eigenval(self, k):
+        """Same contract as ``tbmodels.Model.eigenval`` (reference :1134-1150)."""
+        return self.evaluator().eigenval(k)

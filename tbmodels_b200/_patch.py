@@ -1,0 +1,98 @@
+"""Drop-in switch for the reference package: route ``tbmodels.Model.hamilton`` / ``eigenval`` to the GPU.
+
+    import tbmodels, tbmodels_b200
+    tbmodels_b200.install()          # Model.hamilton / Model.eigenval now run on the B200
+    ...
+    tbmodels_b200.uninstall()        # restore the numpy implementations
+
+Signatures, return types and the ``ValueError`` for a bad ``convention`` are the reference's
+(src/tbmodels/_tb_model.py:1076-1150), so callers such as the ``tbmodels eigenvals`` CLI
+(src/tbmodels/_cli.py:255-257, which passes ``model.eigenval`` as a callable) keep working unchanged.
+
+``Model.hop`` and ``Model.pos`` are public and mutated in place by the reference (``add_hop`` :1215,
+``remove_small_hop`` :1254-1256, plain reads of missing ``defaultdict`` keys :206), so every call re-packs
+the model (O(n_R N^2), tiny next to the batch) and compares a content digest with the cached device copy.
+Device handles live in a side table keyed by ``id(model)`` -- never in ``model.__dict__`` -- so pickling and
+HDF5 serialisation of the model are unaffected (reference tests/test_pickle.py, tests/test_hdf5.py).
+"""
+from __future__ import annotations
+
+import weakref
+
+from ._evaluator import Evaluator
+from ._pack import pack_model
+
+_cache: dict = {}  # id(model) -> (digest, Evaluator)
+_originals: dict = {}
+_device = None
+
+
+def _drop(key):
+    entry = _cache.pop(key, None)
+    if entry is not None:
+        entry[1].close()
+
+
+def evaluator_for(model) -> Evaluator:
+    """Cached device evaluator for ``model`` (rebuilt when its hoppings / positions changed)."""
+    packed = pack_model(model)
+    digest = packed.digest()
+    key = id(model)
+    entry = _cache.get(key)
+    if entry is None or entry[0] != digest:
+        if entry is None:
+            try:
+                weakref.finalize(model, _drop, key)
+            except TypeError:  # object without weakref support: the entry lives until uninstall()
+                pass
+        else:
+            entry[1].close()
+        entry = (digest, Evaluator(packed, device=_device))
+        _cache[key] = entry
+    return entry[1]
+
+
+def _hamilton(self, k, convention=2):
+    if convention not in [1, 2]:
+        raise ValueError(
+            "Invalid value '{}' for 'convention': must be either '1' or '2'".format(convention)
+        )
+    return evaluator_for(self).hamilton(k, convention=convention)
+
+
+def _eigenval(self, k):
+    return evaluator_for(self).eigenval(k)
+
+
+def install(model_cls=None, device=None):
+    """Replace ``hamilton`` / ``eigenval`` on ``tbmodels.Model`` (or on ``model_cls``)."""
+    global _device
+    if model_cls is None:
+        import tbmodels  # the reference package; only needed for the drop-in switch
+
+        model_cls = tbmodels.Model
+    _device = device
+    if model_cls not in _originals:
+        _originals[model_cls] = (model_cls.__dict__.get("hamilton"), model_cls.__dict__.get("eigenval"))
+    _hamilton.__doc__ = getattr(_originals[model_cls][0], "__doc__", None)
+    _eigenval.__doc__ = getattr(_originals[model_cls][1], "__doc__", None)
+    model_cls.hamilton = _hamilton
+    model_cls.eigenval = _eigenval
+    return model_cls
+
+
+def uninstall(model_cls=None):
+    """Restore the original methods and release every cached device copy."""
+    classes = [model_cls] if model_cls is not None else list(_originals)
+    for cls in classes:
+        orig = _originals.pop(cls, None)
+        if orig is None:
+            continue
+        for name, fn in zip(("hamilton", "eigenval"), orig):
+            if fn is None:
+                if name in cls.__dict__:
+                    delattr(cls, name)
+            else:
+                setattr(cls, name, fn)
+    for key in list(_cache):
+        _drop(key)

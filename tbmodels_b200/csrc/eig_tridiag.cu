@@ -1,0 +1,228 @@
+// eig_tridiag.cu -- batched Hermitian -> real symmetric tridiagonal reduction (eigenvalues only).
+//
+// First half of the replacement for the per-k scipy.linalg.eigvalsh loop of Model.eigenval
+// (reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr with JOBZ='N', UPLO='L').
+// A group of G threads (8 .. 256, chosen from N only, never from the batch) reduces one packed
+// lower-triangular matrix with unblocked Householder reflections:
+//     x = A[j+1:, j]  ->  (beta, tau, v);   p = tau A22 v;   w = p - (tau/2)(p^H v) v;   A22 -= v w^H + w v^H.
+// For N <= 160 the matrix is copied once into shared memory (packed: N^2 doubles) and never goes back to
+// HBM; above that the group works in place on the packed H(k) scratch in global memory (L2 resident per
+// chunk).  Every group executes exactly the same instruction sequence (no data-dependent early exits), so
+// sub-warp groups can share a warp and use __syncwarp().  Outputs: D[k][0..N) diagonal, E[k][0..N-1)
+// sub-diagonal, consumed by eig_ql.cu.
+#include "tbk_kernels.h"
+#include "tbk_math.cuh"
+
+namespace tbk {
+
+namespace {
+
+constexpr int TPB = 256;
+
+template <int G>
+__device__ __forceinline__ void group_sync(int group) {
+    if (G <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G) : "memory");
+    }
+}
+
+// Sum (a, b) over the G threads of a group; every thread gets the result.  Fixed butterfly order.
+template <int G>
+__device__ __forceinline__ void group_sum2(double& a, double& b, double* red, int group, int t, int& parity) {
+    constexpr int W = G < 32 ? G : 32;
+#pragma unroll
+    for (int off = W / 2; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off, W);
+        b += __shfl_xor_sync(0xffffffffu, b, off, W);
+    }
+    if (G > 32) {
+        constexpr int NW = G / 32;
+        double* buf = red + parity * 2 * NW;  // double-buffered: one barrier per reduction
+        parity ^= 1;
+        if ((t & 31) == 0) {
+            buf[2 * (t >> 5)] = a;
+            buf[2 * (t >> 5) + 1] = b;
+        }
+        group_sync<G>(group);
+        a = 0.0;
+        b = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            a += buf[2 * w];
+            b += buf[2 * w + 1];
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(TPB)
+tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E, int in_smem) {
+    const int MPB = blockDim.x / G;  // matrices per CTA (run time: bounded by shared memory)
+    constexpr int NW = G > 32 ? G / 32 : 1;
+    extern __shared__ __align__(16) double sm[];
+    const int group = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    const long NN = (long)N * N;
+    const long nre = tri(N);
+
+    const long kidx = (long)blockIdx.x * MPB + group;
+    const bool valid = kidx < nk;
+    const long kk = valid ? kidx : nk - 1;  // idle groups shadow the last matrix (smem mode only) and store nothing
+
+    // per-group shared-memory carve-up
+    const long per_group = (in_smem ? NN : 0) + 6L * N + 4 * NW + 2;
+    double* base = sm + group * per_group;
+    double* A = in_smem ? base : (Hp + kk * NN);
+    double* Vr = base + (in_smem ? NN : 0);
+    double* Vi = Vr + N;
+    double* Pr = Vi + N;
+    double* Pi = Pr + N;
+    double* ds = Pi + N;
+    double* es = ds + N;
+    double* red = es + N;
+
+    if (!in_smem && !valid) return;  // MPB == 1 in global mode: whole CTA leaves together
+
+    if (in_smem) {
+        const double* src = Hp + kk * NN;
+        for (long e = t; e < NN; e += G) A[e] = src[e];
+    }
+    group_sync<G>(group);
+
+    double* Ar = A;
+    double* Ai = A + nre;
+    int parity = 0;
+
+    for (int j = 0; j < N - 1; ++j) {
+        const int m = N - 1 - j;
+        const int r0 = j + 1;
+        // --- reflector from column j ---
+        const double ar = Ar[tri(r0) + j];
+        const double ai = Ai[trs(r0) + j];
+        double xn = 0.0, dummy = 0.0;
+        for (int a = 1 + t; a < m; a += G) {
+            const long I = r0 + a;
+            const double xr = Ar[tri(I) + j], xi = Ai[trs(I) + j];
+            xn += xr * xr + xi * xi;
+        }
+        group_sum2<G>(xn, dummy, red, group, t, parity);
+        double beta, tr, ti, sr, si;
+        householder_gen(ar, ai, xn, beta, tr, ti, sr, si);
+        if (t == 0) {
+            ds[j] = Ar[tri(j) + j];
+            es[j] = beta;
+        }
+        for (int a = t; a < m; a += G) {
+            if (a == 0) {
+                Vr[0] = 1.0;
+                Vi[0] = 0.0;
+            } else {
+                const long I = r0 + a;
+                const double xr = Ar[tri(I) + j], xi = Ai[trs(I) + j];
+                Vr[a] = xr * sr - xi * si;
+                Vi[a] = xr * si + xi * sr;
+            }
+        }
+        group_sync<G>(group);
+        // --- p = tau * A22 v, dot = p^H v ---
+        double dr = 0.0, di = 0.0;
+        for (int a = t; a < m; a += G) {
+            const long I = r0 + a;
+            double sumr = 0.0, sumi = 0.0;
+            const long rowI = tri(I), rowIs = trs(I);
+            // one pass over the row of the full Hermitian matrix: left of the diagonal read the own packed
+            // row, right of it the conjugate of column I (same trip count for every lane of the group)
+            long triJ = tri(r0), trsJ = trs(r0);
+            for (int b = 0; b < m; ++b) {
+                const long J = r0 + b;
+                const bool left = b < a;
+                const long ir = left ? rowI + J : triJ + I;
+                const long ii = (b == a) ? 0 : (left ? rowIs + J : trsJ + I);
+                const double arr = Ar[ir];
+                double aii = Ai[ii];
+                aii = (b == a) ? 0.0 : (left ? aii : -aii);
+                const double vr = Vr[b], vi = Vi[b];
+                sumr += arr * vr - aii * vi;
+                sumi += arr * vi + aii * vr;
+                triJ += J + 1;
+                trsJ += J;
+            }
+            const double pr = tr * sumr - ti * sumi;
+            const double pi = tr * sumi + ti * sumr;
+            Pr[a] = pr;
+            Pi[a] = pi;
+            dr += pr * Vr[a] + pi * Vi[a];
+            di += pr * Vi[a] - pi * Vr[a];
+        }
+        group_sum2<G>(dr, di, red, group, t, parity);
+        const double alr = -0.5 * (tr * dr - ti * di);
+        const double ali = -0.5 * (tr * di + ti * dr);
+        for (int a = t; a < m; a += G) {
+            const double vr = Vr[a], vi = Vi[a];
+            Pr[a] += alr * vr - ali * vi;
+            Pi[a] += alr * vi + ali * vr;
+        }
+        group_sync<G>(group);
+        // --- A22 -= v w^H + w v^H (lower triangle) ---
+        for (int a = t; a < m; a += G) {
+            const long I = r0 + a;
+            const double var = Vr[a], vai = Vi[a], war = Pr[a], wai = Pi[a];
+            double* rowr = Ar + tri(I) + r0;
+            double* rowi = Ai + trs(I) + r0;
+            for (int b = 0; b < a; ++b) {
+                const double vbr = Vr[b], vbi = Vi[b], wbr = Pr[b], wbi = Pi[b];
+                rowr[b] -= var * wbr + vai * wbi + war * vbr + wai * vbi;
+                rowi[b] -= vai * wbr - var * wbi + wai * vbr - war * vbi;
+            }
+            rowr[a] -= 2.0 * (var * war + vai * wai);
+        }
+        group_sync<G>(group);
+    }
+    if (t == 0) {
+        ds[N - 1] = Ar[tri(N - 1) + (N - 1)];
+        es[N - 1] = 0.0;
+    }
+    group_sync<G>(group);
+    if (valid) {
+        for (int i = t; i < N; i += G) {
+            D[kidx * N + i] = ds[i];
+            E[kidx * N + i] = es[i];
+        }
+    }
+}
+
+constexpr size_t kSmemLimit = 220 * 1024;
+
+template <int G>
+cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    constexpr int NW = G > 32 ? G / 32 : 1;
+    const long NN = (long)n * n;
+    const size_t per_mat = (size_t)(NN + 6L * n + 4 * NW + 2) * 8;
+    int mpb = (int)(kSmemLimit / per_mat);
+    if (mpb > TPB / G) mpb = TPB / G;
+    const bool in_smem = mpb >= 1;
+    if (!in_smem) mpb = 1;
+    const size_t smem = in_smem ? per_mat * mpb : (size_t)(6L * n + 4 * NW + 2) * 8;
+    cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const long blocks = (nk + mpb - 1) / mpb;
+    if (blocks <= 0) return cudaSuccess;
+    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_kernel<G><<<(unsigned)blocks, G * mpb, smem, st>>>(Hp, n, nk, D, E, in_smem ? 1 : 0);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    if (n <= 10) return launch_g<8>(n, Hp, nk, D, E, st);
+    if (n <= 20) return launch_g<16>(n, Hp, nk, D, E, st);
+    if (n <= 48) return launch_g<32>(n, Hp, nk, D, E, st);
+    if (n <= 96) return launch_g<64>(n, Hp, nk, D, E, st);
+    if (n <= 128) return launch_g<128>(n, Hp, nk, D, E, st);
+    return launch_g<256>(n, Hp, nk, D, E, st);
+}
+
+}  // namespace tbk

@@ -1,0 +1,165 @@
+// hk_small.cu -- fused thread-per-k-point path for few-band models (N <= 8).
+//
+// One thread owns one k-point end to end: k (D doubles) in, N eigenvalues (or the packed H(k)) out.
+// Nothing else touches HBM: the Hermitian-split weights W [2 n_R][N^2] and the R vectors sit in shared
+// memory, the N^2 accumulators in registers, phases come from sincospi(2 k.R) on chip.
+// Replaces Model.hamilton's Fourier loop + H += H^dagger (reference src/tbmodels/_tb_model.py:1111-1123)
+// and the per-k scipy eigvalsh loop of Model.eigenval (:1147-1150) for small N.
+//   N = 1, 2 : closed-form eigenvalues.
+//   N = 3..8 : per-thread Householder tridiagonalisation + implicit QL on a thread-strided shared-memory
+//              scratch (tbk_math.cuh), i.e. every lane works on its own matrix -- no idle lanes, no shuffles.
+#include "tbk_kernels.h"
+#include "tbk_math.cuh"
+
+namespace tbk {
+
+namespace {
+
+constexpr int TPB = 128;
+
+template <int N>
+constexpr int scratch_doubles() {
+    return (N > 2) ? (N * N + 6 * N) : 0;  // matrix + v/w work (4N) + d, e (2N)
+}
+
+template <int N, int D>  // D = 0: run-time dimension (<= kMaxDim)
+__global__ void __launch_bounds__(TPB)
+hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const double* __restrict__ W,
+                int dim_rt, int nR, double* __restrict__ Hp, double* __restrict__ eig) {
+    constexpr int NN = N * N;
+    const int dim = D ? D : dim_rt;
+    extern __shared__ __align__(16) double sm[];
+    double* Ws = sm;                             // [2 nR][NN]
+    double* Rs = Ws + (size_t)2 * nR * NN;       // [nR][dim]
+    double* scratch = Rs + (((size_t)nR * dim + 1) & ~(size_t)1);
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * nR * NN; i += TPB) Ws[i] = W[i];
+    for (int i = tid; i < nR * dim; i += TPB) Rs[i] = Rd[i];
+    __syncthreads();
+
+    for (long kk = (long)blockIdx.x * TPB + tid; kk < nk; kk += (long)gridDim.x * TPB) {
+        double kv[D ? D : kMaxDim];
+        if (D == 2) {
+            const double2 v = *reinterpret_cast<const double2*>(kpts + kk * 2);
+            kv[0] = v.x;
+            kv[D > 1 ? 1 : 0] = v.y;
+        } else {
+#pragma unroll
+            for (int d = 0; d < (D ? D : kMaxDim); ++d) kv[d] = (d < dim) ? kpts[kk * dim + d] : 0.0;
+        }
+
+        double acc[NN];
+#pragma unroll
+        for (int e = 0; e < NN; ++e) acc[e] = 0.0;
+
+        for (int r = 0; r < nR; ++r) {
+            double x = 0.0;
+#pragma unroll
+            for (int d = 0; d < (D ? D : kMaxDim); ++d)
+                if (d < dim) x = fma(kv[d], Rs[r * dim + d], x);
+            double sn, cs;
+            sincospi(2.0 * x, &sn, &cs);
+            const double* w0 = Ws + (size_t)(2 * r) * NN;
+            const double* w1 = w0 + NN;
+            if (NN % 2 == 0) {
+#pragma unroll
+                for (int e = 0; e < NN; e += 2) {
+                    const double2 a = *reinterpret_cast<const double2*>(w0 + e);
+                    const double2 b = *reinterpret_cast<const double2*>(w1 + e);
+                    acc[e] = fma(cs, a.x, fma(sn, b.x, acc[e]));
+                    acc[e + 1] = fma(cs, a.y, fma(sn, b.y, acc[e + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < NN; ++e) acc[e] = fma(cs, w0[e], fma(sn, w1[e], acc[e]));
+            }
+        }
+
+        if (Hp != nullptr) {
+            double* o = Hp + kk * NN;
+            if (NN % 2 == 0) {
+#pragma unroll
+                for (int e = 0; e < NN; e += 2) *reinterpret_cast<double2*>(o + e) = make_double2(acc[e], acc[e + 1]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < NN; ++e) o[e] = acc[e];
+            }
+        }
+        if (eig != nullptr) {
+            if (N == 1) {
+                eig[kk] = acc[0];
+            } else if (N == 2) {
+                double lo, hi;
+                eig2_closed(acc[0], acc[2], acc[1], acc[3], lo, hi);
+                *reinterpret_cast<double2*>(eig + kk * 2) = make_double2(lo, hi);
+            } else {
+                double* A = scratch + tid;  // element q at A[q * TPB]
+#pragma unroll
+                for (int e = 0; e < NN; ++e) A[(long)e * TPB] = acc[e];
+                double* wv = A + (long)NN * TPB;
+                double* dd = wv + 4L * N * TPB;
+                double* ee = dd + (long)N * TPB;
+                hetrd_serial(N, A, TPB, dd, ee, TPB, wv);
+                tridiag_ql(N, dd, ee, TPB);
+                double* o = eig + kk * N;
+#pragma unroll
+                for (int i = 0; i < N; ++i) o[i] = dd[(long)i * TPB];
+            }
+        }
+    }
+}
+
+template <int N, int D>
+cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    const size_t smem = hk_small_smem_bytes(N, md.dim, md.nR, TPB);
+    cudaError_t err =
+        cudaFuncSetAttribute(hk_small_kernel<N, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long blocks = (nk + TPB - 1) / TPB;
+    // persistent-ish: the tables are loaded once per CTA, so cap the grid at a few waves
+    const long cap = (long)sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks <= 0) return cudaSuccess;
+    hk_small_kernel<N, D><<<(unsigned)blocks, TPB, smem, st>>>(k, nk, md.Rd, md.W, md.dim, md.nR, Hp, eig);
+    return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_n(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    switch (md.dim) {
+        case 1: return launch_nd<N, 1>(md, k, nk, Hp, eig, st);
+        case 2: return launch_nd<N, 2>(md, k, nk, Hp, eig, st);
+        case 3: return launch_nd<N, 3>(md, k, nk, Hp, eig, st);
+        default: return launch_nd<N, 0>(md, k, nk, Hp, eig, st);
+    }
+}
+
+}  // namespace
+
+size_t hk_small_smem_bytes(int n, int dim, int nR, int threads) {
+    if (threads <= 0) threads = TPB;
+    const size_t nn = (size_t)n * n;
+    size_t doubles = 2 * (size_t)nR * nn + (((size_t)nR * dim + 1) & ~(size_t)1);
+    if (n > 2) doubles += (nn + 6 * (size_t)n) * threads;
+    return doubles * 8;
+}
+
+cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    switch (md.n) {
+        case 1: return launch_n<1>(md, k, nk, Hp, eig, st);
+        case 2: return launch_n<2>(md, k, nk, Hp, eig, st);
+        case 3: return launch_n<3>(md, k, nk, Hp, eig, st);
+        case 4: return launch_n<4>(md, k, nk, Hp, eig, st);
+        case 5: return launch_n<5>(md, k, nk, Hp, eig, st);
+        case 6: return launch_n<6>(md, k, nk, Hp, eig, st);
+        case 7: return launch_n<7>(md, k, nk, Hp, eig, st);
+        case 8: return launch_n<8>(md, k, nk, Hp, eig, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace tbk

@@ -1,0 +1,479 @@
+// tbk_api.cu -- the C ABI (include/tbk.h): model packing, chunked launch sequences, host pipelines.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/tbk.h"
+#include "tbk_kernels.h"
+#include "tbk_math.cuh"
+
+using namespace tbk;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(TBK_E_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+void pack_weights_host(int n, int nR, const double* hop, double* W) {
+    const long NN = (long)n * n;
+    const long nre = tri(n);
+    for (int r = 0; r < nR; ++r) {
+        const double* T = hop + (size_t)r * NN * 2;
+        double* w0 = W + (size_t)(2 * r) * NN;
+        double* w1 = w0 + NN;
+        for (int i = 0; i < n; ++i) {
+            for (int j = 0; j <= i; ++j) {
+                const double tr_ij = T[((long)i * n + j) * 2], ti_ij = T[((long)i * n + j) * 2 + 1];
+                const double tr_ji = T[((long)j * n + i) * 2], ti_ji = T[((long)j * n + i) * 2 + 1];
+                // A = T + T^H ; B = i (T - T^H)
+                w0[tri(i) + j] = tr_ij + tr_ji;
+                w1[tri(i) + j] = -(ti_ij + ti_ji);
+                if (j < i) {
+                    w0[nre + trs(i) + j] = ti_ij - ti_ji;
+                    w1[nre + trs(i) + j] = tr_ij - tr_ji;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct tbk_model {
+    int device = 0;
+    ModelDev md;
+    double* dRd = nullptr;
+    double* dW = nullptr;
+    double* dWt = nullptr;
+    double* dPos = nullptr;
+    int* dFail = nullptr;
+    // scratch for the device-pointer entry points
+    double* wsH = nullptr;  // [chunk][n*n] packed H(k)
+    double* wsE = nullptr;  // [chunk][n]   sub-diagonals
+    long chunk = 0;
+    size_t ws_bytes = 0;
+    size_t model_bytes = 0;
+    // host pipeline
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    double* hk[2] = {nullptr, nullptr};
+    double* ho[2] = {nullptr, nullptr};
+    size_t hk_bytes = 0, ho_bytes = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+long pick_chunk(const tbk_model* m) {
+    size_t budget_mb = 1024;
+    if (const char* s = getenv("TBK_WORKSPACE_MB")) {
+        const long v = atol(s);
+        if (v > 0) budget_mb = (size_t)v;
+    }
+    const size_t per_k = ((size_t)m->md.n * m->md.n + m->md.n) * 8;
+    long chunk = (long)((budget_mb << 20) / per_k);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (1L << 22)) chunk = 1L << 22;
+    if (chunk >= 1024) chunk &= ~127L;  // whole GEMM row tiles
+    return chunk;
+}
+
+int ensure_workspace(tbk_model* m, long nk) {
+    const long want = std::min(nk, pick_chunk(m));
+    if (want <= m->chunk) return TBK_OK;
+    if (m->wsH) cudaFree(m->wsH);
+    if (m->wsE) cudaFree(m->wsE);
+    m->wsH = m->wsE = nullptr;
+    m->chunk = 0;
+    m->ws_bytes = 0;
+    const size_t hb = (size_t)want * m->md.n * m->md.n * 8;
+    const size_t eb = (size_t)want * m->md.n * 8;
+    CU(cudaMalloc(&m->wsH, hb));
+    CU(cudaMalloc(&m->wsE, eb));
+    m->chunk = want;
+    m->ws_bytes = hb + eb;
+    return TBK_OK;
+}
+
+int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream_t st) {
+    const ModelDev& md = m->md;
+    if (nk <= 0) return TBK_OK;
+    if (md.small_ok) {
+        CU(launch_hk_small(md, k, nk, nullptr, out, st));
+        m->launches += 1;
+        return TBK_OK;
+    }
+    if (int rc = ensure_workspace(m, nk)) return rc;
+    for (long c0 = 0; c0 < nk; c0 += m->chunk) {
+        const long cn = std::min(m->chunk, nk - c0);
+        double* D = out + c0 * md.n;
+        CU(launch_hk_gemm(md, k + c0 * md.dim, cn, m->wsH, st));
+        CU(launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
+        CU(launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
+        m->launches += 3;
+    }
+    return TBK_OK;
+}
+
+int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double* out, cudaStream_t st) {
+    const ModelDev& md = m->md;
+    if (nk <= 0) return TBK_OK;
+    if (int rc = ensure_workspace(m, nk)) return rc;
+    const long NN = (long)md.n * md.n;
+    for (long c0 = 0; c0 < nk; c0 += m->chunk) {
+        const long cn = std::min(m->chunk, nk - c0);
+        const double* kc = k + c0 * md.dim;
+        if (md.small_ok) CU(launch_hk_small(md, kc, cn, m->wsH, nullptr, st));
+        else CU(launch_hk_gemm(md, kc, cn, m->wsH, st));
+        CU(launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
+        m->launches += 2;
+    }
+    return TBK_OK;
+}
+
+int ensure_pipeline(tbk_model* m, size_t kbytes, size_t obytes) {
+    if (!m->s_in) {
+        CU(cudaStreamCreateWithFlags(&m->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&m->s_comp, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&m->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventCreateWithFlags(&m->ev_in[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&m->ev_comp[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&m->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    if (kbytes > m->hk_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (m->hk[b]) cudaFree(m->hk[b]);
+            m->hk[b] = nullptr;
+        }
+        m->hk_bytes = 0;
+        for (int b = 0; b < 2; ++b) CU(cudaMalloc(&m->hk[b], kbytes));
+        m->hk_bytes = kbytes;
+    }
+    if (obytes > m->ho_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (m->ho[b]) cudaFree(m->ho[b]);
+            m->ho[b] = nullptr;
+        }
+        m->ho_bytes = 0;
+        for (int b = 0; b < 2; ++b) CU(cudaMalloc(&m->ho[b], obytes));
+        m->ho_bytes = obytes;
+    }
+    return TBK_OK;
+}
+
+// Chunked, double-buffered host pipeline shared by the two _host entry points.
+// out_per_k: doubles written per k-point (n for eigenval, 2 n^2 for hamilton).
+int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int convention /*0 = eigenval*/) {
+    const ModelDev& md = m->md;
+    if (nk <= 0) return TBK_OK;
+    const size_t out_per_k = convention ? (size_t)2 * md.n * md.n : (size_t)md.n;
+    const size_t bytes_per_k = ((size_t)md.dim + out_per_k) * 8;
+    size_t target_mb = 64;
+    if (const char* s = getenv("TBK_HOST_CHUNK_MB")) {
+        const long v = atol(s);
+        if (v > 0) target_mb = (size_t)v;
+    }
+    long hchunk = (long)((target_mb << 20) / bytes_per_k);
+    if (hchunk < 1) hchunk = 1;
+    if (hchunk >= 1024) hchunk &= ~127L;
+    if (hchunk > nk) hchunk = nk;
+    if (int rc = ensure_pipeline(m, (size_t)hchunk * md.dim * 8, (size_t)hchunk * out_per_k * 8)) return rc;
+
+    int it = 0;
+    for (long c0 = 0; c0 < nk; c0 += hchunk, ++it) {
+        const long cn = std::min(hchunk, nk - c0);
+        const int b = it & 1;
+        if (it >= 2) {
+            CU(cudaStreamWaitEvent(m->s_in, m->ev_comp[b], 0));   // kernels of chunk it-2 consumed hk[b]
+            CU(cudaStreamWaitEvent(m->s_comp, m->ev_out[b], 0));  // D2H of chunk it-2 drained ho[b]
+        }
+        CU(cudaMemcpyAsync(m->hk[b], k_host + c0 * md.dim, (size_t)cn * md.dim * 8, cudaMemcpyHostToDevice, m->s_in));
+        CU(cudaEventRecord(m->ev_in[b], m->s_in));
+        CU(cudaStreamWaitEvent(m->s_comp, m->ev_in[b], 0));
+        int rc = convention ? run_hamilton(m, m->hk[b], cn, convention, m->ho[b], m->s_comp)
+                            : run_eigenval(m, m->hk[b], cn, m->ho[b], m->s_comp);
+        if (rc) return rc;
+        CU(cudaEventRecord(m->ev_comp[b], m->s_comp));
+        CU(cudaStreamWaitEvent(m->s_out, m->ev_comp[b], 0));
+        CU(cudaMemcpyAsync(out_host + (size_t)c0 * out_per_k, m->ho[b], (size_t)cn * out_per_k * 8,
+                           cudaMemcpyDeviceToHost, m->s_out));
+        CU(cudaEventRecord(m->ev_out[b], m->s_out));
+    }
+    CU(cudaStreamSynchronize(m->s_in));
+    CU(cudaStreamSynchronize(m->s_comp));
+    CU(cudaStreamSynchronize(m->s_out));
+    return TBK_OK;
+}
+
+int check_fail_flag(tbk_model* m) {
+    int h = 0;
+    CU(cudaMemcpy(&h, m->dFail, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h != 0) {
+        cudaMemset(m->dFail, 0, sizeof(int));
+        return fail(TBK_E_NOCONV, "tridiagonal QL did not converge for %d eigenvalue(s)", h);
+    }
+    return TBK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tbk_version(void) { return 100; }
+
+const char* tbk_last_error(void) { return g_err.c_str(); }
+
+int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double* hop, const double* pos, int device,
+                     tbk_model** out) {
+    if (!out) return fail(TBK_E_INVALID, "tbk_model_create: out is null");
+    *out = nullptr;
+    if (n_orb < 1) return fail(TBK_E_INVALID, "tbk_model_create: n_orb = %d must be >= 1", n_orb);
+    if (dim < 1) return fail(TBK_E_INVALID, "tbk_model_create: dim = %d must be >= 1", dim);
+    if (dim > kMaxDim) return fail(TBK_E_UNSUPPORTED, "tbk_model_create: dim = %d > %d is not supported", dim, kMaxDim);
+    if (n_R < 0 || (n_R > 0 && (!R || !hop))) return fail(TBK_E_INVALID, "tbk_model_create: bad hopping arrays");
+    if (!pos) return fail(TBK_E_INVALID, "tbk_model_create: pos is null");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(TBK_E_CUDA, "tbk_model_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TBK_E_INVALID, "tbk_model_create: device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "tbk_model_create: cudaSetDevice(%d) failed", device);
+
+    tbk_model* m = new (std::nothrow) tbk_model();
+    if (!m) return fail(TBK_E_INVALID, "out of host memory");
+    m->device = device;
+    ModelDev& md = m->md;
+    md.n = n_orb;
+    md.dim = dim;
+    md.nR = n_R;
+    md.nRpad = (n_R + 7) & ~7;
+    const long NN = (long)n_orb * n_orb;
+
+    auto bail = [&](int rc) {
+        tbk_model_destroy(m);
+        return rc;
+    };
+#define CUB(call)                                                                                             \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return bail(fail(TBK_E_CUDA, "%s -> %s", #call, cudaGetErrorString(e_)));      \
+    } while (0)
+
+    // R as doubles, padded with zero vectors
+    std::vector<double> Rd((size_t)std::max(md.nRpad, 1) * dim, 0.0);
+    for (int r = 0; r < n_R; ++r)
+        for (int d = 0; d < dim; ++d) Rd[(size_t)r * dim + d] = (double)R[(size_t)r * dim + d];
+    CUB(cudaMalloc(&m->dRd, Rd.size() * 8));
+    CUB(cudaMemcpy(m->dRd, Rd.data(), Rd.size() * 8, cudaMemcpyHostToDevice));
+    md.Rd = m->dRd;
+    m->model_bytes += Rd.size() * 8;
+
+    CUB(cudaMalloc(&m->dPos, (size_t)n_orb * dim * 8));
+    CUB(cudaMemcpy(m->dPos, pos, (size_t)n_orb * dim * 8, cudaMemcpyHostToDevice));
+    md.pos = m->dPos;
+    m->model_bytes += (size_t)n_orb * dim * 8;
+
+    CUB(cudaMalloc(&m->dFail, sizeof(int)));
+    CUB(cudaMemset(m->dFail, 0, sizeof(int)));
+
+    std::vector<double> W((size_t)std::max(2 * n_R, 1) * NN, 0.0);
+    pack_weights_host(n_orb, n_R, hop, W.data());
+
+    md.small_ok = (n_orb <= kSmallMaxN && hk_small_smem_bytes(n_orb, dim, n_R, 0) <= 220 * 1024) ? 1 : 0;
+    if (getenv("TBK_FORCE_GEMM")) md.small_ok = 0;  // test hook: exercise the general path on small models
+    if (md.small_ok) {
+        CUB(cudaMalloc(&m->dW, W.size() * 8));
+        CUB(cudaMemcpy(m->dW, W.data(), W.size() * 8, cudaMemcpyHostToDevice));
+        md.W = m->dW;
+        m->model_bytes += W.size() * 8;
+    } else {
+        // choose the column-tile width that wastes the fewest padded columns (ties -> wider)
+        const int cands[3] = {4, 8, 9};
+        long best_cols = -1;
+        for (int c : cands) {
+            const long bn = 16L * c;
+            const long cols = ((NN + bn - 1) / bn) * bn;
+            if (best_cols < 0 || cols <= best_cols) {
+                best_cols = cols;
+                md.na = c;
+            }
+        }
+        const int bn = 16 * md.na, sb = bn + 4;
+        md.n_tiles = (int)((NN + bn - 1) / bn);
+        md.kchunks = md.nRpad / 8;
+        const size_t stage = (size_t)kGemmKC * sb;
+        std::vector<double> Wt((size_t)std::max(md.n_tiles * md.kchunks, 1) * stage, 0.0);
+        for (int nt = 0; nt < md.n_tiles; ++nt)
+            for (int c = 0; c < md.kchunks; ++c) {
+                double* blk = Wt.data() + ((size_t)nt * md.kchunks + c) * stage;
+                for (int kk = 0; kk < kGemmKC; ++kk) {
+                    const long q = (long)c * kGemmKC + kk;
+                    if (q >= 2L * n_R) continue;
+                    const double* src = W.data() + (size_t)q * NN;
+                    for (int col = 0; col < bn; ++col) {
+                        const long e = (long)nt * bn + col;
+                        if (e < NN) blk[(size_t)kk * sb + col] = src[e];
+                    }
+                }
+            }
+        CUB(cudaMalloc(&m->dWt, Wt.size() * 8));
+        CUB(cudaMemcpy(m->dWt, Wt.data(), Wt.size() * 8, cudaMemcpyHostToDevice));
+        md.Wt = m->dWt;
+        m->model_bytes += Wt.size() * 8;
+    }
+#undef CUB
+    *out = m;
+    return TBK_OK;
+}
+
+int tbk_model_destroy(tbk_model* m) {
+    if (!m) return TBK_OK;
+    DeviceGuard guard(m->device);
+    cudaDeviceSynchronize();
+    cudaFree(m->dRd);
+    cudaFree(m->dW);
+    cudaFree(m->dWt);
+    cudaFree(m->dPos);
+    cudaFree(m->dFail);
+    cudaFree(m->wsH);
+    cudaFree(m->wsE);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(m->hk[b]);
+        cudaFree(m->ho[b]);
+        if (m->ev_in[b]) cudaEventDestroy(m->ev_in[b]);
+        if (m->ev_comp[b]) cudaEventDestroy(m->ev_comp[b]);
+        if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
+    }
+    if (m->s_in) cudaStreamDestroy(m->s_in);
+    if (m->s_comp) cudaStreamDestroy(m->s_comp);
+    if (m->s_out) cudaStreamDestroy(m->s_out);
+    delete m;
+    return TBK_OK;
+}
+
+int tbk_model_info(const tbk_model* m, int* n_orb, int* dim, int* n_R, int* path) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_model_info: null handle");
+    if (n_orb) *n_orb = m->md.n;
+    if (dim) *dim = m->md.dim;
+    if (n_R) *n_R = m->md.nR;
+    if (path) *path = m->md.small_ok ? 0 : 1;
+    return TBK_OK;
+}
+
+int tbk_hamilton(tbk_model* m, const double* k_dev, int64_t n_k, int convention, double* out_dev, void* stream) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_hamilton: null handle");
+    if (convention != 1 && convention != 2)
+        return fail(TBK_E_INVALID, "Invalid value '%d' for 'convention': must be either '1' or '2'", convention);
+    if (n_k < 0 || (n_k > 0 && (!k_dev || !out_dev))) return fail(TBK_E_INVALID, "tbk_hamilton: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    return run_hamilton(m, k_dev, (long)n_k, convention, out_dev, (cudaStream_t)stream);
+}
+
+int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* stream) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigenval: null handle");
+    if (n_k < 0 || (n_k > 0 && (!k_dev || !out_dev))) return fail(TBK_E_INVALID, "tbk_eigenval: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    return run_eigenval(m, k_dev, (long)n_k, out_dev, (cudaStream_t)stream);
+}
+
+int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_hamilton_host: null handle");
+    if (convention != 1 && convention != 2)
+        return fail(TBK_E_INVALID, "Invalid value '%d' for 'convention': must be either '1' or '2'", convention);
+    if (n_k < 0 || (n_k > 0 && (!k_host || !out_host))) return fail(TBK_E_INVALID, "tbk_hamilton_host: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    return run_host(m, k_host, (long)n_k, out_host, convention);
+}
+
+int tbk_eigenval_host(tbk_model* m, const double* k_host, int64_t n_k, double* out_host) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigenval_host: null handle");
+    if (n_k < 0 || (n_k > 0 && (!k_host || !out_host))) return fail(TBK_E_INVALID, "tbk_eigenval_host: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = run_host(m, k_host, (long)n_k, out_host, 0)) return rc;
+    return check_fail_flag(m);
+}
+
+int tbk_model_check(tbk_model* m) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_model_check: null handle");
+    DeviceGuard guard(m->device);
+    CU(cudaDeviceSynchronize());
+    return check_fail_flag(m);
+}
+
+int64_t tbk_launch_count(const tbk_model* m) { return m ? m->launches : 0; }
+
+int64_t tbk_workspace_bytes(const tbk_model* m) {
+    return m ? (int64_t)(m->ws_bytes + 2 * m->hk_bytes + 2 * m->ho_bytes + m->model_bytes) : 0;
+}
+
+int tbk_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(TBK_E_INVALID, "tbk_host_alloc: null");
+    CU(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return TBK_OK;
+}
+
+int tbk_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return TBK_OK;
+}
+
+double tbk_measure_fp64_peak(int kind, int iters) { return measure_fp64_peak(kind, iters); }
+
+int tbk_host_tridiag_ql(int n, double* d, double* e) { return tridiag_ql(n, d, e, 1); }
+
+int tbk_host_hetrd(int n, double* hp, double* d, double* e) {
+    if (n < 1) return fail(TBK_E_INVALID, "n < 1");
+    std::vector<double> wv((size_t)4 * n);
+    hetrd_serial(n, hp, 1, d, e, 1, wv.data());
+    e[n - 1] = 0.0;
+    return TBK_OK;
+}
+
+int tbk_host_pack_weights(int n_orb, int n_R, const double* hop, double* W) {
+    if (n_orb < 1 || n_R < 0) return fail(TBK_E_INVALID, "bad sizes");
+    pack_weights_host(n_orb, n_R, hop, W);
+    return TBK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// tbk_kernels.h -- internal launcher interface between the C-ABI layer (tbk_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tbk {
+
+constexpr int kMaxDim = 8;        // largest lattice dimension supported on the device
+constexpr int kSmallMaxN = 8;     // thread-per-k fused kernel handles N <= 8 (if its tables fit in smem)
+constexpr int kGemmBM = 128;      // k-points per CTA tile of the H(k) GEMM
+constexpr int kGemmKC = 16;       // K (= 2 * R-vectors) per pipeline stage
+constexpr int kGemmStages = 4;
+
+// Device-resident packed model (see DESIGN.md "Data layout in HBM").
+struct ModelDev {
+    int n = 0;        // orbitals
+    int dim = 0;      // lattice dimension
+    int nR = 0;       // stored (half-set) R vectors that are non-zero matrices
+    int nRpad = 0;    // nR rounded up to a multiple of 8 (padding rows: R = 0, zero weights)
+    const double* Rd = nullptr;   // [nRpad][dim]   R vectors as doubles
+    const double* W = nullptr;    // [2*nR][n*n]    Hermitian-split weights, row 2r = hp(T_r + T_r^H), row 2r+1 = hp(i(T_r - T_r^H))
+    const double* Wt = nullptr;   // tiled copy of W for the GEMM: [n_tiles][kchunks][kGemmKC][bn + 4]
+    const double* pos = nullptr;  // [n][dim]
+    int na = 0;        // GEMM: n-atoms (8 columns) per warp -> bn = 16 * na
+    int n_tiles = 0;   // GEMM: column tiles
+    int kchunks = 0;   // GEMM: nRpad / 8
+    int small_ok = 0;  // fused thread-per-k kernel usable
+};
+
+// H(k) build on the FP64 tensor cores: Hp[k][0..n*n) (packed Hermitian, see tbk_math.cuh).
+cudaError_t launch_hk_gemm(const ModelDev& md, const double* k, long nk, double* Hp, cudaStream_t st);
+// Fused thread-per-k-point path for N <= 8: writes packed H (if Hp) and/or ascending eigenvalues (if eig).
+cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st);
+size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);
+// packed H -> full complex128 [nk][n][n]; convention 1 applies the orbital-position phases.
+cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention,
+                          double* out, cudaStream_t st);
+// Batched Hermitian -> tridiagonal reduction (Hp is destroyed). D, E: [nk][n].
+cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
+// Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
+cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st);
+
+// FP64 peak micro-benchmarks (bench.py roofline denominators). Return achieved TFLOP/s, or < 0 on error.
+double measure_fp64_peak(int kind /*0 = DMMA, 1 = DFMA*/, int iters);
+
+}  // namespace tbk

@@ -1,0 +1,212 @@
+// tbk_math.cuh -- scalar building blocks shared by the device kernels and the host-side unit tests.
+//
+// Everything here is __host__ __device__ so the exact code the kernels run can also be exercised on
+// the CPU (tests/test_native_host.py drives it through the tbk_host_* debug entry points).
+//
+// Packed Hermitian layout ("hp"), N*N doubles per matrix, used for H(k) between the build and the
+// eigensolver kernels:
+//   real plane : element (i,j), j <= i  at  i*(i+1)/2 + j                      (N(N+1)/2 doubles)
+//   imag plane : element (i,j), j <  i  at  N(N+1)/2 + i*(i-1)/2 + j            (N(N-1)/2 doubles)
+// Only the lower triangle is stored -- scipy.linalg.eigvalsh reads the lower triangle only
+// (reference src/tbmodels/_tb_model.py:1149 -> LAPACK zheevr, UPLO='L').
+#pragma once
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define TBK_HD __host__ __device__ __forceinline__
+#else
+#define TBK_HD inline
+#endif
+
+namespace tbk {
+
+TBK_HD long tri(long i) { return i * (i + 1) / 2; }  // start of row i in the real plane
+TBK_HD long trs(long i) { return i * (i - 1) / 2; }  // start of row i in the imag plane (strict lower)
+
+// Elementary reflector (same contract as LAPACK zlarfg, restated):
+// given alpha = (ar, ai) and xnorm2 = sum |x_i|^2 over the remaining entries, produce a real beta, a
+// complex tau and a complex scale = 1/(alpha - beta) so that with v = [1; scale * x]
+//   (I - tau v v^H)^H [alpha; x] = [beta; 0].
+// tau == 0 means "no reflection" (x == 0 and alpha real).
+TBK_HD void householder_gen(double ar, double ai, double xnorm2, double& beta, double& tr, double& ti,
+                            double& sr, double& si) {
+    if (xnorm2 == 0.0 && ai == 0.0) {
+        beta = ar;
+        tr = ti = 0.0;
+        sr = si = 0.0;
+        return;
+    }
+    const double nrm = sqrt(ar * ar + ai * ai + xnorm2);
+    beta = (ar >= 0.0) ? -nrm : nrm;
+    const double binv = 1.0 / beta;
+    tr = (beta - ar) * binv;
+    ti = -ai * binv;
+    const double dr = ar - beta;  // same-sign sum: no cancellation
+    const double di = ai;
+    const double den = 1.0 / (dr * dr + di * di);
+    sr = dr * den;
+    si = -di * den;
+}
+
+// Serial Hermitian -> real symmetric tridiagonal reduction on one packed matrix (unblocked Householder,
+// lower storage).  Element e of the matrix lives at A[e * s]; d/e entries at d[i * sde], e[i * sde];
+// wv is scratch for 4*N doubles (element q at wv[q * s]).  Used by the thread-per-matrix small-N kernel
+// and by the host tests; the cooperative kernel in eig_tridiag.cu performs the same steps with a
+// thread group per matrix.
+TBK_HD void hetrd_serial(int N, double* A, long s, double* d, double* e, long sde, double* wv) {
+    const long NRE = tri(N);
+    double* Ar = A;
+    double* Ai = A + NRE * s;
+    double* Vr = wv;
+    double* Vi = wv + (long)N * s;
+    double* Pr = wv + 2L * N * s;
+    double* Pi = wv + 3L * N * s;
+    for (int j = 0; j < N - 1; ++j) {
+        d[j * sde] = Ar[(tri(j) + j) * s];
+        const int m = N - 1 - j;
+        const int r0 = j + 1;
+        const double ar = Ar[(tri(r0) + j) * s];
+        const double ai = Ai[(trs(r0) + j) * s];
+        double xn = 0.0;
+        for (int a = 1; a < m; ++a) {
+            const int I = r0 + a;
+            const double xr = Ar[(tri(I) + j) * s], xi = Ai[(trs(I) + j) * s];
+            xn += xr * xr + xi * xi;
+        }
+        double beta, tr, ti, sr, si;
+        householder_gen(ar, ai, xn, beta, tr, ti, sr, si);
+        e[j * sde] = beta;
+        if (tr == 0.0 && ti == 0.0) continue;
+        Vr[0] = 1.0;
+        Vi[0] = 0.0;
+        for (int a = 1; a < m; ++a) {
+            const int I = r0 + a;
+            const double xr = Ar[(tri(I) + j) * s], xi = Ai[(trs(I) + j) * s];
+            Vr[a * s] = xr * sr - xi * si;
+            Vi[a * s] = xr * si + xi * sr;
+        }
+        // p = tau * A22 * v ; dot = p^H v
+        double dr = 0.0, di = 0.0;
+        for (int a = 0; a < m; ++a) {
+            const int I = r0 + a;
+            double sumr = 0.0, sumi = 0.0;
+            for (int b = 0; b < m; ++b) {
+                const int J = r0 + b;
+                const int lo = I < J ? I : J, hi = I < J ? J : I;
+                const double arr = Ar[(tri(hi) + lo) * s];
+                double aii = (hi != lo) ? Ai[(trs(hi) + lo) * s] : 0.0;
+                if (J > I) aii = -aii;
+                const double vr = Vr[b * s], vi = Vi[b * s];
+                sumr += arr * vr - aii * vi;
+                sumi += arr * vi + aii * vr;
+            }
+            const double pr = tr * sumr - ti * sumi;
+            const double pi = tr * sumi + ti * sumr;
+            Pr[a * s] = pr;
+            Pi[a * s] = pi;
+            dr += pr * Vr[a * s] + pi * Vi[a * s];
+            di += pr * Vi[a * s] - pi * Vr[a * s];
+        }
+        const double alr = -0.5 * (tr * dr - ti * di);
+        const double ali = -0.5 * (tr * di + ti * dr);
+        for (int a = 0; a < m; ++a) {
+            const double vr = Vr[a * s], vi = Vi[a * s];
+            Pr[a * s] += alr * vr - ali * vi;
+            Pi[a * s] += alr * vi + ali * vr;
+        }
+        // A22 -= v w^H + w v^H  (lower triangle only)
+        for (int a = 0; a < m; ++a) {
+            const int I = r0 + a;
+            const double var = Vr[a * s], vai = Vi[a * s], war = Pr[a * s], wai = Pi[a * s];
+            for (int b = 0; b < a; ++b) {
+                const int J = r0 + b;
+                const double vbr = Vr[b * s], vbi = Vi[b * s], wbr = Pr[b * s], wbi = Pi[b * s];
+                Ar[(tri(I) + J) * s] -= var * wbr + vai * wbi + war * vbr + wai * vbi;
+                Ai[(trs(I) + J) * s] -= vai * wbr - var * wbi + wai * vbr - war * vbi;
+            }
+            Ar[(tri(I) + I) * s] -= 2.0 * (var * war + vai * wai);
+        }
+    }
+    d[(long)(N - 1) * sde] = Ar[(tri(N - 1) + (N - 1)) * s];
+}
+
+// Eigenvalues of a real symmetric tridiagonal matrix by the implicitly shifted QL iteration
+// (textbook algorithm, e.g. Wilkinson/Reinsch "imtql1").  d[i*sd] diagonal (n), e[i*sd] sub-diagonal
+// (n-1 used, e[(n-1)*sd] is scratch).  On return d holds the eigenvalues sorted ascending.
+// Returns the number of eigenvalues that failed to converge in 64 iterations (0 = success).
+TBK_HD int tridiag_ql(int n, double* d, double* e, long sd) {
+    int fails = 0;
+    if (n <= 0) return 0;
+    e[(long)(n - 1) * sd] = 0.0;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0;
+        int m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                const double dd = fabs(d[m * sd]) + fabs(d[(m + 1) * sd]);
+                if (fabs(e[m * sd]) <= DBL_EPSILON * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 64) {
+                    ++fails;
+                    break;
+                }
+                const double el = e[l * sd];
+                double g = (d[(l + 1) * sd] - d[l * sd]) / (2.0 * el);
+                double r = sqrt(g * g + 1.0);
+                g = d[m * sd] - d[l * sd] + el / (g + (g >= 0.0 ? r : -r));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                bool underflow = false;
+                for (i = m - 1; i >= l; --i) {
+                    const double ei = e[i * sd];
+                    double f = s * ei;
+                    const double b = c * ei;
+                    r = sqrt(f * f + g * g);
+                    e[(i + 1) * sd] = r;
+                    if (r == 0.0) {
+                        d[(i + 1) * sd] -= p;
+                        e[m * sd] = 0.0;
+                        underflow = true;
+                        break;
+                    }
+                    const double rinv = 1.0 / r;
+                    s = f * rinv;
+                    c = g * rinv;
+                    g = d[(i + 1) * sd] - p;
+                    r = (d[i * sd] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[(i + 1) * sd] = g + p;
+                    g = c * r - b;
+                }
+                if (underflow) continue;
+                d[l * sd] -= p;
+                e[l * sd] = g;
+                e[m * sd] = 0.0;
+            }
+        } while (m != l);
+    }
+    // insertion sort, ascending (QL leaves the spectrum almost ordered)
+    for (int i = 1; i < n; ++i) {
+        const double x = d[i * sd];
+        int j = i - 1;
+        while (j >= 0 && d[j * sd] > x) {
+            d[(j + 1) * sd] = d[j * sd];
+            --j;
+        }
+        d[(j + 1) * sd] = x;
+    }
+    return fails;
+}
+
+// Closed forms for the two smallest sizes (packed input: N=1 -> {h00}; N=2 -> {h00, re h10, h11, im h10}).
+TBK_HD void eig2_closed(double h00, double h11, double br, double bi, double& lo, double& hi) {
+    const double mean = 0.5 * (h00 + h11);
+    const double delta = 0.5 * (h00 - h11);
+    const double rad = sqrt(delta * delta + br * br + bi * bi);
+    lo = mean - rad;
+    hi = mean + rad;
+}
+
+}  // namespace tbk

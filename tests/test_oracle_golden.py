@@ -1,0 +1,126 @@
+"""The oracle (oracle/tb_oracle.py) pinned against the reference: golden vectors produced by the unmodified
+reference, the reference's own known-answer fixtures, and -- when /root/reference is present -- the reference
+itself, live."""
+import numpy as np
+import pytest
+
+from conftest import assert_eig_close, assert_h_close, load_golden, packed_from
+from oracle import tb_oracle as orc
+from oracle.ref_shim import import_reference, reference_available
+
+T_COUNT, K_COUNT = 6, 4
+
+
+def _check_block(d, prefix, with_h=True):
+    p = packed_from(d, prefix)
+    k = d[prefix + "k"]
+    if with_h:
+        # the oracle restates the reference operation by operation -> bit-exact on the same machine,
+        # allclose across BLAS builds
+        np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, k, 1), d[prefix + "H1"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, k, 2), d[prefix + "H2"], rtol=0, atol=1e-13)
+    assert_eig_close(np.array(orc.eigenval(p.R, p.hop, p.pos, k)), d[prefix + "eig"], prefix)
+
+
+def test_silicon_golden():
+    d = load_golden("silicon.npz")
+    _check_block(d, "")
+    p = packed_from(d)
+    assert (p.size, p.dim, p.n_R) == (8, 3, 95)
+    assert_eig_close(orc.eigenval_array(p.R, p.hop, p.pos, d["k_grid"]), d["eig_grid"], "20^3 sub-grid")
+
+
+def test_reference_cli_known_answer():
+    """reference tests/test_cli_eigenvals.py:47-50 compares at atol 1e-10 with this very file's content."""
+    d = load_golden("silicon_cli_eigenvals.npz")
+    p = packed_from(d)
+    got = orc.eigenval_array(p.R, p.hop, p.pos, d["k"])
+    assert np.abs(got - d["eig"]).max() <= 1e-10
+    assert abs(d["eig"][0, 0] - (-5.821847625730381)) < 1e-12  # value quoted in SURVEY.md 8 c3
+
+
+def test_reference_regression_goldens():
+    """96 + 48 goldens of tests/regression_data/test_hamilton|test_eigenval (np.allclose in the reference)."""
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("ref_regression.npz")
+    n = 0
+    for ti, (t1, t2) in enumerate(d["t_values"]):
+        p = wl.simple_model(t1, t2)
+        for ki, kpt in enumerate(d["kpt"]):
+            for conv in (1, 2):
+                want = d[f"H{conv}_t{ti}_k{ki}"]
+                got = orc.hamilton(p.R, p.hop, p.pos, kpt, conv)
+                assert np.allclose(got, want) and np.abs(got - want).max() < 1e-12
+                n += 1
+            want = d[f"E_t{ti}_k{ki}"]
+            got = orc.eigenval(p.R, p.hop, p.pos, kpt)
+            assert np.allclose(got, want) and np.abs(got - want).max() < 1e-12
+            n += 1
+    assert n == T_COUNT * K_COUNT * 3
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_simple_models(dim):
+    d = load_golden("simple_models.npz")
+    for ti in range(T_COUNT):
+        _check_block(d, f"d{dim}_t{ti}_")
+
+
+def test_haldane():
+    _check_block(load_golden("haldane.npz"), "")
+
+
+def test_edge_cases():
+    d = load_golden("edge_cases.npz")
+    for tag in ("empty_", "n1_", "d1_", "shift_"):
+        _check_block(d, tag)
+    p = packed_from(d, "d1_")
+    np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, 0.2, 1), d["d1_scalar_H1"], atol=1e-14)
+    np.testing.assert_allclose(orc.eigenval(p.R, p.hop, p.pos, 0.2), d["d1_scalar_eig"], atol=1e-14)
+    np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, [[1], [2]], 1), d["d1_int_H1"], atol=1e-14)
+    assert not packed_from(d, "empty_").n_R and np.all(d["empty_H2"] == 0)
+
+
+def test_synthetic_golden():
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("synthetic.npz")
+    for tag in ("c3", "n3", "n5", "n7", "n12", "n17", "n33"):
+        n_orb, n_half = (int(x) for x in d[f"{tag}_shape"])
+        p = wl.synthetic(n_orb, n_half, seed=1234)
+        k = d[f"{tag}_k"]
+        nh = d[f"{tag}_H1"].shape[0]
+        np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, k[:nh], 1), d[f"{tag}_H1"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, k[:nh], 2), d[f"{tag}_H2"], rtol=0, atol=1e-12)
+        assert_eig_close(np.array(orc.eigenval(p.R, p.hop, p.pos, k)), d[f"{tag}_eig"], tag)
+
+
+def test_invalid_convention():
+    d = load_golden("haldane.npz")
+    p = packed_from(d)
+    for bad in ("a", "1", None, 3):
+        with pytest.raises(ValueError):
+            orc.hamilton(p.R, p.hop, p.pos, (0, 0), convention=bad)
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_equals_live_reference():
+    """Bit-for-bit: same numpy calls in the same order on the same machine."""
+    import warnings
+
+    from tbmodels_b200 import pack_model
+
+    warnings.simplefilter("ignore")
+    tb = import_reference()
+    rng = np.random.default_rng(5)
+    hop = {}
+    for R in [(0, 0, 0), (1, 0, 0), (0, 1, -1), (1, -2, 3)]:
+        hop[R] = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    m = tb.Model(hop=hop, pos=rng.random((4, 3)), contains_cc=False)
+    p = pack_model(m)
+    k = rng.uniform(-2, 2, size=(17, 3))
+    for conv in (1, 2):
+        assert np.array_equal(m.hamilton(k, convention=conv), orc.hamilton(p.R, p.hop, p.pos, k, conv))
+    assert np.array_equal(np.array(m.eigenval(k)), np.array(orc.eigenval(p.R, p.hop, p.pos, k)))
+    assert np.array_equal(m.hamilton(k[0]), orc.hamilton(p.R, p.hop, p.pos, k[0]))
