@@ -1,0 +1,516 @@
+#!/usr/bin/env python
+"""bench.py -- k-points/s of Model.eigenval (H(k) build + eigenvalues, fp64) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic k-points (per GPU: the workload's batch;
+weak scaling, no data-path collective -- every k-point is independent).  Default workload is
+BASELINE.json configs[1] (C2: 2-band Haldane model, 1e8 k-points per GPU).  Rank 0 prints ONE JSON line.
+
+  value        device-resident throughput (k already in HBM, eigenvalues left in HBM), CUDA events, max over ranks
+  e2e          same metric through the host-buffer C-ABI entry point (tbk_eigenval_host): pinned host k in,
+               pinned host eigenvalues out, H2D/D2H inside the timed region
+  roofline     dominant kernel: algorithmic bytes (or flops) per launch / CUDA-event duration of that kernel
+  cpu_baseline the oracle (numpy/scipy restatement of the reference path) timed on this box's host cores
+  extra        a short C3 run (N = 36, 251 stored R): FP64 tensor-core (DMMA) roofline of the H(k) GEMM
+
+``--impl reference`` times the reference's CPU implementation of the same path (the oracle port; the reference
+itself cannot travel to the GPU box) on all host cores with the same metric / unit / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "kpoints_per_s_eigenval_fp64"
+UNIT = "k-points/s"
+
+WORKLOADS = {
+    # name: (description, default k-points per GPU, default steps, default warmup, cpu sample k-points)
+    "c1": ("silicon sp3 Wannier90 model N=8 95 stored R, 20^3 k-grid", 8000, 50, 5, 8000),
+    "c2": ("2-band Haldane model N=2 D=2 4 stored R, 1e8 random k-points per GPU", 10**8, 50, 5, 300_000),
+    "c3": ("synthetic N=36 251 stored R (seed 1234), 2^21 k-points per GPU (= 256^3 mesh over 8 GPUs)", 2**21, 5, 3, 6000),
+    "c4": ("silicon 4x4x4 supercell N=512 14 stored R, 12500 random k-points per GPU (= 1e5 over 8 GPUs)", 12500, 2, 3, 100),
+    "c5": ("synthetic N=128 1001 stored R (seed 1234), 2^14 k-points per GPU", 2**14, 3, 3, 100),
+}
+
+
+def build_model(workload: str):
+    from tbmodels_b200 import workloads as wl
+
+    if workload == "c1":
+        return wl.load_packed(os.path.join(ROOT, "tests", "golden", "silicon.npz"))
+    if workload == "c2":
+        return wl.haldane()
+    if workload == "c3":
+        return wl.synthetic(36, 250, seed=1234)
+    if workload == "c4":
+        return wl.supercell(wl.load_packed(os.path.join(ROOT, "tests", "golden", "silicon.npz")), (4, 4, 4))
+    if workload == "c5":
+        return wl.synthetic(128, 1000, seed=1234)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def host_kpoints(workload: str, n_k: int, dim: int, seed: int = 0) -> np.ndarray:
+    if workload == "c1":
+        from tbmodels_b200 import workloads as wl
+
+        return wl.kgrid(20, 3)[:n_k]
+    return np.random.default_rng(seed).random((n_k, dim))
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def _ref_chunk(args):
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    R, hop, pos, k = args
+    from oracle import tb_oracle as orc
+
+    t0 = time.perf_counter()
+    orc.eigenval_array(R, hop, pos, k, chunk=2048)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(packed, k: np.ndarray, procs: int, pool=None) -> float:
+    """k-points/s of the oracle port on ``procs`` host processes (contiguous k-chunks, BLAS threads = 1)."""
+    if procs <= 1:
+        t0 = time.perf_counter()
+        _ref_chunk((packed.R, packed.hop, packed.pos, k))
+        return k.shape[0] / (time.perf_counter() - t0)
+    parts = np.array_split(k, procs)
+    t0 = time.perf_counter()
+    pool.map(_ref_chunk, [(packed.R, packed.hop, packed.pos, p) for p in parts])
+    return k.shape[0] / (time.perf_counter() - t0)
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    packed = build_model(args.workload)
+    desc, nk_default, steps_d, warm_d, sample = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    steps = args.steps if args.steps is not None else 3
+    warmup = args.warmup if args.warmup is not None else 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        # calibrate on a small sample, then size each step so the whole run stays within ~2 minutes
+        cal = host_kpoints(args.workload, max(procs * 8, min(sample, 2000) * procs // 8), packed.dim, seed=2)
+        cpu_reference_rate(packed, cal[: procs * 4], procs, pool)  # spin the workers up
+        rate = cpu_reference_rate(packed, cal, procs, pool)
+        step_s = min(12.0, max(1.0, 110.0 / max(steps + warmup, 1)))
+        sample_k = int(max(procs * 8, rate * step_s))
+        if args.workload == "c1":
+            sample_k = min(sample_k, 8000)
+        k = host_kpoints(args.workload, sample_k, packed.dim, seed=1)
+        for _ in range(warmup):
+            cpu_reference_rate(packed, k, procs, pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_rate(packed, k, procs, pool)
+        dt = time.perf_counter() - t0
+    value = steps * k.shape[0] / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": steps,
+        "warmup": warmup,
+        "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "n_orb": packed.size, "n_R_stored": packed.n_R, "dim": packed.dim},
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": procs,
+            "kind": "port",
+            "sample": f"{k.shape[0]} k-points of the same workload per step, numpy/scipy oracle port of "
+            f"Model.eigenval in {procs} processes (OPENBLAS_NUM_THREADS=1 each), host has {cores} cores",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = (
+        "timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+        "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.marks = {}
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=self.tmp,
+                stderr=subprocess.DEVNULL,
+            )
+        except OSError:
+            self.proc = None
+
+    def mark(self, name):
+        self.marks[name] = time.time()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = []
+        import datetime
+
+        for ln in open(self.tmp.name):
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), parts[4], parts[6:10]))
+            except ValueError:
+                continue
+        os.unlink(self.tmp.name)
+        t0, t1 = self.marks.get("timed_start", 0), self.marks.get("timed_end", 1e18)
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 2:
+            r0, r1 = self.marks.get("run_start", 0), self.marks.get("run_end", 1e18)
+            inside = [r for r in rows if r0 <= r[0] <= r1]
+            window = "warm-up + timed + e2e (timed region shorter than the 100 ms sampling period)"
+        if not inside:
+            inside = rows
+            window = "whole run"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[4]) if v.lower().startswith("active")})
+        return {
+            "sm_mhz": float(np.median([r[1] for r in inside])),
+            "sm_max_mhz": float(max(r[2] for r in inside)),
+            "reasons": reasons,
+            "samples": len(inside),
+            "window": window,
+        }
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def flops_per_k(packed):
+    n, nR = packed.size, packed.n_R
+    return {"F_H": 8.0 * nR * n * n + 2.0 * n * n, "F_eig": (16.0 / 3.0) * n**3, "bytes": 8.0 * packed.dim + 8.0 * n}
+
+
+def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None):
+    import torch
+
+    for _ in range(warmup):
+        ev.eigenval_device(k_dev, out=out_dev)
+    ev.check()
+    ev.profile_read()  # drop warm-up records
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.mark("timed_start")
+    l0 = ev.launch_count
+    e0.record()
+    for _ in range(steps):
+        ev.eigenval_device(k_dev, out=out_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    if sampler:
+        sampler.mark("timed_end")
+    ms = e0.elapsed_time(e1)
+    launches = ev.launch_count - l0
+    prof = ev.profile_read()
+    ev.check()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=k_dev.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches, prof
+
+
+def run_gpu_arm(args) -> None:
+    import torch
+
+    import tbmodels_b200 as tbk
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
+
+    desc, nk_default, steps_d, warm_d, cpu_sample = WORKLOADS[args.workload]
+    n_k = args.nk or nk_default
+    steps = args.steps if args.steps is not None else steps_d
+    warmup = max(args.warmup if args.warmup is not None else warm_d, 3)
+    packed = build_model(args.workload)
+    ev = tbk.Evaluator(packed, device=local_rank)
+    ev.profile(True)
+    fl = flops_per_k(packed)
+    dev = torch.device("cuda", local_rank)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sampler.mark("run_start")
+
+    # ---- device-resident batch (synthetic k-points generated on the device, seeded per rank) ----
+    if args.workload == "c1":
+        k_dev = torch.from_numpy(host_kpoints("c1", n_k, 3)).to(dev)
+    else:
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        k_dev = torch.rand((n_k, packed.dim), dtype=torch.float64, device=dev, generator=g)
+    out_dev = torch.empty((n_k, packed.size), dtype=torch.float64, device=dev)
+    ms, launches, prof = time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler)
+    value = world * n_k * steps / (ms * 1e-3)
+
+    # spot parity inside the bench itself (tiny): sorted output, finite
+    chk = out_dev[:: max(1, n_k // 1000)]
+    assert bool(torch.isfinite(chk).all()) and bool((chk[:, 1:] >= chk[:, :-1]).all()), "bench output failed sanity check"
+
+    # ---- roofline of the dominant kernel (CUDA events around each launch, same timed region) ----
+    dom = max(prof, key=lambda c: prof[c][0])
+    dom_ms, dom_n = prof[dom]
+    total_prof_ms = sum(v[0] for v in prof.values())
+    per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
+    k_per_launch = n_k * steps / max(dom_n, 1)
+    hbm_peak, hbm_src = measured_hbm_peak()
+    peaks = tbk.fp64_peaks() if not args.no_peaks else {"dmma": float("nan"), "dfma": float("nan")}
+    if dom == "hk_small" or dom == "expand":
+        achieved = fl["bytes"] * k_per_launch / per_launch_s / 1e9
+        roofline = {
+            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+            "algorithmic_bytes_per_kpoint": fl["bytes"],
+            "note": "fp64 sincospi/FMA work per k-point is co-limiting; see DESIGN.md",
+        }
+    elif dom == "hk_gemm":
+        achieved = fl["F_H"] * k_per_launch / per_launch_s / 1e12
+        roofline = {
+            "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["dmma"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["dmma"], "traffic": None,
+            "peak_source": "tbk_measure_fp64_peak: mma.sync.m8n8k4.f64 register loop on this GPU in this run",
+            "algorithmic_flops_per_kpoint": fl["F_H"],
+        }
+    else:
+        achieved = fl["F_eig"] * k_per_launch / per_launch_s / 1e12
+        roofline = {
+            "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["dfma"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["dfma"], "traffic": None,
+            "peak_source": "tbk_measure_fp64_peak: DFMA register loop (the eigensolver runs on the FP64 FMA pipe)",
+            "algorithmic_flops_per_kpoint": fl["F_eig"],
+        }
+    roofline["kernel_share_of_step"] = dom_ms / max(total_prof_ms, 1e-12)
+    roofline["kernel_ms_per_launch"] = per_launch_s * 1e3
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside) ----
+    e2e_nk = min(n_k, args.e2e_nk) if args.e2e_nk else n_k
+    k_host = tbk.pinned_empty((e2e_nk, packed.dim))
+    k_host[:] = k_dev[:e2e_nk].cpu().numpy()
+    out_host = tbk.pinned_empty((e2e_nk, packed.size))
+    e2e_steps = max(1, min(steps, 10))
+    for _ in range(2):
+        ev.eigenval_array(k_host, out=out_host)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ev.eigenval_array(k_host, out=out_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert np.array_equal(out_host[:64], out_dev[:64].cpu().numpy()), "host and device entry points disagree"
+    e2e = {
+        "value": world * e2e_nk * e2e_steps / e2e_s,
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(e2e_nk * packed.dim * 8),
+        "d2h_bytes_per_step": int(e2e_nk * packed.size * 8),
+        "steps": e2e_steps,
+        "kpoints_per_gpu_per_step": e2e_nk,
+        "api": "Evaluator.eigenval_array -> tbk_eigenval_host (pinned host buffers, chunked 3-stream pipeline)",
+    }
+    ev.profile_read()
+
+    # ---- optional: NCCL all-gather of the eigenvalue shards (the API's exchange step, outside `value`) ----
+    extra = {}
+    if dist is not None and packed.size * n_k * 8 * world <= 8 << 30:
+        gathered = torch.empty((world * n_k, packed.size), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, out_dev)
+        torch.cuda.synchronize()
+        g0 = torch.cuda.Event(enable_timing=True)
+        g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gathered, out_dev)
+        g1.record()
+        torch.cuda.synchronize()
+        extra["allgather_ms"] = g0.elapsed_time(g1)
+        del gathered
+
+    # ---- extra: short C3 run for the FP64 tensor-core roofline of the H(k) GEMM ----
+    if args.workload == "c2" and not args.no_extra:
+        del k_dev, out_dev
+        torch.cuda.empty_cache()
+        p3 = build_model("c3")
+        ev3 = tbk.Evaluator(p3, device=local_rank)
+        ev3.profile(True)
+        nk3 = 2**19
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        k3 = torch.rand((nk3, 3), dtype=torch.float64, device=dev, generator=g)
+        o3 = torch.empty((nk3, 36), dtype=torch.float64, device=dev)
+        ms3, l3, prof3 = time_device_steps(ev3, k3, o3, 3, 3, dist, None)
+        f3 = flops_per_k(p3)
+        gemm_s = prof3["hk_gemm"][0] * 1e-3
+        tf = f3["F_H"] * nk3 * 3 / gemm_s / 1e12
+        extra["c3"] = {
+            "workload": "c3: " + WORKLOADS["c3"][0].split(",")[0] + f", {nk3} k-points per GPU per step",
+            "value": world * nk3 * 3 / (ms3 * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": ms3 / 3,
+            "kernel_ms": {c: v[0] / 3 for c, v in prof3.items() if v[1]},
+            "roofline": {
+                "kernel": "hk_gemm", "bound": "tensor", "achieved": tf, "peak": peaks["dmma"], "unit": "TFLOP/s",
+                "frac": tf / peaks["dmma"], "traffic": None,
+                "algorithmic_flops_per_kpoint": f3["F_H"],
+                "executed_over_algorithmic": 0.5,
+                "peak_source": "tbk_measure_fp64_peak (DMMA register loop, this GPU, this run)",
+            },
+        }
+        launches_extra = l3
+        ev3.close()
+    sampler.mark("run_end")
+    clocks = sampler.stop()
+
+    # ---- CPU baseline: the oracle port on this box's host cores (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ks = host_kpoints(args.workload, min(cpu_sample, n_k), packed.dim, seed=1)
+        rate = cpu_reference_rate(packed, ks, 1)
+        cpu = {
+            "value": rate,
+            "unit": UNIT,
+            "cores": 1,
+            "kind": "port",
+            "sample": f"{ks.shape[0]} k-points of the same workload, numpy/scipy oracle port of Model.eigenval, "
+            f"single process as the reference ships (host has {os.cpu_count()} cores)",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": steps,
+            "warmup": warmup,
+            "ms_per_step": ms / steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {desc}",
+                "kpoints_per_gpu": n_k,
+                "n_orb": packed.size,
+                "n_R_stored": packed.n_R,
+                "dim": packed.dim,
+                "path": ev.path,
+                "parallelism": f"k-shards x{world}, no data-path collective",
+                "l2": "inputs+outputs per step exceed the 126 MB L2" if n_k * fl["bytes"] > 2 * 126e6 else "L2 not flushed: batch smaller than L2 (latency-bound parity config)",
+            },
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "fp64_peak_tflops": peaks,
+            "kernel_ms_per_step": {c: v[0] / steps for c, v in prof.items() if v[1]},
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--nk", type=int, default=None, help="k-points per GPU per step (default: the workload's)")
+    ap.add_argument("--e2e-nk", type=int, default=None, help="cap the k-points per e2e step")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-peaks", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,8 @@ SYMBOLS = (
     "tbk_model_check",
     "tbk_launch_count",
     "tbk_workspace_bytes",
+    "tbk_profile",
+    "tbk_profile_read",
     "tbk_host_alloc",
     "tbk_host_free",
     "tbk_measure_fp64_peak",
@@ -84,6 +86,10 @@ def load() -> C.CDLL:
     lib.tbk_launch_count.restype = C.c_int64
     lib.tbk_workspace_bytes.argtypes = [vp]
     lib.tbk_workspace_bytes.restype = C.c_int64
+    lib.tbk_profile.argtypes = [vp, C.c_int]
+    lib.tbk_profile.restype = C.c_int
+    lib.tbk_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+    lib.tbk_profile_read.restype = C.c_int
     lib.tbk_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.tbk_host_alloc.restype = C.c_int
     lib.tbk_host_free.argtypes = [vp]

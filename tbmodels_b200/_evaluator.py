@@ -105,6 +105,19 @@ class Evaluator:
     def workspace_bytes(self) -> int:
         return int(self._lib.tbk_workspace_bytes(self._handle))
 
+    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql")
+
+    def profile(self, enable: bool = True) -> None:
+        """Bracket every kernel launch with CUDA events on its stream (read back with :meth:`profile_read`)."""
+        _capi.check(self._lib.tbk_profile(self._handle, 1 if enable else 0))
+
+    def profile_read(self) -> dict:
+        """``{class: (total_ms, launches)}`` accumulated since the last read (synchronises the device)."""
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
+        _capi.check(self._lib.tbk_profile_read(self._handle, ms, cnt))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
+
     def close(self) -> None:
         self._finalizer()
 

@@ -43,7 +43,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+    uint32_t spins = 0;
     do {
+        if (++spins > (1u << 26)) __trap();  // a lost TMA completion becomes an error, not a hung GPU
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -198,11 +200,8 @@ template <int NA>
 cudaError_t launch_na(const ModelDev& md, const double* k, long nk, double* Hp, cudaStream_t st) {
     using C = Cfg<NA>;
     const size_t smem = C::smem_bytes(md.dim);
-    static bool configured = false;  // per process; the attribute is per function, not per device context switch
     cudaError_t err = cudaFuncSetAttribute(hk_gemm_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    configured = true;
-    (void)configured;
     const long m_tiles = (nk + BM - 1) / BM;
     const long grid = m_tiles * md.n_tiles;
     if (grid <= 0) return cudaSuccess;

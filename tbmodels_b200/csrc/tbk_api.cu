@@ -95,7 +95,33 @@ struct tbk_model {
     double* ho[2] = {nullptr, nullptr};
     size_t hk_bytes = 0, ho_bytes = 0;
     int64_t launches = 0;
+    // optional per-kernel-class CUDA-event timing (tbk_profile / tbk_profile_read)
+    bool prof_on = false;
+    struct ProfRec {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<ProfRec> prof;
+    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
+    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
 };
+
+// Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the launch stream.
+#define LAUNCH(cls, st, call)                                        \
+    do {                                                             \
+        tbk_model::ProfRec rec_{nullptr, nullptr, (cls)};            \
+        if (m->prof_on) {                                            \
+            CU(cudaEventCreate(&rec_.a));                            \
+            CU(cudaEventCreate(&rec_.b));                            \
+            CU(cudaEventRecord(rec_.a, (st)));                       \
+        }                                                            \
+        CU(call);                                                    \
+        if (m->prof_on) {                                            \
+            CU(cudaEventRecord(rec_.b, (st)));                       \
+            m->prof.push_back(rec_);                                 \
+        }                                                            \
+        m->launches += 1;                                            \
+    } while (0)
 
 namespace {
 
@@ -134,18 +160,16 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (md.small_ok) {
-        CU(launch_hk_small(md, k, nk, nullptr, out, st));
-        m->launches += 1;
+        LAUNCH(1, st, launch_hk_small(md, k, nk, nullptr, out, st));
         return TBK_OK;
     }
     if (int rc = ensure_workspace(m, nk)) return rc;
     for (long c0 = 0; c0 < nk; c0 += m->chunk) {
         const long cn = std::min(m->chunk, nk - c0);
         double* D = out + c0 * md.n;
-        CU(launch_hk_gemm(md, k + c0 * md.dim, cn, m->wsH, st));
-        CU(launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
-        CU(launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
-        m->launches += 3;
+        LAUNCH(0, st, launch_hk_gemm(md, k + c0 * md.dim, cn, m->wsH, st));
+        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
+        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
     }
     return TBK_OK;
 }
@@ -158,10 +182,9 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
     for (long c0 = 0; c0 < nk; c0 += m->chunk) {
         const long cn = std::min(m->chunk, nk - c0);
         const double* kc = k + c0 * md.dim;
-        if (md.small_ok) CU(launch_hk_small(md, kc, cn, m->wsH, nullptr, st));
-        else CU(launch_hk_gemm(md, kc, cn, m->wsH, st));
-        CU(launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
-        m->launches += 2;
+        if (md.small_ok) LAUNCH(1, st, launch_hk_small(md, kc, cn, m->wsH, nullptr, st));
+        else LAUNCH(0, st, launch_hk_gemm(md, kc, cn, m->wsH, st));
+        LAUNCH(2, st, launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
     }
     return TBK_OK;
 }
@@ -442,6 +465,35 @@ int tbk_model_check(tbk_model* m) {
 }
 
 int64_t tbk_launch_count(const tbk_model* m) { return m ? m->launches : 0; }
+
+int tbk_profile(tbk_model* m, int enable) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_profile: null handle");
+    m->prof_on = enable != 0;
+    return TBK_OK;
+}
+
+int tbk_profile_read(tbk_model* m, double* ms, int64_t* count) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_profile_read: null handle");
+    DeviceGuard guard(m->device);
+    CU(cudaDeviceSynchronize());
+    for (auto& r : m->prof) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            m->prof_ms[r.cls] += t;
+            m->prof_n[r.cls] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    m->prof.clear();
+    for (int i = 0; i < TBK_PROFILE_CLASSES; ++i) {
+        if (ms) ms[i] = m->prof_ms[i];
+        if (count) count[i] = m->prof_n[i];
+        m->prof_ms[i] = 0.0;
+        m->prof_n[i] = 0;
+    }
+    return TBK_OK;
+}
 
 int64_t tbk_workspace_bytes(const tbk_model* m) {
     return m ? (int64_t)(m->ws_bytes + 2 * m->hk_bytes + 2 * m->ho_bytes + m->model_bytes) : 0;

@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden vectors.
+
+Bounds (BASELINE.json north_star): H(k): max|dH| <= 1e-11 * max|H_R|; eigenvalues: <= 1e-10 * spectral radius.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_eig_close, assert_h_close, h_scale, load_golden, packed_from
+
+pytestmark = pytest.mark.gpu
+
+T_COUNT = 6
+
+
+@pytest.fixture(scope="module")
+def tbk():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import tbmodels_b200
+
+    return tbmodels_b200
+
+
+def _oracle():
+    from oracle import tb_oracle
+
+    return tb_oracle
+
+
+def _check(tbk, packed, k, H1=None, H2=None, eig=None, what=""):
+    ev = tbk.Evaluator(packed)
+    try:
+        if H1 is not None:
+            assert_h_close(ev.hamilton(k[: len(H1)], convention=1), H1, packed, what + " H conv1")
+        if H2 is not None:
+            got = ev.hamilton(k[: len(H2)], convention=2)
+            assert_h_close(got, H2, packed, what + " H conv2")
+            # structural facts of the reference output: bit-wise Hermitian, real diagonal
+            assert np.array_equal(got, got.conj().transpose(0, 2, 1)), what + ": conv-2 H not bit-wise Hermitian"
+            assert np.all(np.einsum("kii->ki", got).imag == 0.0)
+        if eig is not None:
+            got = ev.eigenval_array(k)
+            assert_eig_close(got, eig, what + " eig")
+            assert np.all(np.diff(got, axis=1) >= 0), what + ": eigenvalues not ascending"
+    finally:
+        ev.close()
+
+
+def _block(tbk, d, prefix):
+    p = packed_from(d, prefix)
+    _check(tbk, p, d[prefix + "k"], d[prefix + "H1"], d[prefix + "H2"], d[prefix + "eig"], prefix or "model")
+
+
+# ----------------------------------------------------------------------------------- golden vectors
+def test_silicon_c1(tbk):
+    d = load_golden("silicon.npz")
+    _block(tbk, d, "")
+    p = packed_from(d)
+    ev = tbk.Evaluator(p)
+    assert ev.path == "fused-small"
+    assert_eig_close(ev.eigenval_array(d["k_grid"]), d["eig_grid"], "silicon 20^3 sub-grid")
+
+
+def test_silicon_c1_full_grid_vs_oracle(tbk):
+    """Config C1 at full size: 20x20x20 mesh, both conventions and eigenvalues, against the oracle."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = packed_from(load_golden("silicon.npz"))
+    k = wl.kgrid(20, 3)
+    _check(
+        tbk,
+        p,
+        k,
+        orc.hamilton(p.R, p.hop, p.pos, k, 1),
+        orc.hamilton(p.R, p.hop, p.pos, k, 2),
+        orc.eigenval_array(p.R, p.hop, p.pos, k),
+        "C1 full grid",
+    )
+
+
+def test_reference_cli_known_answer(tbk):
+    """reference tests/test_cli_eigenvals.py:47-50: atol 1e-10 against silicon_eigenvals.hdf5."""
+    d = load_golden("silicon_cli_eigenvals.npz")
+    got = tbk.Evaluator(packed_from(d)).eigenval_array(d["k"])
+    assert np.abs(got - d["eig"]).max() <= 1e-10
+
+
+def test_reference_regression_goldens(tbk):
+    """The reference's own goldens for test_simple_hamilton / test_simple_eigenval (np.allclose there)."""
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("ref_regression.npz")
+    for ti, (t1, t2) in enumerate(d["t_values"]):
+        m = tbk.KModel.from_packed(wl.simple_model(t1, t2))
+        for ki, kpt in enumerate(d["kpt"]):
+            for conv in (1, 2):
+                got = m.hamilton(tuple(kpt), convention=conv)
+                assert got.shape == (2, 2)
+                assert np.allclose(got, d[f"H{conv}_t{ti}_k{ki}"]) and np.abs(got - d[f"H{conv}_t{ti}_k{ki}"]).max() < 1e-11
+            got = m.eigenval(tuple(kpt))
+            assert got.shape == (2,)
+            assert np.allclose(got, d[f"E_t{ti}_k{ki}"]) and np.abs(got - d[f"E_t{ti}_k{ki}"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_simple_models(tbk, dim):
+    d = load_golden("simple_models.npz")
+    for ti in range(T_COUNT):
+        _block(tbk, d, f"d{dim}_t{ti}_")
+
+
+def test_haldane_c2_golden(tbk):
+    _block(tbk, load_golden("haldane.npz"), "")
+
+
+def test_edge_cases(tbk):
+    d = load_golden("edge_cases.npz")
+    for tag in ("empty_", "n1_", "d1_", "shift_"):
+        _block(tbk, d, tag)
+    m = tbk.KModel.from_packed(packed_from(d, "d1_"))
+    # scalar and integer k (reference tests/test_convention.py:23-33)
+    got = m.hamilton(0.2, convention=1)
+    assert got.shape == (2, 2) and np.abs(got - d["d1_scalar_H1"]).max() < 1e-11
+    got = m.eigenval(0.2)
+    assert got.shape == (2,) and np.abs(got - d["d1_scalar_eig"]).max() < 1e-10
+    got = m.hamilton([[1], [2]], convention=1)
+    assert np.abs(got - d["d1_int_H1"]).max() < 1e-11
+    # empty batch
+    ev = tbk.Evaluator(packed_from(d, "d1_"))
+    assert ev.hamilton(np.zeros((0, 1))).shape == (0, 2, 2)
+    assert ev.eigenval(np.zeros((0, 1))) == []
+
+
+@pytest.mark.parametrize("tag", ["c3", "c5s", "n3", "n5", "n7", "n12", "n17", "n33", "n50", "n70"])
+def test_synthetic_golden(tbk, tag):
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("synthetic.npz")
+    n_orb, n_half = (int(x) for x in d[f"{tag}_shape"])
+    p = wl.synthetic(n_orb, n_half, seed=1234)
+    _check(tbk, p, d[f"{tag}_k"], d[f"{tag}_H1"], d[f"{tag}_H2"], d[f"{tag}_eig"], tag)
+
+
+@pytest.mark.parametrize("tag,size", [("s222", (2, 2, 2)), ("s444", (4, 4, 4))])
+def test_supercell_c4(tbk, tag, size):
+    """Config C4 (N = 512) and its N = 64 little brother, against reference eigenvalues."""
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("supercell.npz")
+    p = wl.supercell(packed_from(load_golden("silicon.npz")), size)
+    assert np.array_equal(p.R, d[f"{tag}_R"])
+    H1 = d.get(f"{tag}_H1")
+    _check(tbk, p, d[f"{tag}_k"], H1, None, d[f"{tag}_eig"], tag)
+
+
+# ----------------------------------------------------------------------------------- general path on small models
+def test_general_path_on_small_models(tbk, monkeypatch):
+    """TBK_FORCE_GEMM routes N <= 8 models through the DMMA GEMM + cooperative eigensolver as well."""
+    monkeypatch.setenv("TBK_FORCE_GEMM", "1")
+    d = load_golden("silicon.npz")
+    p = packed_from(d)
+    ev = tbk.Evaluator(p)
+    assert ev.path == "gemm+tridiag-ql"
+    ev.close()
+    _block(tbk, d, "")
+    _block(tbk, load_golden("haldane.npz"), "")
+    e = load_golden("edge_cases.npz")
+    for tag in ("empty_", "n1_", "d1_"):
+        _block(tbk, e, tag)
+    s = load_golden("simple_models.npz")
+    for dim in (2, 3, 4):
+        _block(tbk, s, f"d{dim}_t0_")
+
+
+# ----------------------------------------------------------------------------------- API contract
+def test_batch_invariance_bit_exact(tbk):
+    """reference tests/test_hamilton.py:21-32, test_eigenval.py:17-20 (assert_allclose rtol 1e-7, atol 0):
+    a k-point's result must not depend on where it sits in the batch."""
+    from tbmodels_b200 import workloads as wl
+
+    rng = np.random.default_rng(3)
+    for p in (packed_from(load_golden("silicon.npz")), wl.synthetic(36, 40), wl.synthetic(12, 10), wl.haldane()):
+        m = tbk.KModel.from_packed(p)
+        k = rng.uniform(-1, 1, size=(301, p.dim))
+        for conv in (1, 2):
+            batched = m.hamilton(k, convention=conv)
+            for i in (0, 1, 127, 128, 129, 300):
+                assert np.array_equal(batched[i], m.hamilton(k[i], convention=conv))
+            assert np.array_equal(batched[130:], m.hamilton(k[130:], convention=conv))
+        eb = m.eigenval(k)
+        assert isinstance(eb, list) and len(eb) == 301
+        for i in (0, 1, 127, 128, 129, 300):
+            assert np.array_equal(eb[i], m.eigenval(k[i]))
+        assert np.array_equal(np.array(eb[130:]), np.array(m.eigenval(k[130:])))
+
+
+def test_invalid_convention_raises_before_device(tbk):
+    m = tbk.KModel.from_packed(packed_from(load_golden("haldane.npz")))
+    for bad in ("a", "1", None, 0, 3):
+        with pytest.raises(ValueError):
+            m.hamilton((0, 0), convention=bad)
+    with pytest.raises(ValueError):
+        m.hamilton((0, 0, 0))  # wrong number of components
+
+
+def test_device_pointer_api_matches_host_api(tbk):
+    import torch
+
+    from tbmodels_b200 import workloads as wl
+
+    rng = np.random.default_rng(11)
+    for p in (wl.haldane(), packed_from(load_golden("silicon.npz")), wl.synthetic(36, 30)):
+        ev = tbk.Evaluator(p)
+        k = rng.random((1000, p.dim))
+        kd = torch.from_numpy(k).cuda()
+        e_dev = ev.eigenval_device(kd)
+        h_dev = ev.hamilton_device(kd, convention=1)
+        ev.check()
+        assert np.array_equal(e_dev.cpu().numpy(), ev.eigenval_array(k))
+        assert np.array_equal(h_dev.cpu().numpy(), ev.hamilton(k, convention=1))
+        assert ev.launch_count > 0
+
+
+def test_mutation_invalidates_device_copy(tbk):
+    """Model.hop is public and mutated in place by the reference (add_hop :1215); the cache must notice."""
+    orc = _oracle()
+    p = packed_from(load_golden("haldane.npz"))
+    m = tbk.KModel.from_packed(p)
+    k = np.array([[0.1, 0.7], [0.3, -0.2]])
+    before = np.array(m.eigenval(k))
+    m.hop[(1, 0)][0, 0] += 0.25
+    after = np.array(m.eigenval(k))
+    assert np.abs(after - before).max() > 1e-3
+    p2 = tbk.pack_model(m)
+    assert_eig_close(after, np.array(orc.eigenval(p2.R, p2.hop, p2.pos, k)), "mutated")
+
+
+def test_patch_model_class(tbk):
+    """install() swaps hamilton/eigenval on a Model class; the instance stays picklable."""
+    import pickle
+
+    orc = _oracle()
+
+    class Model:  # stand-in with the attributes the hot path reads (the reference class is not on the GPU box)
+        def __init__(self, packed):
+            self.hop = tbk.hop_dict(packed)
+            self.pos = packed.pos.copy()
+            self.size = packed.size
+            self.dim = packed.dim
+
+        def hamilton(self, k, convention=2):
+            raise AssertionError("numpy path must not run")
+
+        def eigenval(self, k):
+            raise AssertionError("numpy path must not run")
+
+    p = packed_from(load_golden("silicon.npz"))
+    tbk.install(Model)
+    try:
+        m = Model(p)
+        k = np.array([[0.1, 0.2, 0.7], [0.0, 0.0, 0.0]])
+        assert_eig_close(np.array(m.eigenval(k)), np.array(orc.eigenval(p.R, p.hop, p.pos, k)), "patched")
+        assert_h_close(m.hamilton(k[0], convention=1), orc.hamilton(p.R, p.hop, p.pos, k[0], 1), p, "patched")
+        m2 = pickle.loads(pickle.dumps(m))
+        assert np.array_equal(np.array(m2.eigenval(k)), np.array(m.eigenval(k)))
+    finally:
+        tbk.uninstall(Model)
+    with pytest.raises(AssertionError):
+        Model(p).eigenval([0, 0, 0])
+
+
+# ----------------------------------------------------------------------------------- full-size properties
+def test_haldane_c2_large_properties(tbk):
+    """C2 at 2e7 k-points (device resident): size-independent properties + oracle on a subsample."""
+    import torch
+
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = wl.haldane()
+    ev = tbk.Evaluator(p)
+    n = 20_000_000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    k = torch.rand((n, 2), dtype=torch.float64, device="cuda", generator=g)
+    e = ev.eigenval_device(k)
+    ev.check()
+    assert bool((e[:, 0] <= e[:, 1]).all())
+    # trace of H(k) = sum of eigenvalues: on-site (M, -M) cancels, t2 terms give 2 t2 cos(phi) sum cos = 0 at phi = pi/2
+    assert float((e.sum(dim=1)).abs().max()) < 1e-12
+    # lattice periodicity: eigenvalues at k and k + integer vector agree
+    shift = torch.tensor([3.0, -5.0], dtype=torch.float64, device="cuda")
+    e2 = ev.eigenval_device(k[:1_000_000] + shift)
+    assert float((e2 - e[:1_000_000]).abs().max()) < 1e-10 * 3.5
+    idx = torch.randint(0, n, (20000,), device="cuda", generator=g)
+    ks = k[idx].cpu().numpy()
+    assert_eig_close(e[idx].cpu().numpy(), orc.eigenval_array(p.R, p.hop, p.pos, ks), "C2 subsample")
+
+
+def test_c3_properties_and_subsample(tbk):
+    """C3 model (N = 36, 251 stored R) on a 64^3 slab of the 256^3 mesh: trace identity, ordering, oracle subsample."""
+    import torch
+
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(36, 250, seed=1234)
+    ev = tbk.Evaluator(p)
+    axes = [torch.arange(64, dtype=torch.float64, device="cuda") / 256.0] * 3
+    k = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, 3).contiguous()
+    e = ev.eigenval_device(k)
+    ev.check()
+    assert bool((e[:, 1:] >= e[:, :-1]).all())
+    h = ev.hamilton_device(k[:4096], convention=2)
+    tr = torch.einsum("kii->k", h).real
+    assert float((tr - e[:4096].sum(dim=1)).abs().max()) < 1e-10 * float(e.abs().max()) * 36
+    idx = torch.arange(0, k.shape[0], 64**3 // 200, device="cuda")
+    assert_eig_close(
+        e[idx].cpu().numpy(), orc.eigenval_array(p.R, p.hop, p.pos, k[idx].cpu().numpy()), "C3 subsample"
+    )
+
+
+def test_c5_small_sweep(tbk):
+    """C5 shape (N = 128) with 200 stored R, 512 k-points against the oracle."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(128, 200, seed=1234)
+    k = np.random.default_rng(2).random((512, 3))
+    got = tbk.Evaluator(p).eigenval_array(k)
+    assert_eig_close(got[:64], orc.eigenval_array(p.R, p.hop, p.pos, k[:64]), "C5")
+    assert np.all(np.diff(got, axis=1) >= 0)
+
+
+def test_host_pipeline_chunking(tbk, monkeypatch):
+    """Small host chunks force many pipeline iterations; pinned and pageable buffers give identical results."""
+    from tbmodels_b200 import workloads as wl
+
+    p = wl.haldane()
+    k = np.random.default_rng(4).random((300_001, 2))
+    ev = tbk.Evaluator(p)
+    ref = ev.eigenval_array(k)
+    monkeypatch.setenv("TBK_HOST_CHUNK_MB", "1")
+    ev2 = tbk.Evaluator(p)
+    kp = tbk.pinned_empty(k.shape)
+    kp[:] = k
+    out = tbk.pinned_empty((k.shape[0], 2))
+    got = ev2.eigenval_array(kp, out=out)
+    assert got is out and np.array_equal(got, ref)
+    h_ref = ev.hamilton(k[:70_000], convention=1)
+    assert np.array_equal(ev2.hamilton(k[:70_000], convention=1), h_ref)
