@@ -72,10 +72,11 @@ int tbk_model_check(tbk_model* m);
 /* Number of kernels launched through this handle so far. */
 int64_t tbk_launch_count(const tbk_model* m);
 /* Per-kernel-class device timing with CUDA events recorded on the launching stream.
- * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand, 3 tridiagonalisation, 4 tridiagonal QL.
+ * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand, 3 tridiagonalisation, 4 tridiagonal QL,
+ * 5 phase tiles for the GEMM.
  * tbk_profile(m, 1) starts recording; tbk_profile_read synchronises, returns the accumulated milliseconds
  * and launch counts per class since the last read (arrays of TBK_PROFILE_CLASSES) and resets them. */
-#define TBK_PROFILE_CLASSES 5
+#define TBK_PROFILE_CLASSES 6
 int tbk_profile(tbk_model* m, int enable);
 int tbk_profile_read(tbk_model* m, double* ms, int64_t* count);
 /* Bytes of device scratch currently held by the handle. */

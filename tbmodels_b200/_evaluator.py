@@ -31,7 +31,9 @@ def _check_convention(convention) -> None:
 
 def _normalise_k(k, dim: int):
     """Reference semantics of ``k_array = np.array(k, ndmin=1)`` + single-point reshape (:1103-1108)."""
-    k_array = np.array(k, ndmin=1)
+    k_array = np.asarray(k)  # same values as np.array(k, ndmin=1) at :1103, without copying a ready float64 array
+    if k_array.ndim == 0:
+        k_array = k_array.reshape((1,))
     if k_array.ndim == 1:
         single_point = True
         k_array = k_array.reshape((1, -1))
@@ -105,7 +107,7 @@ class Evaluator:
     def workspace_bytes(self) -> int:
         return int(self._lib.tbk_workspace_bytes(self._handle))
 
-    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql")
+    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase")
 
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on its stream (read back with :meth:`profile_read`)."""
@@ -113,8 +115,8 @@ class Evaluator:
 
     def profile_read(self) -> dict:
         """``{class: (total_ms, launches)}`` accumulated since the last read (synchronises the device)."""
-        ms = (C.c_double * 5)()
-        cnt = (C.c_int64 * 5)()
+        ms = (C.c_double * 6)()
+        cnt = (C.c_int64 * 6)()
         _capi.check(self._lib.tbk_profile_read(self._handle, ms, cnt))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
 
@@ -239,7 +241,7 @@ def fp64_peaks(iters: int = 4000) -> dict:
     """Measured FP64 peaks of the current device in TFLOP/s: ``{"dmma": .., "dfma": ..}``."""
     lib = _capi.load()
     out = {}
-    for name, kind in (("dmma", 0), ("dfma", 1)):
+    for name, kind in (("dmma", 0), ("dfma", 1), ("dmma+dfma", 2)):
         v = float(lib.tbk_measure_fp64_peak(kind, iters))
         if v < 0:
             raise _capi.TbkError(_capi.TBK_E_CUDA, "FP64 peak micro-benchmark failed (no CUDA device?)")

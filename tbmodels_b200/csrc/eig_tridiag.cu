@@ -193,24 +193,170 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shared-memory resident variant (N <= ~164): the packed matrix is re-laid out on load as interleaved
+// complex (double2) lower-packed rows, so every element access is one LDS.128 / STS.128, all indices are
+// 32-bit, and the address space is known at compile time.  Row starts tri(i) are distinct mod 8 over aligned
+// groups of 8 rows, consecutive columns are consecutive 16-byte words: both access patterns of the
+// Hermitian matrix-vector product (own row / conjugated column) are (nearly) bank-conflict free.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }
+
+template <int G>
+__global__ void __launch_bounds__(TPB)
+tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    constexpr int NW = G > 32 ? G / 32 : 1;
+    extern __shared__ __align__(16) double2 sm2[];
+    const int MPB = blockDim.x / G;
+    const int group = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    const int ntri = itri(N);
+    const long NN = (long)N * N;
+
+    const long kidx = (long)blockIdx.x * MPB + group;
+    const bool valid = kidx < nk;
+    const long kk = valid ? kidx : nk - 1;  // idle groups shadow the last matrix and store nothing
+
+    const int per_group = ntri + 3 * N + 2 * NW + 1;  // in double2 units
+    double2* A = sm2 + (size_t)group * per_group;
+    double2* V = A + ntri;
+    double2* P = V + N;
+    double* ds = reinterpret_cast<double*>(P + N);
+    double* es = ds + N;
+    double* red = es + N;
+
+    {   // load + interleave: real plane [tri(i)+j], imag plane [ntri + trs(i)+j]
+        const double* src = Hp + kk * NN;
+        const double* srci = src + ntri;
+        for (int i = 0; i < N; ++i) {
+            const int ro = itri(i), io = ro - i;  // trs(i) = tri(i) - i
+            for (int j = t; j <= i; j += G) A[ro + j] = make_double2(src[ro + j], j < i ? srci[io + j] : 0.0);
+        }
+    }
+    group_sync<G>(group);
+
+    int parity = 0;
+    for (int j = 0; j < N - 1; ++j) {
+        const int m = N - 1 - j;
+        const int r0 = j + 1;
+        // --- reflector from column j ---
+        const double2 alpha = A[itri(r0) + j];
+        double xn = 0.0, dummy = 0.0;
+        for (int a = 1 + t; a < m; a += G) {
+            const double2 x = A[itri(r0 + a) + j];
+            xn += x.x * x.x + x.y * x.y;
+        }
+        group_sum2<G>(xn, dummy, red, group, t, parity);
+        double beta, tr, ti, sr, si;
+        householder_gen(alpha.x, alpha.y, xn, beta, tr, ti, sr, si);
+        if (t == 0) {
+            ds[j] = A[itri(j) + j].x;
+            es[j] = beta;
+        }
+        for (int a = t; a < m; a += G) {
+            if (a == 0) {
+                V[0] = make_double2(1.0, 0.0);
+            } else {
+                const double2 x = A[itri(r0 + a) + j];
+                V[a] = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
+            }
+        }
+        group_sync<G>(group);
+        // --- p = tau * A22 v (row part from the own packed row, column part conjugated), dot = p^H v ---
+        double dr = 0.0, di = 0.0;
+        const int c2_0 = itri(r0);
+        for (int a = t; a < m; a += G) {
+            const int I = r0 + a;
+            const int rowI = itri(I) + r0;
+            int c2 = c2_0 + I;  // tri(J) + I for J = r0
+            double sumr = 0.0, sumi = 0.0;
+#pragma unroll 4
+            for (int b = 0; b < m; ++b) {
+                const bool left = b < a;
+                const double2 z = A[left ? rowI + b : c2];
+                const double zi = left ? z.y : -z.y;
+                const double2 v = V[b];
+                sumr = fma(z.x, v.x, fma(-zi, v.y, sumr));
+                sumi = fma(z.x, v.y, fma(zi, v.x, sumi));
+                c2 += r0 + b + 1;
+            }
+            const double pr = tr * sumr - ti * sumi;
+            const double pi = tr * sumi + ti * sumr;
+            P[a] = make_double2(pr, pi);
+            const double2 va = V[a];
+            dr += pr * va.x + pi * va.y;
+            di += pr * va.y - pi * va.x;
+        }
+        group_sum2<G>(dr, di, red, group, t, parity);
+        const double alr = -0.5 * (tr * dr - ti * di);
+        const double ali = -0.5 * (tr * di + ti * dr);
+        for (int a = t; a < m; a += G) {
+            const double2 v = V[a];
+            double2 p = P[a];
+            p.x += alr * v.x - ali * v.y;
+            p.y += alr * v.y + ali * v.x;
+            P[a] = p;
+        }
+        group_sync<G>(group);
+        // --- A22 -= v w^H + w v^H (lower triangle) ---
+        for (int a = t; a < m; a += G) {
+            const int I = r0 + a;
+            const double2 va = V[a], wa = P[a];
+            double2* row = A + itri(I) + r0;
+#pragma unroll 4
+            for (int b = 0; b < a; ++b) {
+                const double2 vb = V[b], wb = P[b];
+                double2 z = row[b];
+                z.x -= va.x * wb.x + va.y * wb.y + wa.x * vb.x + wa.y * vb.y;
+                z.y -= va.y * wb.x - va.x * wb.y + wa.y * vb.x - wa.x * vb.y;
+                row[b] = z;
+            }
+            row[a].x -= 2.0 * (va.x * wa.x + va.y * wa.y);
+        }
+        group_sync<G>(group);
+    }
+    if (t == 0) {
+        ds[N - 1] = A[itri(N - 1) + (N - 1)].x;
+        es[N - 1] = 0.0;
+    }
+    group_sync<G>(group);
+    if (valid) {
+        for (int i = t; i < N; i += G) {
+            D[kidx * N + i] = ds[i];
+            E[kidx * N + i] = es[i];
+        }
+    }
+}
+
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int G>
 cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
     constexpr int NW = G > 32 ? G / 32 : 1;
-    const long NN = (long)n * n;
-    const size_t per_mat = (size_t)(NN + 6L * n + 4 * NW + 2) * 8;
+    const long ntri = (long)n * (n + 1) / 2;
+    const size_t per_mat = (size_t)(ntri + 3L * n + 2 * NW + 1) * 16;  // double2 units, see tridiag_smem_kernel
     int mpb = (int)(kSmemLimit / per_mat);
     if (mpb > TPB / G) mpb = TPB / G;
-    const bool in_smem = mpb >= 1;
-    if (!in_smem) mpb = 1;
-    const size_t smem = in_smem ? per_mat * mpb : (size_t)(6L * n + 4 * NW + 2) * 8;
+    if (mpb >= 1) {
+        // keep at least two CTAs per SM resident when several matrices share a CTA
+        while (mpb > 1 && per_mat * mpb > kSmemLimit / 2) --mpb;
+        const size_t smem = per_mat * mpb;
+        cudaError_t err =
+            cudaFuncSetAttribute(tridiag_smem_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        const long blocks = (nk + mpb - 1) / mpb;
+        if (blocks <= 0) return cudaSuccess;
+        if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+        tridiag_smem_kernel<G><<<(unsigned)blocks, G * mpb, smem, st>>>(Hp, n, nk, D, E);
+        return cudaGetLastError();
+    }
+    // matrix does not fit in shared memory: one CTA per matrix, in place on the packed scratch (L2 / HBM)
+    const size_t smem = (size_t)(6L * n + 4 * NW + 2) * 8;
     cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const long blocks = (nk + mpb - 1) / mpb;
-    if (blocks <= 0) return cudaSuccess;
-    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_kernel<G><<<(unsigned)blocks, G * mpb, smem, st>>>(Hp, n, nk, D, E, in_smem ? 1 : 0);
+    if (nk <= 0) return cudaSuccess;
+    if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_kernel<G><<<(unsigned)nk, G, smem, st>>>(Hp, n, nk, D, E, 0);
     return cudaGetLastError();
 }
 

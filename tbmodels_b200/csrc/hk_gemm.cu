@@ -8,13 +8,18 @@
 //     Hp[k, e] = sum_q Q[k, q] * W[q, e],   Q = [cos | sin] interleaved, q = 2r / 2r+1,  W = packed weights,
 // a real [n_k x 2 n_R] . [2 n_R x N^2] GEMM with half the flops of the complex product.
 //
-// One CTA computes a 128 (k-points) x BN (packed columns) tile:
-//   * Q is never materialised in HBM: each pipeline stage's 128 x 16 slice is generated on chip with
-//     sincospi(2 k.R) straight into shared memory (A operand);
-//   * W was tiled at model-create time so that each stage's 16 x (BN+4) slice is one contiguous block,
-//     fetched with a single TMA bulk copy (cp.async.bulk + mbarrier) into a 4-deep shared-memory ring;
-//   * 8 warps (4 x 2), warp tile 32 x 8*NA, mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4), accumulators in
-//     registers; padded strides (20 / BN+4 doubles) make every fragment load bank-conflict free.
+// Two kernels per chunk of k-points:
+//   hk_phase_kernel  writes Q = [cos | sin](2 pi k.R) with sincospi, once per (k, R) -- not once per column
+//                    tile -- already cut into the 128 x 16 stage tiles the GEMM consumes (XOR-swizzled rows,
+//                    so the tiles need no padding); the chunk's Q (4 KB per k-point for 251 R) stays in L2.
+//   hk_gemm_kernel   one CTA computes a 128 (k-points) x BN (packed columns) tile.  Both operands of a stage
+//                    (A: 16 KB of Q, B: the 16 x (BN+4) slice of W that was tiled at model-create time) are
+//                    contiguous blocks fetched by TMA bulk copies (cp.async.bulk + mbarrier expect_tx) into a
+//                    5-deep shared-memory ring; 8 warps (4 x 2), warp tile 32 x 8*NA, mma.sync.m8n8k4.f64
+//                    (SASS: DMMA.8x8x4), accumulators in registers; swizzle / padded stride make every
+//                    fragment load bank-conflict free.  The warps do nothing but LDS + DMMA.
+// (Round-1 history: generating Q inside the GEMM CTA cost 9x redundant sincospi work and left the tensor pipe
+//  idle during generation: 62 % DMMA utilisation, profiles/r01a_ncu_summary.txt.)
 // The reduction order over R is fixed by the tiling, so a k-point's result does not depend on its
 // position in the batch (the reference tests compare batched and per-k calls at rtol 1e-7, atol 0).
 #include "tbk_kernels.h"
@@ -26,8 +31,9 @@ namespace {
 constexpr int THREADS = 256;
 constexpr int BM = kGemmBM;
 constexpr int KC = kGemmKC;
-constexpr int SA = KC + 4;  // A row stride in doubles: (20 g + t) mod 16 distinct over a half warp
+constexpr int SA = KC;  // A row stride in doubles; column index is XOR-swizzled with (row & 3) << 2
 constexpr int STAGES = kGemmStages;
+constexpr int A_TILE = BM * SA;  // doubles per stage of Q
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -78,20 +84,47 @@ struct Cfg {
     static constexpr int A_STAGE = BM * SA;      // doubles
     static constexpr int B_STAGE = KC * SB;      // doubles
     static constexpr int STAGE = A_STAGE + B_STAGE;
-    static constexpr size_t smem_bytes(int dim) {
-        return (size_t)STAGES * STAGE * 8 + (size_t)BM * dim * 8 + STAGES * 8;
-    }
+    static constexpr size_t smem_bytes() { return (size_t)STAGES * STAGE * 8 + STAGES * 8; }
 };
+
+// Q tiles: Qt[(m_tile * kchunks + c) * A_TILE + row * 16 + (col ^ ((row & 3) << 2))], col = 2*rq (cos), 2*rq+1 (sin)
+__global__ void __launch_bounds__(THREADS)
+hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, int dim, int kchunks,
+                double* __restrict__ Qt) {
+    extern __shared__ __align__(16) double ks[];  // [BM][dim]
+    const int tid = threadIdx.x;
+    const long m_tile = blockIdx.x;
+    const long m0 = m_tile * BM;
+    for (int i = tid; i < BM * dim; i += THREADS) {
+        const long row = m0 + i / dim;
+        ks[i] = (row < nk) ? kpts[row * dim + (i % dim)] : 0.0;  // rows past the batch: k = 0, never stored by the GEMM
+    }
+    __syncthreads();
+    const int rq = tid & 7;
+    const int mq = tid >> 3;
+    for (int c = blockIdx.y; c < kchunks; c += gridDim.y) {
+        const double* rv = Rd + ((size_t)c * 8 + rq) * dim;
+        double* tile = Qt + ((size_t)m_tile * kchunks + c) * A_TILE;
+#pragma unroll
+        for (int it = 0; it < BM / 32; ++it) {
+            const int m = mq + it * 32;
+            double x = 0.0;
+            for (int d = 0; d < dim; ++d) x = fma(ks[m * dim + d], __ldg(rv + d), x);
+            double sn, cs;
+            sincospi(2.0 * x, &sn, &cs);
+            *reinterpret_cast<double2*>(tile + m * SA + ((2 * rq) ^ ((m & 3) << 2))) = make_double2(cs, sn);
+        }
+    }
+}
 
 template <int NA>
 __global__ void __launch_bounds__(THREADS, 1)
-hk_gemm_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const double* __restrict__ Wt,
-               int dim, int kchunks, int n_tiles, int NN, double* __restrict__ Hp) {
+hk_gemm_kernel(const double* __restrict__ Qt, long nk, const double* __restrict__ Wt, int kchunks, int n_tiles, int NN,
+               double* __restrict__ Hp) {
     using C = Cfg<NA>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
-    double* ks = stages + (size_t)STAGES * C::STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ks + BM * dim);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)STAGES * C::STAGE);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -106,39 +139,24 @@ hk_gemm_kernel(const double* __restrict__ kpts, long nk, const double* __restric
     const int n_tile = (int)(tile - m_tile * n_tiles);
     const long m0 = m_tile * BM;
 
-    // k tile -> shared (rows past the end of the batch evaluate k = 0 and are never stored)
-    for (int i = tid; i < BM * dim; i += THREADS) {
-        const long row = m0 + i / dim;
-        ks[i] = (row < nk) ? kpts[row * dim + (i % dim)] : 0.0;
-    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+    const double* asrc = Qt + ((size_t)m_tile * kchunks) * A_TILE;
     const double* wsrc = Wt + ((size_t)n_tile * kchunks) * C::B_STAGE;
 
-    // A-operand generator: this thread owns R vector (c*8 + rq) of the stage and rows mq, mq+32, mq+64, mq+96
-    const int rq = tid & 7;
-    const int mq = tid >> 3;
+    // one elected thread feeds the ring: two TMA bulk copies per stage, completion counted in bytes on the mbarrier
     auto produce = [&](int c) {
-        const int s = c % STAGES;
-        double* As = stages + (size_t)s * C::STAGE;
         if (tid == 0) {
+            const int s = c % STAGES;
+            double* As = stages + (size_t)s * C::STAGE;
             const uint32_t bar = smem_u32(&bars[s]);
-            mbar_expect_tx(bar, C::B_STAGE * 8);
+            mbar_expect_tx(bar, (A_TILE + C::B_STAGE) * 8);
+            tma_bulk_g2s(smem_u32(As), asrc + (size_t)c * A_TILE, A_TILE * 8, bar);
             tma_bulk_g2s(smem_u32(As + C::A_STAGE), wsrc + (size_t)c * C::B_STAGE, C::B_STAGE * 8, bar);
-        }
-        const double* rv = Rd + ((size_t)c * 8 + rq) * dim;
-#pragma unroll
-        for (int it = 0; it < BM / 32; ++it) {
-            const int m = mq + it * 32;
-            double x = 0.0;
-            for (int d = 0; d < dim; ++d) x = fma(ks[m * dim + d], __ldg(rv + d), x);
-            double sn, cs;
-            sincospi(2.0 * x, &sn, &cs);
-            *reinterpret_cast<double2*>(As + m * SA + 2 * rq) = make_double2(cs, sn);
         }
     };
 
@@ -153,18 +171,19 @@ hk_gemm_kernel(const double* __restrict__ kpts, long nk, const double* __restric
     for (int c = 0; c < kchunks; ++c) {
         const int s = c % STAGES;
         mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / STAGES) & 1));
-        __syncthreads();  // A(c) visible; every warp is done with the stage refilled below
+        __syncthreads();  // every warp is done with the stage refilled below
         if (c + STAGES - 1 < kchunks) produce(c + STAGES - 1);
 
         const double* As = stages + (size_t)s * C::STAGE;
         const double* Bs = As + C::A_STAGE;
-        const double* ap = As + (wm * 32 + g) * SA + t;
+        const double* ap = As + (wm * 32 + g) * SA;
+        const int sw = (g & 3) << 2;  // rows wm*32 + i*8 + g: (row & 3) == (g & 3)
         const double* bp = Bs + t * C::SB + wn * (8 * NA) + g;
 #pragma unroll
         for (int k4 = 0; k4 < KC / 4; ++k4) {
             double a[4], b[NA];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SA + k4 * 4];
+            for (int i = 0; i < 4; ++i) a[i] = ap[i * 8 * SA + ((k4 * 4 + t) ^ sw)];
 #pragma unroll
             for (int j = 0; j < NA; ++j) b[j] = bp[k4 * 4 * C::SB + j * 8];
 #pragma unroll
@@ -197,27 +216,41 @@ hk_gemm_kernel(const double* __restrict__ kpts, long nk, const double* __restric
 }
 
 template <int NA>
-cudaError_t launch_na(const ModelDev& md, const double* k, long nk, double* Hp, cudaStream_t st) {
+cudaError_t launch_na(const ModelDev& md, long nk, const double* Qt, double* Hp, cudaStream_t st) {
     using C = Cfg<NA>;
-    const size_t smem = C::smem_bytes(md.dim);
+    const long m_tiles = (nk + BM - 1) / BM;
+    if (m_tiles <= 0) return cudaSuccess;
+    const size_t smem = C::smem_bytes();
     cudaError_t err = cudaFuncSetAttribute(hk_gemm_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const long m_tiles = (nk + BM - 1) / BM;
     const long grid = m_tiles * md.n_tiles;
-    if (grid <= 0) return cudaSuccess;
     if (grid > 2147483647L) return cudaErrorInvalidConfiguration;
-    hk_gemm_kernel<NA><<<(unsigned)grid, THREADS, smem, st>>>(k, nk, md.Rd, md.Wt, md.dim, md.kchunks, md.n_tiles,
-                                                              md.n * md.n, Hp);
+    hk_gemm_kernel<NA><<<(unsigned)grid, THREADS, smem, st>>>(Qt, nk, md.Wt, md.kchunks, md.n_tiles, md.n * md.n, Hp);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_hk_gemm(const ModelDev& md, const double* k, long nk, double* Hp, cudaStream_t st) {
+size_t hk_gemm_q_doubles(const ModelDev& md, long nk) {
+    return (size_t)((nk + BM - 1) / BM) * (size_t)md.kchunks * A_TILE;
+}
+
+cudaError_t launch_hk_phase(const ModelDev& md, const double* k, long nk, double* Qt, cudaStream_t st) {
+    const long m_tiles = (nk + BM - 1) / BM;
+    if (m_tiles <= 0 || md.kchunks <= 0) return cudaSuccess;
+    if (m_tiles > 2147483647L) return cudaErrorInvalidConfiguration;
+    int ysplit = 1;
+    while (m_tiles * ysplit < 592 && ysplit * 2 <= md.kchunks) ysplit *= 2;  // >= 4 CTAs per SM worth of work
+    hk_phase_kernel<<<dim3((unsigned)m_tiles, (unsigned)ysplit), THREADS, (size_t)BM * md.dim * 8, st>>>(
+        k, nk, md.Rd, md.dim, md.kchunks, Qt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hk_gemm(const ModelDev& md, long nk, const double* Qt, double* Hp, cudaStream_t st) {
     switch (md.na) {
-        case 4: return launch_na<4>(md, k, nk, Hp, st);
-        case 8: return launch_na<8>(md, k, nk, Hp, st);
-        case 9: return launch_na<9>(md, k, nk, Hp, st);
+        case 4: return launch_na<4>(md, nk, Qt, Hp, st);
+        case 8: return launch_na<8>(md, nk, Qt, Hp, st);
+        case 9: return launch_na<9>(md, nk, Qt, Hp, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -5,6 +5,10 @@
 // memory, the N^2 accumulators in registers, phases come from sincospi(2 k.R) on chip.
 // Replaces Model.hamilton's Fourier loop + H += H^dagger (reference src/tbmodels/_tb_model.py:1111-1123)
 // and the per-k scipy eigvalsh loop of Model.eigenval (:1147-1150) for small N.
+// Phases: for short lattice vectors (sum_d |R_d| <= kProductMaxL1, decided on the host) e^{2 pi i k.R} is
+// formed as a product of the per-dimension factors z_d = e^{2 pi i k_d} (one sincospi per dimension per
+// k-point, then sum|R_d| - 1 complex multiplications; the loop bounds depend only on R, so they are uniform
+// across the CTA); longer vectors call sincospi(2 k.R) directly.  R = 0 costs nothing.
 //   N = 1, 2 : closed-form eigenvalues.
 //   N = 3..8 : per-thread Householder tridiagonalisation + implicit QL on a thread-strided shared-memory
 //              scratch (tbk_math.cuh), i.e. every lane works on its own matrix -- no idle lanes, no shuffles.
@@ -17,6 +21,12 @@ namespace {
 
 constexpr int TPB = 128;
 
+// doubles occupied by the R tables in shared memory: [nR][dim] doubles + [nR][dim+1] ints, rounded to 16 bytes
+__host__ __device__ inline size_t small_table_doubles(int nR, int dim) {
+    const size_t d = (size_t)nR * dim + ((size_t)nR * (dim + 1) + 1) / 2;
+    return (d + 1) & ~(size_t)1;
+}
+
 template <int N>
 constexpr int scratch_doubles() {
     return (N > 2) ? (N * N + 6 * N) : 0;  // matrix + v/w work (4N) + d, e (2N)
@@ -24,18 +34,21 @@ constexpr int scratch_doubles() {
 
 template <int N, int D>  // D = 0: run-time dimension (<= kMaxDim)
 __global__ void __launch_bounds__(TPB)
-hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const double* __restrict__ W,
-                int dim_rt, int nR, double* __restrict__ Hp, double* __restrict__ eig) {
+hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const int* __restrict__ Ri,
+                const double* __restrict__ W, int dim_rt, int nR, int use_z, double* __restrict__ Hp,
+                double* __restrict__ eig) {
     constexpr int NN = N * N;
     const int dim = D ? D : dim_rt;
     extern __shared__ __align__(16) double sm[];
     double* Ws = sm;                             // [2 nR][NN]
     double* Rs = Ws + (size_t)2 * nR * NN;       // [nR][dim]
-    double* scratch = Rs + (((size_t)nR * dim + 1) & ~(size_t)1);
+    int* Is = reinterpret_cast<int*>(Rs + (size_t)nR * dim);  // [nR][dim + 1]: R as ints, then the mode flag
+    double* scratch = Rs + small_table_doubles(nR, dim);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 2 * nR * NN; i += TPB) Ws[i] = W[i];
     for (int i = tid; i < nR * dim; i += TPB) Rs[i] = Rd[i];
+    for (int i = tid; i < nR * (dim + 1); i += TPB) Is[i] = Ri[i];
     __syncthreads();
 
     for (long kk = (long)blockIdx.x * TPB + tid; kk < nk; kk += (long)gridDim.x * TPB) {
@@ -53,13 +66,48 @@ hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restri
 #pragma unroll
         for (int e = 0; e < NN; ++e) acc[e] = 0.0;
 
-        for (int r = 0; r < nR; ++r) {
-            double x = 0.0;
+        double zr[D ? D : kMaxDim], zi[D ? D : kMaxDim];
+        if (use_z) {
 #pragma unroll
             for (int d = 0; d < (D ? D : kMaxDim); ++d)
-                if (d < dim) x = fma(kv[d], Rs[r * dim + d], x);
+                if (d < dim) sincospi(2.0 * kv[d], &zi[d], &zr[d]);
+        }
+
+        for (int r = 0; r < nR; ++r) {
             double sn, cs;
-            sincospi(2.0 * x, &sn, &cs);
+            const int* ri = Is + r * (dim + 1);
+            if (ri[dim]) {  // product of per-dimension factors (CTA-uniform control flow)
+                cs = 1.0;
+                sn = 0.0;
+                bool first = true;
+#pragma unroll
+                for (int d = 0; d < (D ? D : kMaxDim); ++d) {
+                    if (d < dim) {
+                        const int n = ri[d];
+                        if (n != 0) {
+                            const double fr = zr[d], fi = n > 0 ? zi[d] : -zi[d];
+                            const int cnt = n > 0 ? n : -n;
+                            for (int q = 0; q < cnt; ++q) {
+                                if (first) {
+                                    cs = fr;
+                                    sn = fi;
+                                    first = false;
+                                } else {
+                                    const double tr_ = cs * fr - sn * fi;
+                                    sn = fma(cs, fi, sn * fr);
+                                    cs = tr_;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                double x = 0.0;
+#pragma unroll
+                for (int d = 0; d < (D ? D : kMaxDim); ++d)
+                    if (d < dim) x = fma(kv[d], Rs[r * dim + d], x);
+                sincospi(2.0 * x, &sn, &cs);
+            }
             const double* w0 = Ws + (size_t)(2 * r) * NN;
             const double* w1 = w0 + NN;
             if (NN % 2 == 0) {
@@ -124,7 +172,8 @@ cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, 
     const long cap = (long)sms * 16;
     if (blocks > cap) blocks = cap;
     if (blocks <= 0) return cudaSuccess;
-    hk_small_kernel<N, D><<<(unsigned)blocks, TPB, smem, st>>>(k, nk, md.Rd, md.W, md.dim, md.nR, Hp, eig);
+    hk_small_kernel<N, D><<<(unsigned)blocks, TPB, smem, st>>>(k, nk, md.Rd, md.Ri, md.W, md.dim, md.nR, md.use_z, Hp,
+                                                               eig);
     return cudaGetLastError();
 }
 
@@ -143,7 +192,7 @@ cudaError_t launch_n(const ModelDev& md, const double* k, long nk, double* Hp, d
 size_t hk_small_smem_bytes(int n, int dim, int nR, int threads) {
     if (threads <= 0) threads = TPB;
     const size_t nn = (size_t)n * n;
-    size_t doubles = 2 * (size_t)nR * nn + (((size_t)nR * dim + 1) & ~(size_t)1);
+    size_t doubles = 2 * (size_t)nR * nn + small_table_doubles(nR, dim);
     if (n > 2) doubles += (nn + 6 * (size_t)n) * threads;
     return doubles * 8;
 }

@@ -49,6 +49,32 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     if (s == 123.456) out[0] = s;
 }
 
+// both at once: do DMMA and DFMA share a datapath?  (reported sum of both flop counts)
+__global__ void __launch_bounds__(256) mixed_peak_kernel(double* out, int iters, double seed) {
+    double c0[ACC], c1[ACC], f[ACC];
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) {
+        c0[i] = seed * i;
+        c1[i] = -seed * i;
+        f[i] = seed * i;
+    }
+    double a = seed + threadIdx.x * 1e-9, b = seed - threadIdx.x * 1e-9;
+    const double fa = 1.0 + seed * 1e-9, fb = seed * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ACC; ++i) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0[i]), "+d"(c1[i])
+                         : "d"(a), "d"(b));
+            f[i] = fma(f[i], fa, fb);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < ACC; ++i) s += c0[i] + c1[i] + f[i];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace
 
 double measure_fp64_peak(int kind, int iters) {
@@ -65,14 +91,16 @@ double measure_fp64_peak(int kind, int iters) {
     for (int rep = 0; rep < 4; ++rep) {
         cudaEventRecord(e0);
         if (kind == 0) dmma_peak_kernel<<<blocks, 256>>>(out, iters, 1.0);
-        else dfma_peak_kernel<<<blocks, 256>>>(out, iters, 1.0);
+        else if (kind == 1) dfma_peak_kernel<<<blocks, 256>>>(out, iters, 1.0);
+        else mixed_peak_kernel<<<blocks, 256>>>(out, iters, 1.0);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         double flops;
         if (kind == 0) flops = (double)blocks * 8 /*warps*/ * (double)iters * ACC * 512.0;   // 8x8x4 MACs x 2
-        else flops = (double)blocks * 256 * (double)iters * ACC * 2.0;
+        else if (kind == 1) flops = (double)blocks * 256 * (double)iters * ACC * 2.0;
+        else flops = (double)blocks * 8 * (double)iters * ACC * 512.0 + (double)blocks * 256 * (double)iters * ACC * 2.0;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;  // first rep is warm-up
     }

@@ -79,12 +79,14 @@ struct tbk_model {
     ModelDev md;
     double* dRd = nullptr;
     double* dW = nullptr;
+    int* dRi = nullptr;
     double* dWt = nullptr;
     double* dPos = nullptr;
     int* dFail = nullptr;
     // scratch for the device-pointer entry points
     double* wsH = nullptr;  // [chunk][n*n] packed H(k)
     double* wsE = nullptr;  // [chunk][n]   sub-diagonals
+    double* wsQ = nullptr;  // phase tiles of the chunk (GEMM path only)
     long chunk = 0;
     size_t ws_bytes = 0;
     size_t model_bytes = 0;
@@ -102,8 +104,8 @@ struct tbk_model {
         int cls;
     };
     std::vector<ProfRec> prof;
-    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
-    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0};
+    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
+    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
 };
 
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the launch stream.
@@ -131,7 +133,7 @@ long pick_chunk(const tbk_model* m) {
         const long v = atol(s);
         if (v > 0) budget_mb = (size_t)v;
     }
-    const size_t per_k = ((size_t)m->md.n * m->md.n + m->md.n) * 8;
+    const size_t per_k = ((size_t)m->md.n * m->md.n + m->md.n + (m->md.small_ok ? 0 : (size_t)m->md.kchunks * kGemmKC)) * 8;
     long chunk = (long)((budget_mb << 20) / per_k);
     if (chunk < 1) chunk = 1;
     if (chunk > (1L << 22)) chunk = 1L << 22;
@@ -144,15 +146,21 @@ int ensure_workspace(tbk_model* m, long nk) {
     if (want <= m->chunk) return TBK_OK;
     if (m->wsH) cudaFree(m->wsH);
     if (m->wsE) cudaFree(m->wsE);
-    m->wsH = m->wsE = nullptr;
+    if (m->wsQ) cudaFree(m->wsQ);
+    m->wsH = m->wsE = m->wsQ = nullptr;
     m->chunk = 0;
     m->ws_bytes = 0;
     const size_t hb = (size_t)want * m->md.n * m->md.n * 8;
     const size_t eb = (size_t)want * m->md.n * 8;
     CU(cudaMalloc(&m->wsH, hb));
     CU(cudaMalloc(&m->wsE, eb));
+    size_t qb = 0;
+    if (!m->md.small_ok) {
+        qb = std::max<size_t>(hk_gemm_q_doubles(m->md, want) * 8, 16);
+        CU(cudaMalloc(&m->wsQ, qb));
+    }
     m->chunk = want;
-    m->ws_bytes = hb + eb;
+    m->ws_bytes = hb + eb + qb;
     return TBK_OK;
 }
 
@@ -167,7 +175,8 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
     for (long c0 = 0; c0 < nk; c0 += m->chunk) {
         const long cn = std::min(m->chunk, nk - c0);
         double* D = out + c0 * md.n;
-        LAUNCH(0, st, launch_hk_gemm(md, k + c0 * md.dim, cn, m->wsH, st));
+        LAUNCH(5, st, launch_hk_phase(md, k + c0 * md.dim, cn, m->wsQ, st));
+        LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
         LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
         LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
     }
@@ -183,7 +192,10 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
         const long cn = std::min(m->chunk, nk - c0);
         const double* kc = k + c0 * md.dim;
         if (md.small_ok) LAUNCH(1, st, launch_hk_small(md, kc, cn, m->wsH, nullptr, st));
-        else LAUNCH(0, st, launch_hk_gemm(md, kc, cn, m->wsH, st));
+        else {
+            LAUNCH(5, st, launch_hk_phase(md, kc, cn, m->wsQ, st));
+            LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
+        }
         LAUNCH(2, st, launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
     }
     return TBK_OK;
@@ -346,6 +358,21 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
         CUB(cudaMemcpy(m->dW, W.data(), W.size() * 8, cudaMemcpyHostToDevice));
         md.W = m->dW;
         m->model_bytes += W.size() * 8;
+        std::vector<int> Ri((size_t)std::max(n_R, 1) * (dim + 1), 0);
+        for (int r = 0; r < n_R; ++r) {
+            long l1 = 0;
+            for (int d = 0; d < dim; ++d) {
+                const int v = R[(size_t)r * dim + d];
+                Ri[(size_t)r * (dim + 1) + d] = v;
+                l1 += v < 0 ? -(long)v : v;
+            }
+            const int product = l1 <= kProductMaxL1 ? 1 : 0;
+            Ri[(size_t)r * (dim + 1) + dim] = product;
+            if (product && l1 > 0) md.use_z = 1;
+        }
+        CUB(cudaMalloc(&m->dRi, Ri.size() * sizeof(int)));
+        CUB(cudaMemcpy(m->dRi, Ri.data(), Ri.size() * sizeof(int), cudaMemcpyHostToDevice));
+        md.Ri = m->dRi;
     } else {
         // choose the column-tile width that wastes the fewest padded columns (ties -> wider)
         const int cands[3] = {4, 8, 9};
@@ -392,11 +419,13 @@ int tbk_model_destroy(tbk_model* m) {
     cudaDeviceSynchronize();
     cudaFree(m->dRd);
     cudaFree(m->dW);
+    cudaFree(m->dRi);
     cudaFree(m->dWt);
     cudaFree(m->dPos);
     cudaFree(m->dFail);
     cudaFree(m->wsH);
     cudaFree(m->wsE);
+    cudaFree(m->wsQ);
     for (int b = 0; b < 2; ++b) {
         cudaFree(m->hk[b]);
         cudaFree(m->ho[b]);

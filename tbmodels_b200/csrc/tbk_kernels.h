@@ -9,7 +9,8 @@ constexpr int kMaxDim = 8;        // largest lattice dimension supported on the 
 constexpr int kSmallMaxN = 8;     // thread-per-k fused kernel handles N <= 8 (if its tables fit in smem)
 constexpr int kGemmBM = 128;      // k-points per CTA tile of the H(k) GEMM
 constexpr int kGemmKC = 16;       // K (= 2 * R-vectors) per pipeline stage
-constexpr int kGemmStages = 4;
+constexpr int kGemmStages = 5;
+constexpr int kProductMaxL1 = 6;  // fused path: sum_d |R_d| up to which a phase is built by complex products
 
 // Device-resident packed model (see DESIGN.md "Data layout in HBM").
 struct ModelDev {
@@ -18,6 +19,8 @@ struct ModelDev {
     int nR = 0;       // stored (half-set) R vectors that are non-zero matrices
     int nRpad = 0;    // nR rounded up to a multiple of 8 (padding rows: R = 0, zero weights)
     const double* Rd = nullptr;   // [nRpad][dim]   R vectors as doubles
+    const int* Ri = nullptr;      // [nR][dim + 1]  fused path: R as ints + flag "phase = product of per-dimension factors"
+    int use_z = 0;                // fused path: any R uses the product form
     const double* W = nullptr;    // [2*nR][n*n]    Hermitian-split weights, row 2r = hp(T_r + T_r^H), row 2r+1 = hp(i(T_r - T_r^H))
     const double* Wt = nullptr;   // tiled copy of W for the GEMM: [n_tiles][kchunks][kGemmKC][bn + 4]
     const double* pos = nullptr;  // [n][dim]
@@ -28,7 +31,11 @@ struct ModelDev {
 };
 
 // H(k) build on the FP64 tensor cores: Hp[k][0..n*n) (packed Hermitian, see tbk_math.cuh).
-cudaError_t launch_hk_gemm(const ModelDev& md, const double* k, long nk, double* Hp, cudaStream_t st);
+// Two launches per chunk: launch_hk_phase fills Qt (hk_gemm_q_doubles(md, nk) doubles of scratch) with the
+// [cos | sin] tiles, launch_hk_gemm contracts them with the tiled weights.
+cudaError_t launch_hk_phase(const ModelDev& md, const double* k, long nk, double* Qt, cudaStream_t st);
+cudaError_t launch_hk_gemm(const ModelDev& md, long nk, const double* Qt, double* Hp, cudaStream_t st);
+size_t hk_gemm_q_doubles(const ModelDev& md, long nk);
 // Fused thread-per-k-point path for N <= 8: writes packed H (if Hp) and/or ascending eigenvalues (if eig).
 cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st);
 size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);

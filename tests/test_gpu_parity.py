@@ -239,25 +239,27 @@ def test_mutation_invalidates_device_copy(tbk):
     assert_eig_close(after, np.array(orc.eigenval(p2.R, p2.hop, p2.pos, k)), "mutated")
 
 
+class Model:  # stand-in with the attributes the hot path reads (the reference class is not on the GPU box)
+    def __init__(self, packed):
+        import tbmodels_b200
+
+        self.hop = tbmodels_b200.hop_dict(packed)
+        self.pos = packed.pos.copy()
+        self.size = packed.size
+        self.dim = packed.dim
+
+    def hamilton(self, k, convention=2):
+        raise AssertionError("numpy path must not run")
+
+    def eigenval(self, k):
+        raise AssertionError("numpy path must not run")
+
+
 def test_patch_model_class(tbk):
     """install() swaps hamilton/eigenval on a Model class; the instance stays picklable."""
     import pickle
 
     orc = _oracle()
-
-    class Model:  # stand-in with the attributes the hot path reads (the reference class is not on the GPU box)
-        def __init__(self, packed):
-            self.hop = tbk.hop_dict(packed)
-            self.pos = packed.pos.copy()
-            self.size = packed.size
-            self.dim = packed.dim
-
-        def hamilton(self, k, convention=2):
-            raise AssertionError("numpy path must not run")
-
-        def eigenval(self, k):
-            raise AssertionError("numpy path must not run")
-
     p = packed_from(load_golden("silicon.npz"))
     tbk.install(Model)
     try:
