@@ -55,6 +55,18 @@ ql_global_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk,
 
 }  // namespace
 
+long ql_wave_matrices(int n) {
+    // matrices one full wave of the shared-memory QL kernel processes (0: not applicable)
+    const size_t smem = (size_t)2 * n * LDS * 8;
+    if (n <= 0 || smem > 210 * 1024) return 0;
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(ql_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_smem_kernel, TPB, smem) != cudaSuccess) return 0;
+    return (long)sms * per_sm * TPB;
+}
+
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st) {
     if (nk <= 0 || n <= 0) return cudaSuccess;
     const long blocks = (nk + TPB - 1) / TPB;

@@ -225,13 +225,22 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     double* es = ds + N;
     double* red = es + N;
 
-    {   // load + interleave: real plane [tri(i)+j], imag plane [ntri + trs(i)+j]
+    {   // load + interleave.  The real plane has the same packed order as the complex rows (flat copy); an imag
+        // plane entry f = trs(i) + j lands at f + i.  Flat loops keep many independent loads in flight.
         const double* src = Hp + kk * NN;
         const double* srci = src + ntri;
-        for (int i = 0; i < N; ++i) {
-            const int ro = itri(i), io = ro - i;  // trs(i) = tri(i) - i
-            for (int j = t; j <= i; j += G) A[ro + j] = make_double2(src[ro + j], j < i ? srci[io + j] : 0.0);
+        double* Ad = reinterpret_cast<double*>(A);
+#pragma unroll 4
+        for (int e = t; e < ntri; e += G) Ad[2 * e] = src[e];
+        const int nim = ntri - N;
+#pragma unroll 4
+        for (int f = t; f < nim; f += G) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)f)) * 0.5f);  // row of strict-lower entry f (approx.)
+            while ((i * (i - 1)) / 2 > f) --i;
+            while ((i * (i + 1)) / 2 <= f) ++i;
+            Ad[2 * (f + i) + 1] = srci[f];
         }
+        for (int i = t; i < N; i += G) Ad[2 * (itri(i) + i) + 1] = 0.0;
     }
     group_sync<G>(group);
 
@@ -242,7 +251,9 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
         // --- reflector from column j ---
         const double2 alpha = A[itri(r0) + j];
         double xn = 0.0, dummy = 0.0;
-        for (int a = 1 + t; a < m; a += G) {
+        const double2 x0 = (t < m) ? A[itri(r0 + t) + j] : make_double2(0.0, 0.0);  // first row of this thread
+        if (t >= 1 && t < m) xn = x0.x * x0.x + x0.y * x0.y;
+        for (int a = t + G; a < m; a += G) {
             const double2 x = A[itri(r0 + a) + j];
             xn += x.x * x.x + x.y * x.y;
         }
@@ -252,34 +263,48 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
         if (t == 0) {
             ds[j] = A[itri(j) + j].x;
             es[j] = beta;
+            V[0] = make_double2(1.0, 0.0);
+        } else if (t < m) {
+            V[t] = make_double2(x0.x * sr - x0.y * si, x0.x * si + x0.y * sr);
         }
-        for (int a = t; a < m; a += G) {
-            if (a == 0) {
-                V[0] = make_double2(1.0, 0.0);
-            } else {
-                const double2 x = A[itri(r0 + a) + j];
-                V[a] = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
-            }
+        for (int a = t + G; a < m; a += G) {
+            const double2 x = A[itri(r0 + a) + j];
+            V[a] = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
         }
         group_sync<G>(group);
         // --- p = tau * A22 v (row part from the own packed row, column part conjugated), dot = p^H v ---
+        // two independent accumulator pairs (even / odd columns) halve the DFMA dependency chains
         double dr = 0.0, di = 0.0;
         const int c2_0 = itri(r0);
         for (int a = t; a < m; a += G) {
             const int I = r0 + a;
             const int rowI = itri(I) + r0;
             int c2 = c2_0 + I;  // tri(J) + I for J = r0
-            double sumr = 0.0, sumi = 0.0;
-#pragma unroll 4
-            for (int b = 0; b < m; ++b) {
-                const bool left = b < a;
-                const double2 z = A[left ? rowI + b : c2];
-                const double zi = left ? z.y : -z.y;
-                const double2 v = V[b];
-                sumr = fma(z.x, v.x, fma(-zi, v.y, sumr));
-                sumi = fma(z.x, v.y, fma(zi, v.x, sumi));
-                c2 += r0 + b + 1;
+            double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
+            int b = 0;
+            for (; b + 1 < m; b += 2) {
+                const bool l0 = b < a, l1 = b + 1 < a;
+                const int c2b = c2 + r0 + b + 1;
+                const double2 z0 = A[l0 ? rowI + b : c2];
+                const double2 z1 = A[l1 ? rowI + b + 1 : c2b];
+                const double2 v0 = V[b], v1 = V[b + 1];
+                const double y0 = l0 ? z0.y : -z0.y;
+                const double y1 = l1 ? z1.y : -z1.y;
+                sr0 = fma(z0.x, v0.x, fma(-y0, v0.y, sr0));
+                si0 = fma(z0.x, v0.y, fma(y0, v0.x, si0));
+                sr1 = fma(z1.x, v1.x, fma(-y1, v1.y, sr1));
+                si1 = fma(z1.x, v1.y, fma(y1, v1.x, si1));
+                c2 = c2b + r0 + b + 2;
             }
+            if (b < m) {
+                const bool l0 = b < a;
+                const double2 z0 = A[l0 ? rowI + b : c2];
+                const double2 v0 = V[b];
+                const double y0 = l0 ? z0.y : -z0.y;
+                sr0 = fma(z0.x, v0.x, fma(-y0, v0.y, sr0));
+                si0 = fma(z0.x, v0.y, fma(y0, v0.x, si0));
+            }
+            const double sumr = sr0 + sr1, sumi = si0 + si1;
             const double pr = tr * sumr - ti * sumi;
             const double pi = tr * sumi + ti * sumr;
             P[a] = make_double2(pr, pi);

@@ -5,10 +5,9 @@
 // memory, the N^2 accumulators in registers, phases come from sincospi(2 k.R) on chip.
 // Replaces Model.hamilton's Fourier loop + H += H^dagger (reference src/tbmodels/_tb_model.py:1111-1123)
 // and the per-k scipy eigvalsh loop of Model.eigenval (:1147-1150) for small N.
-// Phases: for short lattice vectors (sum_d |R_d| <= kProductMaxL1, decided on the host) e^{2 pi i k.R} is
-// formed as a product of the per-dimension factors z_d = e^{2 pi i k_d} (one sincospi per dimension per
-// k-point, then sum|R_d| - 1 complex multiplications; the loop bounds depend only on R, so they are uniform
-// across the CTA); longer vectors call sincospi(2 k.R) directly.  R = 0 costs nothing.
+// Phases: for nearest-cell lattice vectors (all |R_d| <= 1, flagged on the host) e^{2 pi i k.R} is the product
+// of per-dimension factors  f_d = 1, z_d or conj(z_d)  with z_d = e^{2 pi i k_d}  (one sincospi per dimension
+// per k-point, then D - 1 complex multiplications per R, branch free); longer vectors call sincospi(2 k.R).
 //   N = 1, 2 : closed-form eigenvalues.
 //   N = 3..8 : per-thread Householder tridiagonalisation + implicit QL on a thread-strided shared-memory
 //              scratch (tbk_math.cuh), i.e. every lane works on its own matrix -- no idle lanes, no shuffles.
@@ -21,15 +20,29 @@ namespace {
 
 constexpr int TPB = 128;
 
-// doubles occupied by the R tables in shared memory: [nR][dim] doubles + [nR][dim+1] ints, rounded to 16 bytes
+// doubles occupied by the R tables in shared memory: [nR][dim] doubles + [nR] int flags, rounded to 16 bytes
 __host__ __device__ inline size_t small_table_doubles(int nR, int dim) {
-    const size_t d = (size_t)nR * dim + ((size_t)nR * (dim + 1) + 1) / 2;
+    const size_t d = (size_t)nR * dim + ((size_t)nR + 1) / 2;
     return (d + 1) & ~(size_t)1;
 }
 
 template <int N>
 constexpr int scratch_doubles() {
     return (N > 2) ? (N * N + 6 * N) : 0;  // matrix + v/w work (4N) + d, e (2N)
+}
+
+template <int D>
+__device__ __forceinline__ void load_kpoint(double (&kn)[D ? D : kMaxDim], const double* __restrict__ kpts, long idx,
+                                            long nk, int dim) {
+    if (idx >= nk) return;
+    if (D == 2) {
+        const double2 v = *reinterpret_cast<const double2*>(kpts + idx * 2);
+        kn[0] = v.x;
+        kn[D > 1 ? 1 : 0] = v.y;
+    } else {
+#pragma unroll
+        for (int d = 0; d < (D ? D : kMaxDim); ++d) kn[d] = (d < dim) ? kpts[idx * dim + d] : 0.0;
+    }
 }
 
 template <int N, int D>  // D = 0: run-time dimension (<= kMaxDim)
@@ -42,25 +55,24 @@ hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restri
     extern __shared__ __align__(16) double sm[];
     double* Ws = sm;                             // [2 nR][NN]
     double* Rs = Ws + (size_t)2 * nR * NN;       // [nR][dim]
-    int* Is = reinterpret_cast<int*>(Rs + (size_t)nR * dim);  // [nR][dim + 1]: R as ints, then the mode flag
+    int* Is = reinterpret_cast<int*>(Rs + (size_t)nR * dim);  // [nR] flag: phase = product of per-dimension factors
     double* scratch = Rs + small_table_doubles(nR, dim);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 2 * nR * NN; i += TPB) Ws[i] = W[i];
     for (int i = tid; i < nR * dim; i += TPB) Rs[i] = Rd[i];
-    for (int i = tid; i < nR * (dim + 1); i += TPB) Is[i] = Ri[i];
+    for (int i = tid; i < nR; i += TPB) Is[i] = Ri[i];
     __syncthreads();
 
-    for (long kk = (long)blockIdx.x * TPB + tid; kk < nk; kk += (long)gridDim.x * TPB) {
+    const long stride = (long)gridDim.x * TPB;
+    long kk = (long)blockIdx.x * TPB + tid;
+    double kn[D ? D : kMaxDim];  // software prefetch: the next k-point is in flight while this one is evaluated
+    load_kpoint<D>(kn, kpts, kk, nk, dim);
+    for (; kk < nk; kk += stride) {
         double kv[D ? D : kMaxDim];
-        if (D == 2) {
-            const double2 v = *reinterpret_cast<const double2*>(kpts + kk * 2);
-            kv[0] = v.x;
-            kv[D > 1 ? 1 : 0] = v.y;
-        } else {
 #pragma unroll
-            for (int d = 0; d < (D ? D : kMaxDim); ++d) kv[d] = (d < dim) ? kpts[kk * dim + d] : 0.0;
-        }
+        for (int d = 0; d < (D ? D : kMaxDim); ++d) kv[d] = kn[d];
+        load_kpoint<D>(kn, kpts, kk + stride, nk, dim);
 
         double acc[NN];
 #pragma unroll
@@ -75,30 +87,19 @@ hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restri
 
         for (int r = 0; r < nR; ++r) {
             double sn, cs;
-            const int* ri = Is + r * (dim + 1);
-            if (ri[dim]) {  // product of per-dimension factors (CTA-uniform control flow)
-                cs = 1.0;
-                sn = 0.0;
-                bool first = true;
+            if (Is[r]) {  // CTA-uniform: all |R_d| <= 1, so R_d itself is the sign / presence of the factor
+                const double r0_ = Rs[r * dim];
+                cs = (r0_ != 0.0) ? zr[0] : 1.0;
+                sn = r0_ * zi[0];
 #pragma unroll
-                for (int d = 0; d < (D ? D : kMaxDim); ++d) {
+                for (int d = 1; d < (D ? D : kMaxDim); ++d) {
                     if (d < dim) {
-                        const int n = ri[d];
-                        if (n != 0) {
-                            const double fr = zr[d], fi = n > 0 ? zi[d] : -zi[d];
-                            const int cnt = n > 0 ? n : -n;
-                            for (int q = 0; q < cnt; ++q) {
-                                if (first) {
-                                    cs = fr;
-                                    sn = fi;
-                                    first = false;
-                                } else {
-                                    const double tr_ = cs * fr - sn * fi;
-                                    sn = fma(cs, fi, sn * fr);
-                                    cs = tr_;
-                                }
-                            }
-                        }
+                        const double rd = Rs[r * dim + d];
+                        const double fr = (rd != 0.0) ? zr[d] : 1.0;
+                        const double fi = rd * zi[d];
+                        const double tr_ = cs * fr - sn * fi;
+                        sn = fma(cs, fi, sn * fr);
+                        cs = tr_;
                     }
                 }
             } else {

@@ -128,7 +128,7 @@ struct tbk_model {
 namespace {
 
 long pick_chunk(const tbk_model* m) {
-    size_t budget_mb = 1024;
+    size_t budget_mb = 2048;
     if (const char* s = getenv("TBK_WORKSPACE_MB")) {
         const long v = atol(s);
         if (v > 0) budget_mb = (size_t)v;
@@ -138,6 +138,11 @@ long pick_chunk(const tbk_model* m) {
     if (chunk < 1) chunk = 1;
     if (chunk > (1L << 22)) chunk = 1L << 22;
     if (chunk >= 1024) chunk &= ~127L;  // whole GEMM row tiles
+    if (!m->md.small_ok) {
+        // whole waves of the thread-per-matrix QL kernel (its threads all run equally long: a partial wave idles SMs)
+        const long wave = ql_wave_matrices(m->md.n);
+        if (wave > 0 && chunk > wave) chunk -= chunk % wave;
+    }
     return chunk;
 }
 
@@ -358,17 +363,15 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
         CUB(cudaMemcpy(m->dW, W.data(), W.size() * 8, cudaMemcpyHostToDevice));
         md.W = m->dW;
         m->model_bytes += W.size() * 8;
-        std::vector<int> Ri((size_t)std::max(n_R, 1) * (dim + 1), 0);
+        std::vector<int> Ri((size_t)std::max(n_R, 1), 0);
         for (int r = 0; r < n_R; ++r) {
-            long l1 = 0;
+            bool unit = true;
             for (int d = 0; d < dim; ++d) {
                 const int v = R[(size_t)r * dim + d];
-                Ri[(size_t)r * (dim + 1) + d] = v;
-                l1 += v < 0 ? -(long)v : v;
+                if (v < -1 || v > 1) unit = false;
             }
-            const int product = l1 <= kProductMaxL1 ? 1 : 0;
-            Ri[(size_t)r * (dim + 1) + dim] = product;
-            if (product && l1 > 0) md.use_z = 1;
+            Ri[r] = unit ? 1 : 0;
+            if (unit) md.use_z = 1;
         }
         CUB(cudaMalloc(&m->dRi, Ri.size() * sizeof(int)));
         CUB(cudaMemcpy(m->dRi, Ri.data(), Ri.size() * sizeof(int), cudaMemcpyHostToDevice));

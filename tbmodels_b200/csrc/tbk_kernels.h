@@ -10,7 +10,6 @@ constexpr int kSmallMaxN = 8;     // thread-per-k fused kernel handles N <= 8 (i
 constexpr int kGemmBM = 128;      // k-points per CTA tile of the H(k) GEMM
 constexpr int kGemmKC = 16;       // K (= 2 * R-vectors) per pipeline stage
 constexpr int kGemmStages = 5;
-constexpr int kProductMaxL1 = 6;  // fused path: sum_d |R_d| up to which a phase is built by complex products
 
 // Device-resident packed model (see DESIGN.md "Data layout in HBM").
 struct ModelDev {
@@ -19,7 +18,7 @@ struct ModelDev {
     int nR = 0;       // stored (half-set) R vectors that are non-zero matrices
     int nRpad = 0;    // nR rounded up to a multiple of 8 (padding rows: R = 0, zero weights)
     const double* Rd = nullptr;   // [nRpad][dim]   R vectors as doubles
-    const int* Ri = nullptr;      // [nR][dim + 1]  fused path: R as ints + flag "phase = product of per-dimension factors"
+    const int* Ri = nullptr;      // [nR]  fused path: 1 = all |R_d| <= 1, phase is a product of per-dimension factors
     int use_z = 0;                // fused path: any R uses the product form
     const double* W = nullptr;    // [2*nR][n*n]    Hermitian-split weights, row 2r = hp(T_r + T_r^H), row 2r+1 = hp(i(T_r - T_r^H))
     const double* Wt = nullptr;   // tiled copy of W for the GEMM: [n_tiles][kchunks][kGemmKC][bn + 4]
@@ -46,6 +45,8 @@ cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp,
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
 // Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st);
+// Matrices per full wave of the QL kernel on the current device (chunks are sized in whole waves); 0 if n/a.
+long ql_wave_matrices(int n);
 
 // FP64 peak micro-benchmarks (bench.py roofline denominators). Return achieved TFLOP/s, or < 0 on error.
 double measure_fp64_peak(int kind /*0 = DMMA, 1 = DFMA*/, int iters);

@@ -163,15 +163,21 @@ TBK_HD int tridiag_ql(int n, double* d, double* e, long sd) {
                     const double ei = e[i * sd];
                     double f = s * ei;
                     const double b = c * ei;
-                    r = sqrt(f * f + g * g);
-                    e[(i + 1) * sd] = r;
-                    if (r == 0.0) {
+                    const double h = f * f + g * g;
+                    if (h == 0.0) {
+                        e[(i + 1) * sd] = 0.0;
                         d[(i + 1) * sd] -= p;
                         e[m * sd] = 0.0;
                         underflow = true;
                         break;
                     }
-                    const double rinv = 1.0 / r;
+#if defined(__CUDA_ARCH__)
+                    const double rinv = rsqrt(h);  // one reciprocal square root instead of sqrt + divide
+#else
+                    const double rinv = 1.0 / sqrt(h);
+#endif
+                    r = h * rinv;
+                    e[(i + 1) * sd] = r;
                     s = f * rinv;
                     c = g * rinv;
                     g = d[(i + 1) * sd] - p;
