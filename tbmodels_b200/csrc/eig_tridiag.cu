@@ -10,6 +10,8 @@
 // chunk).  Every group executes exactly the same instruction sequence (no data-dependent early exits), so
 // sub-warp groups can share a warp and use __syncwarp().  Outputs: D[k][0..N) diagonal, E[k][0..N-1)
 // sub-diagonal, consumed by eig_ql.cu.
+#include <cstdlib>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -353,6 +355,233 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core variant for 21 <= N <= 64: one warp per matrix, the FULL Hermitian matrix (both triangles,
+// interleaved complex, odd row stride) in shared memory.
+//   * the Hermitian matrix-vector product reads plain rows (no triangle selects): LDS.128 + 4 DFMA per element;
+//   * the rank-2 update  A -= v w^H + w v^H  runs on the FP64 tensor cores.  Per 8x8 block it is a real product
+//     with K = 4:   Re(A) -= [vr vi wr wi] . [wr wi vr vi]^T,   Im(A) -= [vi -vr wi -wr] . [wr wi vr vi]^T,
+//     i.e. exactly one mma.sync.m8n8k4.f64 (DMMA.8x8x4) per plane per block, accumulating in place on the
+//     C fragments loaded from / stored to shared memory (lower blocks only; each off-diagonal block is mirrored
+//     with a conjugate store so the full matrix stays Hermitian for the next matrix-vector product).
+//   v and w live in one table XY[row] = (vr, vi, wr, wi) that is zero outside the trailing sub-matrix, so
+//   blocks straddling its border need no masking.
+// Same arithmetic as the scalar kernels up to the summation order inside the 4-term block products.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_acc(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct MmaLayout {
+    int N, NB, S;          // size, 8x8 blocks per dimension, row stride in double2 (odd)
+    int as_words;          // N * S
+    int per_matrix;        // double2 units per matrix
+    __host__ __device__ explicit MmaLayout(int n) {
+        N = n;
+        NB = (n + 7) / 8;
+        S = n | 1;
+        as_words = n * S;
+        per_matrix = as_words + 2 * NB * 8 /*XY*/ + n /*ds, es*/ + 2 /*pad*/;
+    }
+};
+
+__global__ void __launch_bounds__(TPB)
+tridiag_mma_kernel(const double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    extern __shared__ __align__(16) double2 sm2[];
+    const MmaLayout L(N);
+    const int MPB = blockDim.x >> 5;
+    const int group = threadIdx.x >> 5;
+    const int t = threadIdx.x & 31;
+    const int g = t >> 2, tq = t & 3;
+    const int S = L.S, NB = L.NB;
+    const int ntri = itri(N);
+    const long NN = (long)N * N;
+
+    const long kidx = (long)blockIdx.x * MPB + group;
+    const bool valid = kidx < nk;
+    const long kk = valid ? kidx : nk - 1;  // idle warps shadow the last matrix and store nothing
+
+    double2* As = sm2 + (size_t)group * L.per_matrix;
+    double2* XY2 = As + L.as_words;                          // row i: XY2[2i] = v_i, XY2[2i+1] = w_i
+    double* XY = reinterpret_cast<double*>(XY2);             // row i: (vr, vi, wr, wi)
+    double* ds = reinterpret_cast<double*>(XY2 + 2 * NB * 8);
+    double* es = ds + N;
+
+    {   // load the packed planes and mirror them into the full matrix
+        const double* src = Hp + kk * NN;
+        const double* srci = src + ntri;
+        double* Ad = reinterpret_cast<double*>(As);
+#pragma unroll 4
+        for (int e = t; e < ntri; e += 32) {
+            int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while (itri(i) > e) --i;
+            while (itri(i + 1) <= e) ++i;
+            const int j = e - itri(i);
+            const double v = src[e];
+            Ad[2 * (i * S + j)] = v;
+            Ad[2 * (j * S + i)] = v;
+        }
+        const int nim = ntri - N;
+#pragma unroll 4
+        for (int f = t; f < nim; f += 32) {
+            int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)f)) * 0.5f);
+            while ((i * (i - 1)) / 2 > f) --i;
+            while ((i * (i + 1)) / 2 <= f) ++i;
+            const int j = f - (i * (i - 1)) / 2;
+            const double v = srci[f];
+            Ad[2 * (i * S + j) + 1] = v;
+            Ad[2 * (j * S + i) + 1] = -v;
+        }
+        for (int i = t; i < N; i += 32) Ad[2 * (i * S + i) + 1] = 0.0;
+        for (int i = t; i < 2 * NB * 8; i += 32) XY2[i] = make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+
+    for (int j = 0; j < N - 1; ++j) {
+        const int r0 = j + 1;
+        // --- reflector from column j (rows r0 .. N-1); this lane owns rows r0 + t, r0 + t + 32 ---
+        const double2 alpha = As[r0 * S + j];
+        const int i0 = r0 + t, i1 = i0 + 32;
+        const double2 x0 = (i0 < N) ? As[i0 * S + j] : make_double2(0.0, 0.0);
+        const double2 x1 = (i1 < N) ? As[i1 * S + j] : make_double2(0.0, 0.0);
+        double xn = x1.x * x1.x + x1.y * x1.y;
+        if (t >= 1) xn += x0.x * x0.x + x0.y * x0.y;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) xn += __shfl_xor_sync(0xffffffffu, xn, off);
+        double beta, tr, ti, sr, si;
+        householder_gen(alpha.x, alpha.y, xn, beta, tr, ti, sr, si);
+        if (t == 0) {
+            ds[j] = As[j * S + j].x;
+            es[j] = beta;
+            XY2[2 * j] = make_double2(0.0, 0.0);      // row j leaves the trailing block: v_j = w_j = 0
+            XY2[2 * j + 1] = make_double2(0.0, 0.0);
+            XY2[2 * r0] = make_double2(1.0, 0.0);
+        } else if (i0 < N) {
+            XY2[2 * i0] = make_double2(x0.x * sr - x0.y * si, x0.x * si + x0.y * sr);
+        }
+        if (i1 < N) XY2[2 * i1] = make_double2(x1.x * sr - x1.y * si, x1.x * si + x1.y * sr);
+        __syncwarp();
+        // --- p = tau * A22 v (plain rows of the full matrix), dot = p^H v ---
+        double dr = 0.0, di = 0.0;
+        double2 pv[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 32 * q;
+            pv[q] = make_double2(0.0, 0.0);
+            if (i < N) {
+                const double2* row = As + i * S;
+                double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
+                int b = r0;
+#pragma unroll 2
+                for (; b + 1 < N; b += 2) {
+                    const double2 z0 = row[b], z1 = row[b + 1];
+                    const double2 v0 = XY2[2 * b], v1 = XY2[2 * b + 2];
+                    sr0 = fma(z0.x, v0.x, fma(-z0.y, v0.y, sr0));
+                    si0 = fma(z0.x, v0.y, fma(z0.y, v0.x, si0));
+                    sr1 = fma(z1.x, v1.x, fma(-z1.y, v1.y, sr1));
+                    si1 = fma(z1.x, v1.y, fma(z1.y, v1.x, si1));
+                }
+                if (b < N) {
+                    const double2 z0 = row[b];
+                    const double2 v0 = XY2[2 * b];
+                    sr0 = fma(z0.x, v0.x, fma(-z0.y, v0.y, sr0));
+                    si0 = fma(z0.x, v0.y, fma(z0.y, v0.x, si0));
+                }
+                const double sumr = sr0 + sr1, sumi = si0 + si1;
+                const double pr = tr * sumr - ti * sumi;
+                const double pi = tr * sumi + ti * sumr;
+                pv[q] = make_double2(pr, pi);
+                const double2 va = XY2[2 * i];
+                dr += pr * va.x + pi * va.y;
+                di += pr * va.y - pi * va.x;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            dr += __shfl_xor_sync(0xffffffffu, dr, off);
+            di += __shfl_xor_sync(0xffffffffu, di, off);
+        }
+        const double alr = -0.5 * (tr * dr - ti * di);
+        const double ali = -0.5 * (tr * di + ti * dr);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = i0 + 32 * q;
+            if (i < N) {
+                const double2 v = XY2[2 * i];
+                XY2[2 * i + 1] = make_double2(pv[q].x + alr * v.x - ali * v.y, pv[q].y + alr * v.y + ali * v.x);
+            }
+        }
+        __syncwarp();
+        // --- A -= v w^H + w v^H on the tensor cores, lower 8x8 blocks that touch the trailing sub-matrix ---
+        const int qb = r0 >> 3;
+        const double sgn = (tq & 1) ? 1.0 : -1.0;
+        for (int I = qb; I < NB; ++I) {
+            const int row = I * 8 + g;
+            const double xr = -XY[row * 4 + tq];                 // -(vr, vi, wr, wi)[tq]
+            const double xi = sgn * XY[row * 4 + (tq ^ 1)];      // (-vi, vr, -wi, wr)[tq]
+            const bool row_ok = row < N;
+            for (int J = qb; J <= I; ++J) {
+                const double y = XY[(J * 8 + g) * 4 + (tq ^ 2)];  // (wr, wi, vr, vi)[tq] of column-block row g
+                const int c0 = J * 8 + 2 * tq;
+                const bool ok0 = row_ok && c0 < N, ok1 = row_ok && c0 + 1 < N;
+                const double2 z0 = ok0 ? As[row * S + c0] : make_double2(0.0, 0.0);
+                const double2 z1 = ok1 ? As[row * S + c0 + 1] : make_double2(0.0, 0.0);
+                double cre0 = z0.x, cre1 = z1.x, cim0 = z0.y, cim1 = z1.y;
+                dmma_acc(cre0, cre1, xr, y);
+                dmma_acc(cim0, cim1, xi, y);
+                if (I == J) {  // keep the diagonal exactly real
+                    if (row == c0) cim0 = 0.0;
+                    if (row == c0 + 1) cim1 = 0.0;
+                }
+                if (ok0) As[row * S + c0] = make_double2(cre0, cim0);
+                if (ok1) As[row * S + c0 + 1] = make_double2(cre1, cim1);
+                if (I != J) {
+                    if (ok0) As[c0 * S + row] = make_double2(cre0, -cim0);
+                    if (ok1) As[(c0 + 1) * S + row] = make_double2(cre1, -cim1);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (t == 0) {
+        ds[N - 1] = As[(N - 1) * S + (N - 1)].x;
+        es[N - 1] = 0.0;
+    }
+    __syncwarp();
+    if (valid) {
+        for (int i = t; i < N; i += 32) {
+            D[kidx * N + i] = ds[i];
+            E[kidx * N + i] = es[i];
+        }
+    }
+}
+
+cudaError_t launch_mma(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    const MmaLayout L(n);
+    const size_t per_mat = (size_t)L.per_matrix * 16;
+    // matrices per CTA that maximise the number resident per SM (228 KB, 1 KB reserved per CTA); ties -> smaller CTA
+    int best_mpb = 1, best_res = 0;
+    for (int mpb = 1; mpb <= TPB / 32; ++mpb) {
+        const size_t cta = per_mat * mpb + 1024;
+        if (per_mat * mpb > 227 * 1024) break;
+        const int res = (int)((228 * 1024) / cta) * mpb;
+        if (res > best_res) {
+            best_res = res;
+            best_mpb = mpb;
+        }
+    }
+    const size_t smem = per_mat * best_mpb;
+    cudaError_t err = cudaFuncSetAttribute(tridiag_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const long blocks = (nk + best_mpb - 1) / best_mpb;
+    if (blocks <= 0) return cudaSuccess;
+    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_mma_kernel<<<(unsigned)blocks, 32 * best_mpb, smem, st>>>(Hp, n, nk, D, E);
+    return cudaGetLastError();
+}
+
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int G>
@@ -388,6 +617,19 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
 }  // namespace
 
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    if (const char* g = getenv("TBK_TRIDIAG_G")) {  // tuning hook: threads per matrix
+        switch (atoi(g)) {
+            case 8: return launch_g<8>(n, Hp, nk, D, E, st);
+            case 16: return launch_g<16>(n, Hp, nk, D, E, st);
+            case 32: return launch_g<32>(n, Hp, nk, D, E, st);
+            case 64: return launch_g<64>(n, Hp, nk, D, E, st);
+            case 128: return launch_g<128>(n, Hp, nk, D, E, st);
+            case 256: return launch_g<256>(n, Hp, nk, D, E, st);
+            case 1: return launch_mma(n, Hp, nk, D, E, st);
+            default: break;
+        }
+    }
+    if (n > 20 && n <= 64) return launch_mma(n, Hp, nk, D, E, st);
     if (n <= 10) return launch_g<8>(n, Hp, nk, D, E, st);
     if (n <= 20) return launch_g<16>(n, Hp, nk, D, E, st);
     if (n <= 48) return launch_g<32>(n, Hp, nk, D, E, st);
