@@ -334,8 +334,8 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
             for (int b = 0; b < a; ++b) {
                 const double2 vb = V[b], wb = P[b];
                 double2 z = row[b];
-                z.x -= va.x * wb.x + va.y * wb.y + wa.x * vb.x + wa.y * vb.y;
-                z.y -= va.y * wb.x - va.x * wb.y + wa.y * vb.x - wa.x * vb.y;
+                z.x = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, z.x))));
+                z.y = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, z.y))));
                 row[b] = z;
             }
             row[a].x -= 2.0 * (va.x * wa.x + va.y * wa.y);
@@ -517,29 +517,66 @@ tridiag_mma_kernel(const double* __restrict__ Hp, int N, long nk, double* __rest
         // --- A -= v w^H + w v^H on the tensor cores, lower 8x8 blocks that touch the trailing sub-matrix ---
         const int qb = r0 >> 3;
         const double sgn = (tq & 1) ? 1.0 : -1.0;
+        const bool ragged = (N & 7) != 0;
         for (int I = qb; I < NB; ++I) {
             const int row = I * 8 + g;
             const double xr = -XY[row * 4 + tq];                 // -(vr, vi, wr, wi)[tq]
             const double xi = sgn * XY[row * 4 + (tq ^ 1)];      // (-vi, vr, -wi, wr)[tq]
-            const bool row_ok = row < N;
-            for (int J = qb; J <= I; ++J) {
-                const double y = XY[(J * 8 + g) * 4 + (tq ^ 2)];  // (wr, wi, vr, vi)[tq] of column-block row g
-                const int c0 = J * 8 + 2 * tq;
-                const bool ok0 = row_ok && c0 < N, ok1 = row_ok && c0 + 1 < N;
-                const double2 z0 = ok0 ? As[row * S + c0] : make_double2(0.0, 0.0);
-                const double2 z1 = ok1 ? As[row * S + c0 + 1] : make_double2(0.0, 0.0);
-                double cre0 = z0.x, cre1 = z1.x, cim0 = z0.y, cim1 = z1.y;
-                dmma_acc(cre0, cre1, xr, y);
-                dmma_acc(cim0, cim1, xi, y);
-                if (I == J) {  // keep the diagonal exactly real
-                    if (row == c0) cim0 = 0.0;
-                    if (row == c0 + 1) cim1 = 0.0;
+            double2* rp = As + row * S + qb * 8 + 2 * tq;        // C fragment (row, J*8 + 2 tq), J = qb
+            double2* mp = As + (qb * 8 + 2 * tq) * S + row;      // its mirror (J*8 + 2 tq, row)
+            const double* yp = XY + (qb * 8 + g) * 4 + (tq ^ 2);  // (wr, wi, vr, vi)[tq] of row J*8 + g
+            if (!(ragged && I == NB - 1)) {
+                // every element of these blocks exists: no predicates
+                for (int J = qb; J < I; ++J) {
+                    const double y = *yp;
+                    const double2 z0 = rp[0], z1 = rp[1];
+                    double cre0 = z0.x, cre1 = z1.x, cim0 = z0.y, cim1 = z1.y;
+                    dmma_acc(cre0, cre1, xr, y);
+                    dmma_acc(cim0, cim1, xi, y);
+                    rp[0] = make_double2(cre0, cim0);
+                    rp[1] = make_double2(cre1, cim1);
+                    mp[0] = make_double2(cre0, -cim0);
+                    mp[S] = make_double2(cre1, -cim1);
+                    rp += 8;
+                    mp += 8 * S;
+                    yp += 32;
                 }
-                if (ok0) As[row * S + c0] = make_double2(cre0, cim0);
-                if (ok1) As[row * S + c0 + 1] = make_double2(cre1, cim1);
-                if (I != J) {
-                    if (ok0) As[c0 * S + row] = make_double2(cre0, -cim0);
-                    if (ok1) As[(c0 + 1) * S + row] = make_double2(cre1, -cim1);
+                {   // diagonal block: the product also yields its upper half; keep the diagonal exactly real
+                    const double y = *yp;
+                    const double2 z0 = rp[0], z1 = rp[1];
+                    double cre0 = z0.x, cre1 = z1.x, cim0 = z0.y, cim1 = z1.y;
+                    dmma_acc(cre0, cre1, xr, y);
+                    dmma_acc(cim0, cim1, xi, y);
+                    if (g == 2 * tq) cim0 = 0.0;
+                    if (g == 2 * tq + 1) cim1 = 0.0;
+                    rp[0] = make_double2(cre0, cim0);
+                    rp[1] = make_double2(cre1, cim1);
+                }
+            } else {
+                // last block row of a matrix whose size is not a multiple of 8: rows / columns >= N do not exist
+                const bool row_ok = row < N;
+                for (int J = qb; J <= I; ++J) {
+                    const double y = *yp;
+                    const int c0 = J * 8 + 2 * tq;
+                    const bool ok0 = row_ok && c0 < N, ok1 = row_ok && c0 + 1 < N;
+                    const double2 z0 = ok0 ? rp[0] : make_double2(0.0, 0.0);
+                    const double2 z1 = ok1 ? rp[1] : make_double2(0.0, 0.0);
+                    double cre0 = z0.x, cre1 = z1.x, cim0 = z0.y, cim1 = z1.y;
+                    dmma_acc(cre0, cre1, xr, y);
+                    dmma_acc(cim0, cim1, xi, y);
+                    if (J == I) {
+                        if (g == 2 * tq) cim0 = 0.0;
+                        if (g == 2 * tq + 1) cim1 = 0.0;
+                    }
+                    if (ok0) rp[0] = make_double2(cre0, cim0);
+                    if (ok1) rp[1] = make_double2(cre1, cim1);
+                    if (J != I) {
+                        if (ok0) mp[0] = make_double2(cre0, -cim0);
+                        if (ok1) mp[S] = make_double2(cre1, -cim1);
+                    }
+                    rp += 8;
+                    mp += 8 * S;
+                    yp += 32;
                 }
             }
         }
@@ -629,7 +666,8 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
             default: break;
         }
     }
-    if (n > 20 && n <= 64) return launch_mma(n, Hp, nk, D, E, st);
+    // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
+    //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
     if (n <= 10) return launch_g<8>(n, Hp, nk, D, E, st);
     if (n <= 20) return launch_g<16>(n, Hp, nk, D, E, st);
     if (n <= 48) return launch_g<32>(n, Hp, nk, D, E, st);

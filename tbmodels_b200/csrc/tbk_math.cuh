@@ -29,6 +29,33 @@ TBK_HD long trs(long i) { return i * (i - 1) / 2; }  // start of row i in the im
 // complex tau and a complex scale = 1/(alpha - beta) so that with v = [1; scale * x]
 //   (I - tau v v^H)^H [alpha; x] = [beta; 0].
 // tau == 0 means "no reflection" (x == 0 and alpha real).
+#if defined(__CUDA_ARCH__)
+// 1/x and 1/sqrt(x) for normal, finite, positive-or-negative (rcp) / positive (rsqrt) x: hardware seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~2^-23) + three Newton steps -> <= 1 ulp.  No subnormal / inf / nan handling: the callers' arguments
+// are sums of squares and norms of O(max |H|) numbers.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
+}
+#endif
+
 TBK_HD void householder_gen(double ar, double ai, double xnorm2, double& beta, double& tr, double& ti,
                             double& sr, double& si) {
     if (xnorm2 == 0.0 && ai == 0.0) {
@@ -37,14 +64,26 @@ TBK_HD void householder_gen(double ar, double ai, double xnorm2, double& beta, d
         sr = si = 0.0;
         return;
     }
-    const double nrm = sqrt(ar * ar + ai * ai + xnorm2);
+    const double h = ar * ar + ai * ai + xnorm2;
+#if defined(__CUDA_ARCH__)
+    const bool tame = h > 1e-280 && h < 1e280;
+    const double rn = tame ? fast_rsqrt(h) : 1.0 / sqrt(h);
+#else
+    const double rn = 1.0 / sqrt(h);
+#endif
+    const double nrm = h * rn;
     beta = (ar >= 0.0) ? -nrm : nrm;
-    const double binv = 1.0 / beta;
+    const double binv = (ar >= 0.0) ? -rn : rn;  // 1 / beta
     tr = (beta - ar) * binv;
     ti = -ai * binv;
     const double dr = ar - beta;  // same-sign sum: no cancellation
     const double di = ai;
-    const double den = 1.0 / (dr * dr + di * di);
+    const double q = dr * dr + di * di;
+#if defined(__CUDA_ARCH__)
+    const double den = tame ? fast_rcp(q) : 1.0 / q;
+#else
+    const double den = 1.0 / q;
+#endif
     sr = dr * den;
     si = -di * den;
 }

@@ -1,0 +1,65 @@
+"""Two real GPUs, NCCL: sharded evaluation equals the single-GPU result (skipped on a 1-GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_k, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from tbmodels_b200 import workloads as wl
+    from tbmodels_b200.sharded import ShardedEvaluator, broadcast_model
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        packed = broadcast_model(wl.synthetic(12, 10) if rank == 0 else None, src=0, device=f"cuda:{rank}")
+        sh = ShardedEvaluator(packed, device=rank)
+        g = torch.Generator(device=f"cuda:{rank}").manual_seed(7)  # same k-points on every rank
+        k_all = torch.rand((n_k, 3), dtype=torch.float64, device=f"cuda:{rank}", generator=g)
+        lo, hi, e_loc = sh.eigenval_local(k_all)
+        full = sh.eigenval_allgather(k_all)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, hi=hi, e_loc=e_loc.cpu().numpy(), full=full.cpu().numpy(),
+                 k=k_all.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_k", [4096, 5001])
+def test_two_gpu_nccl_sharding(tmp_path, n_k):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import tbmodels_b200 as tbk
+    from tbmodels_b200 import workloads as wl
+
+    mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path)), nprocs=2, join=True)
+    d0 = np.load(tmp_path / "r0.npz")
+    d1 = np.load(tmp_path / "r1.npz")
+    want = tbk.Evaluator(wl.synthetic(12, 10), device=0).eigenval_array(d0["k"])
+    assert np.array_equal(d0["k"], d1["k"])
+    for d in (d0, d1):
+        assert np.array_equal(d["full"], want)  # bit-identical regardless of the shard a k-point landed in
+        assert np.array_equal(d["e_loc"], want[int(d["lo"]) : int(d["hi"])])
+    assert int(d0["hi"]) == int(d1["lo"]) and int(d1["hi"]) == n_k

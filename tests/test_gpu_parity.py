@@ -354,3 +354,16 @@ def test_host_pipeline_chunking(tbk, monkeypatch):
     assert got is out and np.array_equal(got, ref)
     h_ref = ev.hamilton(k[:70_000], convention=1)
     assert np.array_equal(ev2.hamilton(k[:70_000], convention=1), h_ref)
+
+
+@pytest.mark.parametrize("g", ["1", "32", "64"])
+def test_tridiag_variants_agree(tbk, monkeypatch, g):
+    """Every thread-group size of the packed kernel and the tensor-core variant give reference eigenvalues."""
+    from tbmodels_b200 import workloads as wl
+
+    monkeypatch.setenv("TBK_TRIDIAG_G", g)
+    d = load_golden("synthetic.npz")
+    for tag in ("n33", "c3", "n50"):
+        n_orb, n_half = (int(x) for x in d[f"{tag}_shape"])
+        p = wl.synthetic(n_orb, n_half, seed=1234)
+        _check(tbk, p, d[f"{tag}_k"], None, None, d[f"{tag}_eig"], f"{tag} G={g}")
