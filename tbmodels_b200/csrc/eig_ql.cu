@@ -2,9 +2,10 @@
 //
 // Second half of the replacement for scipy.linalg.eigvalsh in Model.eigenval (reference
 // src/tbmodels/_tb_model.py:1148-1149).  The QL sweep is a serial recurrence, so parallelism comes from
-// the batch: each lane runs tbk::tridiag_ql on its own (d, e).  For N <= 100 a CTA of 128 threads stages
-// its 128 matrices through shared memory with coalesced global loads/stores and a thread-strided
-// (conflict-free) layout; above that each thread works in place on its row of D/E in global memory.
+// the batch: each lane runs tbk::tridiag_ql on its own (d, e).  A CTA of T threads (128 for small N down to 8
+// for N = 512: shared memory per thread is 2 N doubles) stages its T matrices through shared memory with
+// coalesced global loads/stores and a thread-strided (conflict-free) layout; only when even 8 matrices do not
+// fit does each thread work in place on its row of D/E in global memory.
 // Eigenvalues come out ascending, like LAPACK's.
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
@@ -13,21 +14,24 @@ namespace tbk {
 
 namespace {
 
-constexpr int TPB = 128;
-constexpr int LDS = TPB + 1;  // odd row stride: the transposing loads/stores are conflict-free too
+constexpr int TPB_GLOBAL = 128;
 
-__global__ void __launch_bounds__(TPB)
+// T matrices (threads) per CTA.  Shared memory per thread is 2 N doubles, so large N means small CTAs; the odd row
+// stride T + 1 keeps the transposing loads/stores conflict free.
+template <int T>
+__global__ void __launch_bounds__(T)
 ql_smem_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk, int* __restrict__ fail_count) {
+    constexpr int LDS = T + 1;
     extern __shared__ __align__(16) double sm[];
     double* ds = sm;                  // [N][LDS]
     double* es = sm + (size_t)N * LDS;
-    const long k0 = (long)blockIdx.x * TPB;
-    const int nmat = (int)((nk - k0) < TPB ? (nk - k0) : TPB);
+    const long k0 = (long)blockIdx.x * T;
+    const int nmat = (int)((nk - k0) < T ? (nk - k0) : T);
     const int tid = threadIdx.x;
     const long total = (long)nmat * N;
     const double* Dg = D + k0 * N;
     const double* Eg = E + k0 * N;
-    for (long idx = tid; idx < total; idx += TPB) {
+    for (long idx = tid; idx < total; idx += T) {
         const int mat = (int)(idx / N), i = (int)(idx - (long)mat * N);
         ds[i * LDS + mat] = Dg[idx];
         es[i * LDS + mat] = Eg[idx];
@@ -39,47 +43,82 @@ ql_smem_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk, i
     }
     __syncthreads();
     double* Do = D + k0 * N;
-    for (long idx = tid; idx < total; idx += TPB) {
+    for (long idx = tid; idx < total; idx += T) {
         const int mat = (int)(idx / N), i = (int)(idx - (long)mat * N);
         Do[idx] = ds[i * LDS + mat];
     }
 }
 
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB_GLOBAL)
 ql_global_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk, int* __restrict__ fail_count) {
-    const long kk = (long)blockIdx.x * TPB + threadIdx.x;
+    const long kk = (long)blockIdx.x * TPB_GLOBAL + threadIdx.x;
     if (kk >= nk) return;
     const int fails = tridiag_ql(N, D + kk * N, E + kk * N, 1);
     if (fails && fail_count) atomicAdd(fail_count, fails);
+}
+
+size_t ql_smem_bytes(int n, int t) { return (size_t)2 * n * (t + 1) * 8; }
+
+// Largest CTA that still lets three (else two, else one) CTAs share an SM; 0 -> global-memory fallback.
+int ql_pick_threads(int n) {
+    const int cand[5] = {128, 64, 32, 16, 8};
+    const size_t limits[3] = {72 * 1024, 110 * 1024, 220 * 1024};
+    for (size_t lim : limits)
+        for (int t : cand)
+            if (ql_smem_bytes(n, t) <= lim) return t;
+    return 0;
+}
+
+template <int T>
+cudaError_t launch_t(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave) {
+    const size_t smem = ql_smem_bytes(n, T);
+    cudaError_t err = cudaFuncSetAttribute(ql_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (wave) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_smem_kernel<T>, T, smem);
+        *wave = (err == cudaSuccess) ? (long)sms * per_sm * T : 0;
+        return err;
+    }
+    const long blocks = (nk + T - 1) / T;
+    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+    ql_smem_kernel<T><<<(unsigned)blocks, T, smem, st>>>(D, E, n, nk, fail_count);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave) {
+    switch (ql_pick_threads(n)) {
+        case 128: return launch_t<128>(n, D, E, nk, fail_count, st, wave);
+        case 64: return launch_t<64>(n, D, E, nk, fail_count, st, wave);
+        case 32: return launch_t<32>(n, D, E, nk, fail_count, st, wave);
+        case 16: return launch_t<16>(n, D, E, nk, fail_count, st, wave);
+        case 8: return launch_t<8>(n, D, E, nk, fail_count, st, wave);
+        default: break;
+    }
+    if (wave) {
+        *wave = 0;
+        return cudaSuccess;
+    }
+    const long blocks = (nk + TPB_GLOBAL - 1) / TPB_GLOBAL;
+    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+    ql_global_kernel<<<(unsigned)blocks, TPB_GLOBAL, 0, st>>>(D, E, n, nk, fail_count);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
 long ql_wave_matrices(int n) {
     // matrices one full wave of the shared-memory QL kernel processes (0: not applicable)
-    const size_t smem = (size_t)2 * n * LDS * 8;
-    if (n <= 0 || smem > 210 * 1024) return 0;
-    int dev = 0, sms = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(ql_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ql_smem_kernel, TPB, smem) != cudaSuccess) return 0;
-    return (long)sms * per_sm * TPB;
+    long wave = 0;
+    if (n <= 0 || dispatch(n, nullptr, nullptr, 0, nullptr, nullptr, &wave) != cudaSuccess) return 0;
+    return wave;
 }
 
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st) {
     if (nk <= 0 || n <= 0) return cudaSuccess;
-    const long blocks = (nk + TPB - 1) / TPB;
-    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
-    const size_t smem = (size_t)2 * n * LDS * 8;
-    if (smem <= 210 * 1024) {
-        cudaError_t err = cudaFuncSetAttribute(ql_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        ql_smem_kernel<<<(unsigned)blocks, TPB, smem, st>>>(D, E, n, nk, fail_count);
-    } else {
-        ql_global_kernel<<<(unsigned)blocks, TPB, 0, st>>>(D, E, n, nk, fail_count);
-    }
-    return cudaGetLastError();
+    return dispatch(n, D, E, nk, fail_count, st, nullptr);
 }
 
 }  // namespace tbk

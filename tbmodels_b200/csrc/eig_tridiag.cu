@@ -204,14 +204,20 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }
 
-template <int G>
-__global__ void __launch_bounds__(TPB)
+// G threads per matrix = RT row-threads x CS column slices.  CS > 1 splits every row of the matrix-vector product and
+// of the rank-2 update over CS threads (partial sums combined through shared memory): more warps per resident
+// matrix, shorter serial loops -- the kernel is latency bound, shared memory caps the number of resident matrices.
+template <int G, int CS>
+__global__ void __launch_bounds__((G > TPB ? G : TPB))
 tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
     constexpr int NW = G > 32 ? G / 32 : 1;
+    constexpr int RT = G / CS;
+    static_assert(CS == 1 || (RT % 32 == 0), "column slices must be whole warps");
     extern __shared__ __align__(16) double2 sm2[];
     const int MPB = blockDim.x / G;
     const int group = threadIdx.x / G;
     const int t = threadIdx.x % G;
+    const int rr = t % RT, cs = t / RT;
     const int ntri = itri(N);
     const long NN = (long)N * N;
 
@@ -219,13 +225,14 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     const bool valid = kidx < nk;
     const long kk = valid ? kidx : nk - 1;  // idle groups shadow the last matrix and store nothing
 
-    const int per_group = ntri + 3 * N + 2 * NW + 1;  // in double2 units
+    const int per_group = ntri + 3 * N + (CS > 1 ? CS * N : 0) + 2 * NW + 1;  // in double2 units
     double2* A = sm2 + (size_t)group * per_group;
     double2* V = A + ntri;
     double2* P = V + N;
     double* ds = reinterpret_cast<double*>(P + N);
     double* es = ds + N;
-    double* red = es + N;
+    double2* PP = reinterpret_cast<double2*>(es + N);  // [CS][N] partial row sums (CS > 1)
+    double* red = reinterpret_cast<double*>(PP + (CS > 1 ? CS * N : 0));
 
     {   // load + interleave.  The real plane has the same packed order as the complex rows (flat copy); an imag
         // plane entry f = trs(i) + j lands at f + i.  Flat loops keep many independent loads in flight.
@@ -275,44 +282,63 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
         }
         group_sync<G>(group);
         // --- p = tau * A22 v (row part from the own packed row, column part conjugated), dot = p^H v ---
-        // two independent accumulator pairs (even / odd columns) halve the DFMA dependency chains
+        // two independent accumulator pairs halve the DFMA dependency chains
         double dr = 0.0, di = 0.0;
-        const int c2_0 = itri(r0);
-        for (int a = t; a < m; a += G) {
+        for (int a = rr; a < m; a += RT) {
             const int I = r0 + a;
             const int rowI = itri(I) + r0;
-            int c2 = c2_0 + I;  // tri(J) + I for J = r0
             double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
-            int b = 0;
-            for (; b + 1 < m; b += 2) {
-                const bool l0 = b < a, l1 = b + 1 < a;
-                const int c2b = c2 + r0 + b + 1;
-                const double2 z0 = A[l0 ? rowI + b : c2];
-                const double2 z1 = A[l1 ? rowI + b + 1 : c2b];
-                const double2 v0 = V[b], v1 = V[b + 1];
+            int b = cs;
+            for (; b + CS < m; b += 2 * CS) {
+                const int b1 = b + CS;
+                const bool l0 = b < a, l1 = b1 < a;
+                const double2 z0 = A[l0 ? rowI + b : itri(r0 + b) + I];
+                const double2 z1 = A[l1 ? rowI + b1 : itri(r0 + b1) + I];
+                const double2 v0 = V[b], v1 = V[b1];
                 const double y0 = l0 ? z0.y : -z0.y;
                 const double y1 = l1 ? z1.y : -z1.y;
                 sr0 = fma(z0.x, v0.x, fma(-y0, v0.y, sr0));
                 si0 = fma(z0.x, v0.y, fma(y0, v0.x, si0));
                 sr1 = fma(z1.x, v1.x, fma(-y1, v1.y, sr1));
                 si1 = fma(z1.x, v1.y, fma(y1, v1.x, si1));
-                c2 = c2b + r0 + b + 2;
             }
             if (b < m) {
                 const bool l0 = b < a;
-                const double2 z0 = A[l0 ? rowI + b : c2];
+                const double2 z0 = A[l0 ? rowI + b : itri(r0 + b) + I];
                 const double2 v0 = V[b];
                 const double y0 = l0 ? z0.y : -z0.y;
                 sr0 = fma(z0.x, v0.x, fma(-y0, v0.y, sr0));
                 si0 = fma(z0.x, v0.y, fma(y0, v0.x, si0));
             }
             const double sumr = sr0 + sr1, sumi = si0 + si1;
-            const double pr = tr * sumr - ti * sumi;
-            const double pi = tr * sumi + ti * sumr;
-            P[a] = make_double2(pr, pi);
-            const double2 va = V[a];
-            dr += pr * va.x + pi * va.y;
-            di += pr * va.y - pi * va.x;
+            if (CS == 1) {
+                const double pr = tr * sumr - ti * sumi;
+                const double pi = tr * sumi + ti * sumr;
+                P[a] = make_double2(pr, pi);
+                const double2 va = V[a];
+                dr += pr * va.x + pi * va.y;
+                di += pr * va.y - pi * va.x;
+            } else {
+                PP[cs * N + a] = make_double2(sumr, sumi);
+            }
+        }
+        if (CS > 1) {
+            group_sync<G>(group);
+            for (int a = t; a < m; a += G) {
+                double sumr = 0.0, sumi = 0.0;
+#pragma unroll
+                for (int c = 0; c < CS; ++c) {
+                    const double2 q = PP[c * N + a];
+                    sumr += q.x;
+                    sumi += q.y;
+                }
+                const double pr = tr * sumr - ti * sumi;
+                const double pi = tr * sumi + ti * sumr;
+                P[a] = make_double2(pr, pi);
+                const double2 va = V[a];
+                dr += pr * va.x + pi * va.y;
+                di += pr * va.y - pi * va.x;
+            }
         }
         group_sum2<G>(dr, di, red, group, t, parity);
         const double alr = -0.5 * (tr * dr - ti * di);
@@ -326,19 +352,19 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
         }
         group_sync<G>(group);
         // --- A22 -= v w^H + w v^H (lower triangle) ---
-        for (int a = t; a < m; a += G) {
+        for (int a = rr; a < m; a += RT) {
             const int I = r0 + a;
             const double2 va = V[a], wa = P[a];
             double2* row = A + itri(I) + r0;
 #pragma unroll 4
-            for (int b = 0; b < a; ++b) {
+            for (int b = cs; b < a; b += CS) {
                 const double2 vb = V[b], wb = P[b];
                 double2 z = row[b];
                 z.x = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, z.x))));
                 z.y = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, z.y))));
                 row[b] = z;
             }
-            row[a].x -= 2.0 * (va.x * wa.x + va.y * wa.y);
+            if (cs == 0) row[a].x -= 2.0 * (va.x * wa.x + va.y * wa.y);
         }
         group_sync<G>(group);
     }
@@ -621,59 +647,82 @@ cudaError_t launch_mma(int n, double* Hp, long nk, double* D, double* E, cudaStr
 
 constexpr size_t kSmemLimit = 220 * 1024;
 
-template <int G>
+template <int G, int CS>
 cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
     constexpr int NW = G > 32 ? G / 32 : 1;
+    constexpr int CTA = G > TPB ? G : TPB;
     const long ntri = (long)n * (n + 1) / 2;
-    const size_t per_mat = (size_t)(ntri + 3L * n + 2 * NW + 1) * 16;  // double2 units, see tridiag_smem_kernel
-    int mpb = (int)(kSmemLimit / per_mat);
-    if (mpb > TPB / G) mpb = TPB / G;
-    if (mpb >= 1) {
-        // keep at least two CTAs per SM resident when several matrices share a CTA
-        while (mpb > 1 && per_mat * mpb > kSmemLimit / 2) --mpb;
-        const size_t smem = per_mat * mpb;
-        cudaError_t err =
-            cudaFuncSetAttribute(tridiag_smem_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t per_mat = (size_t)(ntri + 3L * n + (CS > 1 ? (long)CS * n : 0) + 2 * NW + 1) * 16;  // see the kernel
+    if (per_mat <= kSmemLimit) {
+        // matrices per CTA that maximise the number resident per SM (228 KB, 1 KB reserved per CTA, 2048 threads,
+        // 15 named barriers per CTA); ties -> smaller CTA
+        int best_mpb = 1, best_res = 0;
+        for (int mpb = 1; mpb <= CTA / G && mpb <= 15; ++mpb) {
+            if (per_mat * mpb > kSmemLimit) break;
+            int ctas = (int)((228 * 1024) / (per_mat * mpb + 1024));
+            const int by_threads = 2048 / (G * mpb);
+            if (ctas > by_threads) ctas = by_threads;
+            if (ctas * mpb > best_res) {
+                best_res = ctas * mpb;
+                best_mpb = mpb;
+            }
+        }
+        const size_t smem = per_mat * best_mpb;
+        cudaError_t err = cudaFuncSetAttribute(tridiag_smem_kernel<G, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem);
         if (err != cudaSuccess) return err;
-        const long blocks = (nk + mpb - 1) / mpb;
+        const long blocks = (nk + best_mpb - 1) / best_mpb;
         if (blocks <= 0) return cudaSuccess;
         if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
-        tridiag_smem_kernel<G><<<(unsigned)blocks, G * mpb, smem, st>>>(Hp, n, nk, D, E);
+        tridiag_smem_kernel<G, CS><<<(unsigned)blocks, G * best_mpb, smem, st>>>(Hp, n, nk, D, E);
         return cudaGetLastError();
     }
-    // matrix does not fit in shared memory: one CTA per matrix, in place on the packed scratch (L2 / HBM)
-    const size_t smem = (size_t)(6L * n + 4 * NW + 2) * 8;
-    cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // matrix does not fit in shared memory: one CTA of 256 threads per matrix, in place on the packed scratch (L2 / HBM)
+    const size_t smem = (size_t)(6L * n + 4 * 8 + 2) * 8;
+    cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_kernel<G><<<(unsigned)nk, G, smem, st>>>(Hp, n, nk, D, E, 0);
+    tridiag_kernel<256><<<(unsigned)nk, 256, smem, st>>>(Hp, n, nk, D, E, 0);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    if (const char* g = getenv("TBK_TRIDIAG_G")) {  // tuning hook: threads per matrix
-        switch (atoi(g)) {
-            case 8: return launch_g<8>(n, Hp, nk, D, E, st);
-            case 16: return launch_g<16>(n, Hp, nk, D, E, st);
-            case 32: return launch_g<32>(n, Hp, nk, D, E, st);
-            case 64: return launch_g<64>(n, Hp, nk, D, E, st);
-            case 128: return launch_g<128>(n, Hp, nk, D, E, st);
-            case 256: return launch_g<256>(n, Hp, nk, D, E, st);
-            case 1: return launch_mma(n, Hp, nk, D, E, st);
-            default: break;
-        }
-    }
+    int g = 0, cs = 1;
+    if (const char* e = getenv("TBK_TRIDIAG_G")) g = atoi(e);  // tuning hooks: threads per matrix / column slices
+    if (const char* e = getenv("TBK_TRIDIAG_CS")) cs = atoi(e);
+    if (g == 1) return launch_mma(n, Hp, nk, D, E, st);
     // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
     //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
-    if (n <= 10) return launch_g<8>(n, Hp, nk, D, E, st);
-    if (n <= 20) return launch_g<16>(n, Hp, nk, D, E, st);
-    if (n <= 48) return launch_g<32>(n, Hp, nk, D, E, st);
-    if (n <= 96) return launch_g<64>(n, Hp, nk, D, E, st);
-    if (n <= 128) return launch_g<128>(n, Hp, nk, D, E, st);
-    return launch_g<256>(n, Hp, nk, D, E, st);
+    if (g == 0) {  // defaults, from N only (never from the batch: results must not depend on the batch size)
+        if (n <= 10) g = 8;
+        else if (n <= 20) g = 16;
+        else if (n <= 48) g = 32;
+        else if (n <= 96) g = 64;
+        else if (n <= 128) g = 128;
+        else g = 256;
+        cs = 1;
+    }
+#define TBK_CASE(G_, CS_) \
+    if (g == G_ && cs == CS_) return launch_g<G_, CS_>(n, Hp, nk, D, E, st)
+    TBK_CASE(8, 1);
+    TBK_CASE(16, 1);
+    TBK_CASE(32, 1);
+    TBK_CASE(64, 1);
+    TBK_CASE(64, 2);
+    TBK_CASE(128, 1);
+    TBK_CASE(128, 2);
+    TBK_CASE(128, 4);
+    TBK_CASE(256, 1);
+    TBK_CASE(256, 2);
+    TBK_CASE(256, 4);
+    TBK_CASE(256, 8);
+    TBK_CASE(512, 4);
+    TBK_CASE(512, 8);
+#undef TBK_CASE
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace tbk
