@@ -92,6 +92,8 @@ double tbk_measure_fp64_peak(int kind, int iters);
 /* ---- host-side debug entry points: run the exact scalar code of the kernels on the CPU (tests only) ---- */
 /* In-place eigenvalues of a real symmetric tridiagonal matrix; d[n], e[n] (e[n-1] scratch). Returns #failures. */
 int tbk_host_tridiag_ql(int n, double* d, double* e);
+/* Same result by bisection with Sturm counts (the large-N device path); e is not modified. */
+int tbk_host_tridiag_bisect(int n, double* d, const double* e);
 /* Packed Hermitian (n*n doubles, destroyed) -> d[n], e[n]. */
 int tbk_host_hetrd(int n, double* hp, double* d, double* e);
 /* Hermitian-split weights W[2*n_R][n_orb*n_orb] the kernels consume, from hop[n_R][n_orb][n_orb] c128. */

@@ -6,7 +6,7 @@
 // for N = 512: shared memory per thread is 2 N doubles) stages its T matrices through shared memory with
 // coalesced global loads/stores and a thread-strided (conflict-free) layout; only when even 8 matrices do not
 // fit does each thread work in place on its row of D/E in global memory.
-// Eigenvalues come out ascending, like LAPACK's.
+// N > 128 switches to bisection (bisect_kernel below).  Eigenvalues come out ascending, like LAPACK's.
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -57,6 +57,55 @@ ql_global_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk,
     if (fails && fail_count) atomicAdd(fail_count, fails);
 }
 
+// Large N (> 128): the serial QL recurrence leaves the GPU idle (shared memory allows only a few threads per SM), so
+// the eigenvalues are found by bisection instead -- one CTA per matrix, one thread per eigenvalue, every thread runs
+// the same Sturm recurrence on the broadcast (d, e^2) in shared memory.  ~50 N^2 divisions per matrix, all parallel.
+constexpr int TPB_BISECT = 256;
+
+__global__ void __launch_bounds__(TPB_BISECT)
+bisect_kernel(double* __restrict__ D, const double* __restrict__ E, int N, long nk) {
+    extern __shared__ __align__(16) double sm[];
+    double* ds = sm;
+    double* e2 = sm + N;
+    __shared__ double red[4][TPB_BISECT / 32];
+    const long kk = blockIdx.x;
+    const int tid = threadIdx.x;
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    for (int i = tid; i < N; i += TPB_BISECT) {
+        const double di = D[kk * N + i];
+        const double el = i > 0 ? fabs(E[kk * N + i - 1]) : 0.0;
+        const double er = i + 1 < N ? fabs(E[kk * N + i]) : 0.0;
+        ds[i] = di;
+        e2[i] = er * er;
+        lo = fmin(lo, di - el - er);  // Gershgorin
+        hi = fmax(hi, di + el + er);
+        emax = fmax(emax, er * er);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, off));
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = lo;
+        red[1][tid >> 5] = hi;
+        red[2][tid >> 5] = emax;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < TPB_BISECT / 32; ++w) {
+        lo = fmin(lo, red[0][w]);
+        hi = fmax(hi, red[1][w]);
+        emax = fmax(emax, red[2][w]);
+    }
+    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    const double span = fmax(fabs(lo), fabs(hi));
+    const double gl = lo - 2.0 * DBL_EPSILON * span * N - 2.0 * pivmin;
+    const double gu = hi + 2.0 * DBL_EPSILON * span * N + 2.0 * pivmin;
+    for (int i = tid; i < N; i += TPB_BISECT) D[kk * N + i] = bisect_eig(N, ds, e2, i, gl, gu, pivmin);
+}
+
 size_t ql_smem_bytes(int n, int t) { return (size_t)2 * n * (t + 1) * 8; }
 
 // Largest CTA that still lets three (else two, else one) CTAs share an SM; 0 -> global-memory fallback.
@@ -88,7 +137,21 @@ cudaError_t launch_t(int n, double* D, double* E, long nk, int* fail_count, cuda
     return cudaGetLastError();
 }
 
+constexpr int kBisectMinN = 129;
+
 cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave) {
+    if (n >= kBisectMinN && (size_t)2 * n * 8 <= 200 * 1024) {
+        if (wave) {
+            *wave = 0;  // one CTA per matrix: no wave quantisation to respect
+            return cudaSuccess;
+        }
+        const size_t smem = (size_t)2 * n * 8;
+        cudaError_t err = cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+        bisect_kernel<<<(unsigned)nk, TPB_BISECT, smem, st>>>(D, E, n, nk);
+        return cudaGetLastError();
+    }
     switch (ql_pick_threads(n)) {
         case 128: return launch_t<128>(n, D, E, nk, fail_count, st, wave);
         case 64: return launch_t<64>(n, D, E, nk, fail_count, st, wave);

@@ -289,11 +289,13 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
             const int rowI = itri(I) + r0;
             double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
             int b = cs;
+            int c0 = itri(r0 + cs) + I;  // tri(J) + I for J = r0 + b, advanced incrementally
             for (; b + CS < m; b += 2 * CS) {
                 const int b1 = b + CS;
+                const int c1 = c0 + CS * (r0 + b) + (CS * (CS + 1)) / 2;  // tri(J + CS) - tri(J) = CS J + CS (CS + 1) / 2
                 const bool l0 = b < a, l1 = b1 < a;
-                const double2 z0 = A[l0 ? rowI + b : itri(r0 + b) + I];
-                const double2 z1 = A[l1 ? rowI + b1 : itri(r0 + b1) + I];
+                const double2 z0 = A[l0 ? rowI + b : c0];
+                const double2 z1 = A[l1 ? rowI + b1 : c1];
                 const double2 v0 = V[b], v1 = V[b1];
                 const double y0 = l0 ? z0.y : -z0.y;
                 const double y1 = l1 ? z1.y : -z1.y;
@@ -301,10 +303,11 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
                 si0 = fma(z0.x, v0.y, fma(y0, v0.x, si0));
                 sr1 = fma(z1.x, v1.x, fma(-y1, v1.y, sr1));
                 si1 = fma(z1.x, v1.y, fma(y1, v1.x, si1));
+                c0 = c1 + CS * (r0 + b1) + (CS * (CS + 1)) / 2;
             }
             if (b < m) {
                 const bool l0 = b < a;
-                const double2 z0 = A[l0 ? rowI + b : itri(r0 + b) + I];
+                const double2 z0 = A[l0 ? rowI + b : c0];
                 const double2 v0 = V[b];
                 const double y0 = l0 ? z0.y : -z0.y;
                 sr0 = fma(z0.x, v0.x, fma(-y0, v0.y, sr0));
@@ -645,6 +648,191 @@ cudaError_t launch_mma(int n, double* Hp, long nk, double* D, double* E, cudaStr
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Large matrices (N > 164, up to 32 * MAXC): one CTA of 16 warps per matrix, in place on the packed planes in
+// global memory (L2 / HBM).  Everything is organised as coalesced ROW sweeps: a warp owns rows a = w, w + 16, ...
+// of the trailing block and strides its lanes over the columns.  The Hermitian matrix-vector product needs the
+// column part  sum_{J > I} conj(A[J][I]) v_J  as well; instead of gathering columns, each row sweep also scatters
+// conj(A[I][J]) v_I into per-lane register accumulators (one per 32-column chunk), which are combined across the
+// 16 warps through shared memory in a fixed order (deterministic, no atomics).  The matrix is therefore read once
+// per product and read + written once per rank-2 update.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BIG_THREADS = 512;
+constexpr int BIG_WARPS = BIG_THREADS / 32;
+
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* red, int tid, int& parity) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    double* buf = red + parity * 2 * BIG_WARPS;
+    parity ^= 1;
+    if ((tid & 31) == 0) {
+        buf[2 * (tid >> 5)] = a;
+        buf[2 * (tid >> 5) + 1] = b;
+    }
+    __syncthreads();
+    a = 0.0;
+    b = 0.0;
+#pragma unroll
+    for (int w = 0; w < BIG_WARPS; ++w) {
+        a += buf[2 * w];
+        b += buf[2 * w + 1];
+    }
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(BIG_THREADS, 1)
+tridiag_big_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    extern __shared__ __align__(16) double2 smb[];
+    double2* V = smb;                 // [N]
+    double2* P = V + N;               // [N] p, then w
+    double2* S = P + N;               // [N] row-part sums
+    double2* QW = S + N;              // [BIG_WARPS][N] column-part partials
+    double* ds = reinterpret_cast<double*>(QW + (size_t)BIG_WARPS * N);
+    double* es = ds + N;
+    double* red = es + N;             // [2][2 * BIG_WARPS]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long kk = blockIdx.x;
+    const long NN = (long)N * N;
+    double* Ar = Hp + kk * NN;
+    double* Ai = Ar + tri(N);
+    int parity = 0;
+
+    for (int j = 0; j < N - 1; ++j) {
+        const int m = N - 1 - j;
+        const int r0 = j + 1;
+        // --- reflector from column j (strided gather: one element per row) ---
+        const double ar = Ar[tri(r0) + j], ai = Ai[trs(r0) + j];
+        double xn = 0.0, dummy = 0.0;
+        for (int a = 1 + tid; a < m; a += BIG_THREADS) {
+            const long I = r0 + a;
+            const double xr = Ar[tri(I) + j], xi = Ai[trs(I) + j];
+            xn += xr * xr + xi * xi;
+            V[a] = make_double2(xr, xi);  // raw column, scaled below
+        }
+        block_sum2(xn, dummy, red, tid, parity);
+        double beta, tr, ti, sr, si;
+        householder_gen(ar, ai, xn, beta, tr, ti, sr, si);
+        for (int a = 1 + tid; a < m; a += BIG_THREADS) {
+            const double2 x = V[a];
+            V[a] = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
+        }
+        if (tid == 0) {
+            ds[j] = Ar[tri(j) + j];
+            es[j] = beta;
+            V[0] = make_double2(1.0, 0.0);
+        }
+        __syncthreads();
+        // --- row sweep: row parts into S, column parts into per-lane accumulators ---
+        double2 qacc[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) qacc[c] = make_double2(0.0, 0.0);
+        for (int a = w; a < m; a += BIG_WARPS) {
+            const long I = r0 + a;
+            const double* rre = Ar + tri(I) + r0;
+            const double* rim = Ai + trs(I) + r0;
+            const double2 va = V[a];
+            double sumr = 0.0, sumi = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                if (c * 32 < a) {  // warp-uniform
+                    const int b = c * 32 + lane;
+                    if (b < a) {
+                        const double zr = rre[b], zi = rim[b];
+                        const double2 vb = V[b];
+                        sumr = fma(zr, vb.x, fma(-zi, vb.y, sumr));
+                        sumi = fma(zr, vb.y, fma(zi, vb.x, sumi));
+                        qacc[c].x = fma(zr, va.x, fma(zi, va.y, qacc[c].x));   // conj(z) * v_a
+                        qacc[c].y = fma(zr, va.y, fma(-zi, va.x, qacc[c].y));
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                sumr += __shfl_xor_sync(0xffffffffu, sumr, off);
+                sumi += __shfl_xor_sync(0xffffffffu, sumi, off);
+            }
+            if (lane == 0) {
+                const double dg = rre[a];  // real diagonal
+                S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            const int b = c * 32 + lane;
+            if (b < m) QW[(size_t)w * N + b] = qacc[c];
+        }
+        __syncthreads();
+        double dr = 0.0, di = 0.0;
+        for (int a = tid; a < m; a += BIG_THREADS) {
+            double2 q = S[a];
+#pragma unroll
+            for (int ww = 0; ww < BIG_WARPS; ++ww) {
+                const double2 t2 = QW[(size_t)ww * N + a];
+                q.x += t2.x;
+                q.y += t2.y;
+            }
+            const double pr = tr * q.x - ti * q.y;
+            const double pi = tr * q.y + ti * q.x;
+            P[a] = make_double2(pr, pi);
+            const double2 va = V[a];
+            dr += pr * va.x + pi * va.y;
+            di += pr * va.y - pi * va.x;
+        }
+        block_sum2(dr, di, red, tid, parity);
+        const double alr = -0.5 * (tr * dr - ti * di);
+        const double ali = -0.5 * (tr * di + ti * dr);
+        for (int a = tid; a < m; a += BIG_THREADS) {
+            const double2 v = V[a];
+            double2 pq = P[a];
+            pq.x += alr * v.x - ali * v.y;
+            pq.y += alr * v.y + ali * v.x;
+            P[a] = pq;
+        }
+        __syncthreads();
+        // --- rank-2 update, row sweeps ---
+        for (int a = w; a < m; a += BIG_WARPS) {
+            const long I = r0 + a;
+            double* rre = Ar + tri(I) + r0;
+            double* rim = Ai + trs(I) + r0;
+            const double2 va = V[a], wa = P[a];
+            for (int b = lane; b < a; b += 32) {
+                const double2 vb = V[b], wb = P[b];
+                rre[b] = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, rre[b]))));
+                rim[b] = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, rim[b]))));
+            }
+            if (lane == 0) rre[a] -= 2.0 * (va.x * wa.x + va.y * wa.y);
+        }
+        __syncthreads();
+        __threadfence_block();
+    }
+    if (tid == 0) {
+        ds[N - 1] = Ar[tri(N - 1) + (N - 1)];
+        es[N - 1] = 0.0;
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += BIG_THREADS) {
+        D[kk * N + i] = ds[i];
+        E[kk * N + i] = es[i];
+    }
+}
+
+template <int MAXC>
+cudaError_t launch_big(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    const size_t smem = ((size_t)(3 + BIG_WARPS) * n * 16) + (size_t)2 * n * 8 + 4 * BIG_WARPS * 8 + 64;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t err =
+        cudaFuncSetAttribute(tridiag_big_kernel<MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (nk <= 0) return cudaSuccess;
+    if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_big_kernel<MAXC><<<(unsigned)nk, BIG_THREADS, smem, st>>>(Hp, n, nk, D, E);
+    return cudaGetLastError();
+}
+
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int G, int CS>
@@ -677,7 +865,11 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         tridiag_smem_kernel<G, CS><<<(unsigned)blocks, G * best_mpb, smem, st>>>(Hp, n, nk, D, E);
         return cudaGetLastError();
     }
-    // matrix does not fit in shared memory: one CTA of 256 threads per matrix, in place on the packed scratch (L2 / HBM)
+    // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
+    if (!getenv("TBK_TRIDIAG_OLDBIG")) {
+        if (n <= 32 * 16) return launch_big<16>(n, Hp, nk, D, E, st);
+        if (n <= 32 * 22) return launch_big<22>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
+    }
     const size_t smem = (size_t)(6L * n + 4 * 8 + 2) * 8;
     cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -700,10 +892,9 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         if (n <= 10) g = 8;
         else if (n <= 20) g = 16;
         else if (n <= 48) g = 32;
-        else if (n <= 96) g = 64;
-        else if (n <= 128) g = 128;
+        else if (n <= 96) g = 128;
         else g = 256;
-        cs = 1;
+        cs = n <= 48 ? 1 : (n <= 96 ? 2 : 4);  // measured on B200: N = 36 best at (32, 1), N = 128 at (256, 4)
     }
 #define TBK_CASE(G_, CS_) \
     if (g == G_ && cs == CS_) return launch_g<G_, CS_>(n, Hp, nk, D, E, st)

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -545,6 +547,24 @@ int tbk_host_free(void* p) {
 double tbk_measure_fp64_peak(int kind, int iters) { return measure_fp64_peak(kind, iters); }
 
 int tbk_host_tridiag_ql(int n, double* d, double* e) { return tridiag_ql(n, d, e, 1); }
+
+int tbk_host_tridiag_bisect(int n, double* d, const double* e) {
+    if (n < 1) return fail(TBK_E_INVALID, "n < 1");
+    std::vector<double> dd(d, d + n), e2((size_t)n, 0.0);
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double el = i > 0 ? fabs(e[i - 1]) : 0.0, er = i + 1 < n ? fabs(e[i]) : 0.0;
+        e2[i] = er * er;
+        lo = std::min(lo, dd[i] - el - er);
+        hi = std::max(hi, dd[i] + el + er);
+        emax = std::max(emax, er * er);
+    }
+    const double pivmin = DBL_MIN * std::max(1.0, emax);
+    const double span = std::max(fabs(lo), fabs(hi));
+    const double gl = lo - 2.0 * DBL_EPSILON * span * n - 2.0 * pivmin, gu = hi + 2.0 * DBL_EPSILON * span * n + 2.0 * pivmin;
+    for (int i = 0; i < n; ++i) d[i] = bisect_eig(n, dd.data(), e2.data(), i, gl, gu, pivmin);
+    return TBK_OK;
+}
 
 int tbk_host_hetrd(int n, double* hp, double* d, double* e) {
     if (n < 1) return fail(TBK_E_INVALID, "n < 1");

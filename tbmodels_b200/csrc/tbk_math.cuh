@@ -245,6 +245,37 @@ TBK_HD int tridiag_ql(int n, double* d, double* e, long sd) {
     return fails;
 }
 
+// Number of eigenvalues of the symmetric tridiagonal (d, e) that are < x (Sturm sequence of the LDL^T pivots of
+// T - x I; e2[i] = e[i]^2).  |pivot| is kept >= pivmin so the recurrence never divides by zero.
+TBK_HD int sturm_count(int n, const double* d, const double* e2, double x, double pivmin) {
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    int cnt = q < 0.0 ? 1 : 0;
+    for (int i = 1; i < n; ++i) {
+#if defined(__CUDA_ARCH__)
+        q = fma(-e2[i - 1], fast_rcp(q), d[i] - x);
+#else
+        q = d[i] - x - e2[i - 1] / q;
+#endif
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += q < 0.0 ? 1 : 0;
+    }
+    return cnt;
+}
+
+// idx-th smallest eigenvalue (0-based) by bisection inside the Gershgorin interval [gl, gu].
+TBK_HD double bisect_eig(int n, const double* d, const double* e2, int idx, double gl, double gu, double pivmin) {
+    double lo = gl, hi = gu;
+    const double tol = 4.0 * DBL_EPSILON * fmax(fabs(gl), fabs(gu)) + 2.0 * pivmin;
+    for (int it = 0; it < 80 && hi - lo > tol; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid <= lo || mid >= hi) break;
+        if (sturm_count(n, d, e2, mid, pivmin) <= idx) lo = mid;
+        else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+
 // Closed forms for the two smallest sizes (packed input: N=1 -> {h00}; N=2 -> {h00, re h10, h11, im h10}).
 TBK_HD void eig2_closed(double h00, double h11, double br, double bi, double& lo, double& hi) {
     const double mean = 0.5 * (h00 + h11);

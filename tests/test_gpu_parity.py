@@ -367,3 +367,15 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
         n_orb, n_half = (int(x) for x in d[f"{tag}_shape"])
         p = wl.synthetic(n_orb, n_half, seed=1234)
         _check(tbk, p, d[f"{tag}_k"], None, None, d[f"{tag}_eig"], f"{tag} G={g}")
+
+
+@pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 48, 49, 64, 65, 96, 97, 128, 129, 164, 165, 200, 300])
+def test_size_boundaries_vs_oracle(tbk, n_orb):
+    """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection)."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(n_orb, 4, seed=n_orb)
+    nk = 37 if n_orb <= 128 else 5
+    k = np.random.default_rng(n_orb).uniform(-1, 1, size=(nk, 3))
+    _check(tbk, p, k, None, orc.hamilton(p.R, p.hop, p.pos, k[:3], 2), orc.eigenval_array(p.R, p.hop, p.pos, k), f"N={n_orb}")

@@ -77,6 +77,10 @@ def test_host_hetrd_and_ql_match_lapack(n):
         assert lib.tbk_host_hetrd(n, hp.ctypes.data_as(dp), d.ctypes.data_as(dp), e.ctypes.data_as(dp)) == 0
         if n > 1:
             assert np.abs(la.eigvalsh_tridiagonal(d, e[: n - 1]) - ref).max() <= 1e-13 * max(1, np.abs(ref).max())
+        db = d.copy()
+        assert lib.tbk_host_tridiag_bisect(n, db.ctypes.data_as(dp), e.ctypes.data_as(dp)) == 0
+        assert np.all(np.diff(db) >= 0)
+        assert np.abs(db - ref).max() <= 1e-13 * max(1, np.abs(ref).max())
         assert lib.tbk_host_tridiag_ql(n, d.ctypes.data_as(dp), e.ctypes.data_as(dp)) == 0
         assert np.all(np.diff(d) >= 0)
         assert np.abs(d - ref).max() <= 1e-13 * max(1, np.abs(ref).max())
