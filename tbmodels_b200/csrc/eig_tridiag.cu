@@ -208,7 +208,7 @@ __device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }
 // of the rank-2 update over CS threads (partial sums combined through shared memory): more warps per resident
 // matrix, shorter serial loops -- the kernel is latency bound, shared memory caps the number of resident matrices.
 template <int G, int CS>
-__global__ void __launch_bounds__((G > TPB ? G : TPB))
+__global__ void __launch_bounds__((G > 512 ? G : 512))
 tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
     constexpr int NW = G > 32 ? G / 32 : 1;
     constexpr int RT = G / CS;
@@ -737,16 +737,26 @@ tridiag_big_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__
             const double2 va = V[a];
             double sumr = 0.0, sumi = 0.0;
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) {
-                if (c * 32 < a) {  // warp-uniform
-                    const int b = c * 32 + lane;
-                    if (b < a) {
-                        const double zr = rre[b], zi = rim[b];
-                        const double2 vb = V[b];
-                        sumr = fma(zr, vb.x, fma(-zi, vb.y, sumr));
-                        sumi = fma(zr, vb.y, fma(zi, vb.x, sumi));
-                        qacc[c].x = fma(zr, va.x, fma(zi, va.y, qacc[c].x));   // conj(z) * v_a
-                        qacc[c].y = fma(zr, va.y, fma(-zi, va.x, qacc[c].y));
+            for (int c0 = 0; c0 < MAXC; c0 += 4) {
+                if (c0 * 32 < a) {  // warp-uniform; four 32-column chunks per batch keep 8 loads in flight per lane
+                    double zr[4], zi[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int b = (c0 + q) * 32 + lane;
+                        const bool ok = b < a;
+                        zr[q] = ok ? rre[b] : 0.0;
+                        zi[q] = ok ? rim[b] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int b = (c0 + q) * 32 + lane;
+                        if (b < a) {
+                            const double2 vb = V[b];
+                            sumr = fma(zr[q], vb.x, fma(-zi[q], vb.y, sumr));
+                            sumi = fma(zr[q], vb.y, fma(zi[q], vb.x, sumi));
+                            qacc[c0 + q].x = fma(zr[q], va.x, fma(zi[q], va.y, qacc[c0 + q].x));   // conj(z) * v_a
+                            qacc[c0 + q].y = fma(zr[q], va.y, fma(-zi[q], va.x, qacc[c0 + q].y));
+                        }
                     }
                 }
             }
@@ -799,10 +809,24 @@ tridiag_big_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__
             double* rre = Ar + tri(I) + r0;
             double* rim = Ai + trs(I) + r0;
             const double2 va = V[a], wa = P[a];
-            for (int b = lane; b < a; b += 32) {
-                const double2 vb = V[b], wb = P[b];
-                rre[b] = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, rre[b]))));
-                rim[b] = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, rim[b]))));
+            for (int b0 = 0; b0 < a; b0 += 128) {  // batches of four chunks: loads first, then arithmetic and stores
+                double zr[4], zi[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = b0 + q * 32 + lane;
+                    const bool ok = b < a;
+                    zr[q] = ok ? rre[b] : 0.0;
+                    zi[q] = ok ? rim[b] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = b0 + q * 32 + lane;
+                    if (b < a) {
+                        const double2 vb = V[b], wb = P[b];
+                        rre[b] = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, zr[q]))));
+                        rim[b] = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, zi[q]))));
+                    }
+                }
             }
             if (lane == 0) rre[a] -= 2.0 * (va.x * wa.x + va.y * wa.y);
         }
@@ -855,6 +879,10 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
                 best_mpb = mpb;
             }
         }
+        if (const char* e = getenv("TBK_TRIDIAG_MPB")) {  // tuning hook: matrices per CTA
+            const int v = atoi(e);
+            if (v >= 1 && v <= 15 && (size_t)v * G <= 1024 && per_mat * v <= kSmemLimit) best_mpb = v;
+        }
         const size_t smem = per_mat * best_mpb;
         cudaError_t err = cudaFuncSetAttribute(tridiag_smem_kernel<G, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem);
@@ -868,7 +896,7 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
     // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
     if (!getenv("TBK_TRIDIAG_OLDBIG")) {
         if (n <= 32 * 16) return launch_big<16>(n, Hp, nk, D, E, st);
-        if (n <= 32 * 22) return launch_big<22>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
+        if (n <= 32 * 20) return launch_big<20>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
     }
     const size_t smem = (size_t)(6L * n + 4 * 8 + 2) * 8;
     cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
