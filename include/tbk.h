@@ -50,6 +50,13 @@ const char* tbk_last_error(void);
  * All three are HOST pointers, copied during the call.  n_R may be 0 (H == 0). */
 int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double* hop, const double* pos,
                      int device, tbk_model** out);
+/* Pack a k.p model (tbmodels.kdotp.KdotpModel, reference src/tbmodels/kdotp.py:19-49): H(k) = sum_q prod_d k_d^{p_qd} C_q.
+ *   powers [n_terms][dim]            int32  keys of KdotpModel.taylor_coefficients
+ *   coeff  [n_terms][n_orb][n_orb]   c128   the Hermitian coefficient matrices
+ * The handle is used with tbk_hamilton[_host] (convention must be 2: a k.p model has none, kdotp.py:51-82) and
+ * tbk_eigenval[_host] (kdotp.py:84-100). */
+int tbk_kdotp_create(int dim, int n_orb, int n_terms, const int32_t* powers, const double* coeff, int device,
+                     tbk_model** out);
 int tbk_model_destroy(tbk_model* m);
 /* path: 0 = fused thread-per-k kernel (N <= 8), 1 = DMMA GEMM + batched tridiagonal/QL eigensolver. */
 int tbk_model_info(const tbk_model* m, int* n_orb, int* dim, int* n_R, int* path);

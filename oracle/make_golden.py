@@ -271,6 +271,30 @@ def main():
         edge[f"shift_{key}"] = val
     np.savez_compressed(os.path.join(GOLD, "edge_cases.npz"), **edge)
 
+    # ---- k.p models (reference src/tbmodels/kdotp.py; tests/test_kdotp.py:19-37 and construct_kdotp :47-57) ----
+    from tbmodels.kdotp import KdotpModel
+
+    kd = {}
+    kp = KdotpModel({(0, 0): np.eye(2), (1, 0): [[0, 1j], [-1j, 0]], (0, 2): [[0, 1], [1, 0]]})
+    k = np.array([(0, 0), (0, 0.5), (1, 0), (0.3, -0.7)])
+    kd["toy_powers"] = np.array(list(kp.taylor_coefficients.keys()))
+    kd["toy_coeff"] = np.array(list(kp.taylor_coefficients.values()))
+    kd["toy_k"] = k
+    kd["toy_H"] = kp.hamilton(k)
+    kd["toy_eig"] = np.array(kp.eigenval(k))
+    for order in (0, 1, 2, 3):
+        kp = si.construct_kdotp(KPT[0], order=order)
+        k = rng.uniform(-0.05, 0.05, size=(24, 3))
+        k[0] = 0.0
+        kd[f"si{order}_powers"] = np.array(list(kp.taylor_coefficients.keys()))
+        kd[f"si{order}_coeff"] = np.array(list(kp.taylor_coefficients.values()))
+        kd[f"si{order}_k"] = k
+        kd[f"si{order}_H"] = kp.hamilton(k)
+        kd[f"si{order}_eig"] = np.array(kp.eigenval(k))
+        if order == 0:  # tests/test_kdotp.py:55-57: the k.p model at k = 0 reproduces the tight-binding bands at kpt
+            assert np.allclose(kp.eigenval((0, 0, 0)), si.eigenval(KPT[0]))
+    np.savez_compressed(os.path.join(GOLD, "kdotp.npz"), **kd)
+
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print(f"wrote {len(os.listdir(GOLD))} files, {total / 1e6:.2f} MB, to {GOLD}")
 

@@ -95,6 +95,32 @@ def eigenval_array(R, hop, pos, k, chunk=4096):
     return out
 
 
+def kdotp_hamilton(taylor_coefficients, k):
+    """Restates ``KdotpModel.hamilton`` (reference src/tbmodels/kdotp.py:51-82): sum over the Taylor terms of
+    ``prod(k**powers) * C`` in dict order."""
+    k_array = np.array(k, ndmin=1)
+    if k_array.ndim == 1:
+        single_point = True
+        k_array = k_array.reshape((1, -1))
+    else:
+        single_point = False
+    ham = sum(
+        np.prod(k_array**k_powers, axis=-1).reshape(-1, 1, 1) * np.asarray(mat, dtype=complex)[np.newaxis, :, :]
+        for k_powers, mat in taylor_coefficients.items()
+    )
+    if single_point:
+        return ham[0]
+    return ham
+
+
+def kdotp_eigenval(taylor_coefficients, k):
+    """Restates ``KdotpModel.eigenval`` (reference src/tbmodels/kdotp.py:84-100)."""
+    hamiltonians = kdotp_hamilton(taylor_coefficients, k)
+    if hamiltonians.ndim == 3:
+        return [la.eigvalsh(ham) for ham in hamiltonians]
+    return la.eigvalsh(hamiltonians)
+
+
 def hamilton_longdouble(R, hop, pos, k, convention=2):
     """Same formula evaluated with 80-bit phases (argument reduced exactly); used only to show which of two
     f64 implementations is closer to the exact answer when they disagree at the 1e-15 level."""

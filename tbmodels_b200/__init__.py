@@ -9,14 +9,16 @@ Public surface
     pack_model / pack_arrays / PackedModel   host-side packing of ``hop`` / ``pos``
     Evaluator                                owns the device copy; host- and device-buffer entry points
     KModel                                   minimal ``Model`` duck-type (hop, pos, size, dim + the two methods)
+    KdotpModel                               ``tbmodels.kdotp.KdotpModel`` duck-type (k.p models, same kernels)
     install / uninstall                      switch ``tbmodels.Model`` itself over to the GPU path
     sharded                                  one-process-per-GPU k-point sharding (torch.distributed)
     workloads                                the benchmark / parity model generators of BASELINE.json
 """
 from ._capi import TbkError  # noqa: F401
 from ._evaluator import Evaluator, fp64_peaks, pinned_empty  # noqa: F401
+from ._kdotp import KdotpModel, pack_kdotp  # noqa: F401
 from ._model import KModel  # noqa: F401
 from ._pack import PackedModel, hop_dict, pack_arrays, pack_model  # noqa: F401
-from ._patch import evaluator_for, install, uninstall  # noqa: F401
+from ._patch import evaluator_for, install, install_kdotp, uninstall  # noqa: F401
 
 __version__ = "0.1.0"

@@ -17,6 +17,7 @@ SYMBOLS = (
     "tbk_version",
     "tbk_last_error",
     "tbk_model_create",
+    "tbk_kdotp_create",
     "tbk_model_destroy",
     "tbk_model_info",
     "tbk_hamilton",
@@ -69,6 +70,8 @@ def load() -> C.CDLL:
     lib.tbk_last_error.restype = C.c_char_p
     lib.tbk_model_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.POINTER(vp)]
     lib.tbk_model_create.restype = C.c_int
+    lib.tbk_kdotp_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(vp)]
+    lib.tbk_kdotp_create.restype = C.c_int
     lib.tbk_model_destroy.argtypes = [vp]
     lib.tbk_model_destroy.restype = C.c_int
     lib.tbk_model_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 4

@@ -92,6 +92,39 @@ class Evaluator:
         self._handle = handle
         self._finalizer = weakref.finalize(self, self._lib.tbk_model_destroy, handle)
 
+    @classmethod
+    def from_kdotp(cls, powers, coeff, device=None) -> "Evaluator":
+        """Evaluator of a k.p model ``H(k) = sum_q prod_d k_d^{p_qd} C_q`` (reference src/tbmodels/kdotp.py:51-100).
+
+        ``powers`` int [n_terms, dim], ``coeff`` complex128 [n_terms, N, N] (Hermitian matrices).  ``hamilton`` must be
+        called with the default ``convention=2`` (a k.p model has no orbital positions).
+        """
+        powers = np.ascontiguousarray(powers, dtype=np.int32)
+        coeff = np.ascontiguousarray(coeff, dtype=np.complex128)
+        if powers.ndim != 2 or coeff.ndim != 3 or coeff.shape[0] != powers.shape[0] or coeff.shape[1] != coeff.shape[2]:
+            raise ValueError(f"inconsistent k.p arrays: powers {powers.shape}, coeff {coeff.shape}")
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        self.packed = None
+        self.size = coeff.shape[1]
+        self.dim = powers.shape[1]
+        self.device = int(_default_device() if device is None else device)
+        handle = C.c_void_p()
+        _capi.check(
+            self._lib.tbk_kdotp_create(
+                self.dim,
+                self.size,
+                powers.shape[0],
+                powers.ctypes.data_as(C.c_void_p),
+                coeff.ctypes.data_as(C.c_void_p),
+                self.device,
+                C.byref(handle),
+            )
+        )
+        self._handle = handle
+        self._finalizer = weakref.finalize(self, self._lib.tbk_model_destroy, handle)
+        return self
+
     # ------------------------------------------------------------------ info
     @property
     def path(self) -> str:

@@ -64,13 +64,49 @@ def _eigenval(self, k):
     return evaluator_for(self).eigenval(k)
 
 
+def _kdotp_hamilton(self, k):
+    from ._kdotp import kdotp_evaluator_for
+
+    return kdotp_evaluator_for(self, cache=_kdotp_cache, device=_device).hamilton(k)
+
+
+def _kdotp_eigenval(self, k):
+    from ._kdotp import kdotp_evaluator_for
+
+    return kdotp_evaluator_for(self, cache=_kdotp_cache, device=_device).eigenval(k)
+
+
+_kdotp_cache: dict = {}
+
+
+def install_kdotp(kdotp_cls=None, device=None):
+    """Replace ``hamilton`` / ``eigenval`` on ``tbmodels.kdotp.KdotpModel`` (reference src/tbmodels/kdotp.py:51-100)."""
+    global _device
+    if kdotp_cls is None:
+        import tbmodels.kdotp
+
+        kdotp_cls = tbmodels.kdotp.KdotpModel
+    if device is not None:
+        _device = device
+    if kdotp_cls not in _originals:
+        _originals[kdotp_cls] = (kdotp_cls.__dict__.get("hamilton"), kdotp_cls.__dict__.get("eigenval"))
+    kdotp_cls.hamilton = _kdotp_hamilton
+    kdotp_cls.eigenval = _kdotp_eigenval
+    return kdotp_cls
+
+
 def install(model_cls=None, device=None):
-    """Replace ``hamilton`` / ``eigenval`` on ``tbmodels.Model`` (or on ``model_cls``)."""
+    """Replace ``hamilton`` / ``eigenval`` on ``tbmodels.Model`` (or on ``model_cls``); with no argument the
+    reference's ``KdotpModel`` is switched over as well."""
     global _device
     if model_cls is None:
         import tbmodels  # the reference package; only needed for the drop-in switch
 
         model_cls = tbmodels.Model
+        try:
+            install_kdotp(device=device)
+        except ImportError:
+            pass
     _device = device
     if model_cls not in _originals:
         _originals[model_cls] = (model_cls.__dict__.get("hamilton"), model_cls.__dict__.get("eigenval"))
@@ -96,3 +132,5 @@ def uninstall(model_cls=None):
                 setattr(cls, name, fn)
     for key in list(_cache):
         _drop(key)
+    for key in list(_kdotp_cache):
+        _kdotp_cache.pop(key)[1].close()

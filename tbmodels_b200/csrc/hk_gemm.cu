@@ -89,8 +89,8 @@ struct Cfg {
 
 // Q tiles: Qt[(m_tile * kchunks + c) * A_TILE + row * 16 + (col ^ ((row & 3) << 2))], col = 2*rq (cos), 2*rq+1 (sin)
 __global__ void __launch_bounds__(THREADS)
-hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, int dim, int kchunks,
-                double* __restrict__ Qt) {
+hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const int* __restrict__ Pw,
+                int kind, int dim, int kchunks, double* __restrict__ Qt) {
     extern __shared__ __align__(16) double ks[];  // [BM][dim]
     const int tid = threadIdx.x;
     const long m_tile = blockIdx.x;
@@ -102,6 +102,31 @@ hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restri
     __syncthreads();
     const int rq = tid & 7;
     const int mq = tid >> 3;
+    if (kind == 1) {
+        // k.p model: column q of Q is the monomial prod_d k_d^{p_d} of Taylor term q (kdotp.py:74); this thread
+        // writes terms 2 rq and 2 rq + 1 of each 16-term chunk
+        for (int c = blockIdx.y; c < kchunks; c += gridDim.y) {
+            const int* pw = Pw + ((size_t)c * 16 + 2 * rq) * dim;
+            double* tile = Qt + ((size_t)m_tile * kchunks + c) * A_TILE;
+#pragma unroll
+            for (int it = 0; it < BM / 32; ++it) {
+                const int m = mq + it * 32;
+                double mono[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    double v = 1.0;
+                    for (int d = 0; d < dim; ++d) {
+                        const double x = ks[m * dim + d];
+                        const int e = __ldg(pw + s * dim + d);
+                        for (int i = 0; i < e; ++i) v *= x;
+                    }
+                    mono[s] = v;
+                }
+                *reinterpret_cast<double2*>(tile + m * SA + ((2 * rq) ^ ((m & 3) << 2))) = make_double2(mono[0], mono[1]);
+            }
+        }
+        return;
+    }
     for (int c = blockIdx.y; c < kchunks; c += gridDim.y) {
         const double* rv = Rd + ((size_t)c * 8 + rq) * dim;
         double* tile = Qt + ((size_t)m_tile * kchunks + c) * A_TILE;
@@ -242,7 +267,7 @@ cudaError_t launch_hk_phase(const ModelDev& md, const double* k, long nk, double
     int ysplit = 1;
     while (m_tiles * ysplit < 592 && ysplit * 2 <= md.kchunks) ysplit *= 2;  // >= 4 CTAs per SM worth of work
     hk_phase_kernel<<<dim3((unsigned)m_tiles, (unsigned)ysplit), THREADS, (size_t)BM * md.dim * 8, st>>>(
-        k, nk, md.Rd, md.dim, md.kchunks, Qt);
+        k, nk, md.Rd, md.Pw, md.kind, md.dim, md.kchunks, Qt);
     return cudaGetLastError();
 }
 

@@ -74,6 +74,21 @@ void pack_weights_host(int n, int nR, const double* hop, double* W) {
     }
 }
 
+// one row per Taylor term: the packed lower triangle of the (Hermitian) coefficient matrix itself
+void pack_hermitian_rows_host(int n, int nterms, const double* mats, double* W) {
+    const long NN = (long)n * n;
+    const long nre = tri(n);
+    for (int q = 0; q < nterms; ++q) {
+        const double* C = mats + (size_t)q * NN * 2;
+        double* w = W + (size_t)q * NN;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j <= i; ++j) {
+                w[tri(i) + j] = C[((long)i * n + j) * 2];
+                if (j < i) w[nre + trs(i) + j] = C[((long)i * n + j) * 2 + 1];
+            }
+    }
+}
+
 }  // namespace
 
 struct tbk_model {
@@ -82,6 +97,7 @@ struct tbk_model {
     double* dRd = nullptr;
     double* dW = nullptr;
     int* dRi = nullptr;
+    int* dPw = nullptr;
     double* dWt = nullptr;
     double* dPos = nullptr;
     int* dFail = nullptr;
@@ -128,6 +144,46 @@ struct tbk_model {
     } while (0)
 
 namespace {
+
+// Tile the weight rows W[n_rows][n*n] for the GEMM (column tiles x 16-row K stages, padding baked in) and upload.
+int upload_gemm_weights(tbk_model* m, const std::vector<double>& W, int n_rows) {
+    ModelDev& md = m->md;
+    const long NN = (long)md.n * md.n;
+    // choose the column-tile width that wastes the fewest padded columns (ties -> wider)
+    const int cands[3] = {4, 8, 9};
+    long best_cols = -1;
+    for (int c : cands) {
+        const long bn = 16L * c;
+        const long cols = ((NN + bn - 1) / bn) * bn;
+        if (best_cols < 0 || cols <= best_cols) {
+            best_cols = cols;
+            md.na = c;
+        }
+    }
+    const int bn = 16 * md.na, sb = bn + 4;
+    md.n_tiles = (int)((NN + bn - 1) / bn);
+    md.kchunks = (n_rows + kGemmKC - 1) / kGemmKC;
+    const size_t stage = (size_t)kGemmKC * sb;
+    std::vector<double> Wt((size_t)std::max(md.n_tiles * md.kchunks, 1) * stage, 0.0);
+    for (int nt = 0; nt < md.n_tiles; ++nt)
+        for (int c = 0; c < md.kchunks; ++c) {
+            double* blk = Wt.data() + ((size_t)nt * md.kchunks + c) * stage;
+            for (int kk = 0; kk < kGemmKC; ++kk) {
+                const long q = (long)c * kGemmKC + kk;
+                if (q >= n_rows) continue;
+                const double* src = W.data() + (size_t)q * NN;
+                for (int col = 0; col < bn; ++col) {
+                    const long e = (long)nt * bn + col;
+                    if (e < NN) blk[(size_t)kk * sb + col] = src[e];
+                }
+            }
+        }
+    CU(cudaMalloc(&m->dWt, Wt.size() * 8));
+    CU(cudaMemcpy(m->dWt, Wt.data(), Wt.size() * 8, cudaMemcpyHostToDevice));
+    md.Wt = m->dWt;
+    m->model_bytes += Wt.size() * 8;
+    return TBK_OK;
+}
 
 long pick_chunk(const tbk_model* m) {
     size_t budget_mb = 2048;
@@ -379,40 +435,61 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
         CUB(cudaMemcpy(m->dRi, Ri.data(), Ri.size() * sizeof(int), cudaMemcpyHostToDevice));
         md.Ri = m->dRi;
     } else {
-        // choose the column-tile width that wastes the fewest padded columns (ties -> wider)
-        const int cands[3] = {4, 8, 9};
-        long best_cols = -1;
-        for (int c : cands) {
-            const long bn = 16L * c;
-            const long cols = ((NN + bn - 1) / bn) * bn;
-            if (best_cols < 0 || cols <= best_cols) {
-                best_cols = cols;
-                md.na = c;
-            }
-        }
-        const int bn = 16 * md.na, sb = bn + 4;
-        md.n_tiles = (int)((NN + bn - 1) / bn);
-        md.kchunks = md.nRpad / 8;
-        const size_t stage = (size_t)kGemmKC * sb;
-        std::vector<double> Wt((size_t)std::max(md.n_tiles * md.kchunks, 1) * stage, 0.0);
-        for (int nt = 0; nt < md.n_tiles; ++nt)
-            for (int c = 0; c < md.kchunks; ++c) {
-                double* blk = Wt.data() + ((size_t)nt * md.kchunks + c) * stage;
-                for (int kk = 0; kk < kGemmKC; ++kk) {
-                    const long q = (long)c * kGemmKC + kk;
-                    if (q >= 2L * n_R) continue;
-                    const double* src = W.data() + (size_t)q * NN;
-                    for (int col = 0; col < bn; ++col) {
-                        const long e = (long)nt * bn + col;
-                        if (e < NN) blk[(size_t)kk * sb + col] = src[e];
-                    }
-                }
-            }
-        CUB(cudaMalloc(&m->dWt, Wt.size() * 8));
-        CUB(cudaMemcpy(m->dWt, Wt.data(), Wt.size() * 8, cudaMemcpyHostToDevice));
-        md.Wt = m->dWt;
-        m->model_bytes += Wt.size() * 8;
+        if (int rc = upload_gemm_weights(m, W, 2 * n_R)) return bail(rc);
     }
+#undef CUB
+    *out = m;
+    return TBK_OK;
+}
+
+int tbk_kdotp_create(int dim, int n_orb, int n_terms, const int32_t* powers, const double* coeff, int device,
+                     tbk_model** out) {
+    if (!out) return fail(TBK_E_INVALID, "tbk_kdotp_create: out is null");
+    *out = nullptr;
+    if (n_orb < 1 || dim < 1) return fail(TBK_E_INVALID, "tbk_kdotp_create: bad sizes");
+    if (dim > kMaxDim) return fail(TBK_E_UNSUPPORTED, "tbk_kdotp_create: dim = %d > %d is not supported", dim, kMaxDim);
+    if (n_terms < 0 || (n_terms > 0 && (!powers || !coeff))) return fail(TBK_E_INVALID, "tbk_kdotp_create: bad arrays");
+    for (long i = 0; i < (long)n_terms * dim; ++i)
+        if (powers[i] < 0 || powers[i] > 64) return fail(TBK_E_INVALID, "tbk_kdotp_create: powers must be in [0, 64]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(TBK_E_CUDA, "tbk_kdotp_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TBK_E_INVALID, "tbk_kdotp_create: device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "tbk_kdotp_create: cudaSetDevice(%d) failed", device);
+    tbk_model* m = new (std::nothrow) tbk_model();
+    if (!m) return fail(TBK_E_INVALID, "out of host memory");
+    m->device = device;
+    ModelDev& md = m->md;
+    md.n = n_orb;
+    md.dim = dim;
+    md.nR = n_terms;
+    md.kind = 1;
+    md.small_ok = 0;
+    auto bail = [&](int rc) {
+        tbk_model_destroy(m);
+        return rc;
+    };
+#define CUB(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return bail(fail(TBK_E_CUDA, "%s -> %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    const long NN = (long)n_orb * n_orb;
+    std::vector<double> W((size_t)std::max(n_terms, 1) * NN, 0.0);
+    pack_hermitian_rows_host(n_orb, n_terms, coeff, W.data());
+    if (int rc = upload_gemm_weights(m, W, n_terms)) return bail(rc);
+    std::vector<int> Pw((size_t)std::max(md.kchunks, 1) * kGemmKC * dim, 0);
+    for (long i = 0; i < (long)n_terms * dim; ++i) Pw[i] = powers[i];
+    CUB(cudaMalloc(&m->dPw, Pw.size() * sizeof(int)));
+    CUB(cudaMemcpy(m->dPw, Pw.data(), Pw.size() * sizeof(int), cudaMemcpyHostToDevice));
+    md.Pw = m->dPw;
+    std::vector<double> zeros((size_t)n_orb * dim, 0.0);
+    CUB(cudaMalloc(&m->dPos, zeros.size() * 8));
+    CUB(cudaMemcpy(m->dPos, zeros.data(), zeros.size() * 8, cudaMemcpyHostToDevice));
+    md.pos = m->dPos;
+    CUB(cudaMalloc(&m->dFail, sizeof(int)));
+    CUB(cudaMemset(m->dFail, 0, sizeof(int)));
 #undef CUB
     *out = m;
     return TBK_OK;
@@ -425,6 +502,7 @@ int tbk_model_destroy(tbk_model* m) {
     cudaFree(m->dRd);
     cudaFree(m->dW);
     cudaFree(m->dRi);
+    cudaFree(m->dPw);
     cudaFree(m->dWt);
     cudaFree(m->dPos);
     cudaFree(m->dFail);

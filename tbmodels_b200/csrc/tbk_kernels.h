@@ -27,6 +27,10 @@ struct ModelDev {
     int n_tiles = 0;   // GEMM: column tiles
     int kchunks = 0;   // GEMM: nRpad / 8
     int small_ok = 0;  // fused thread-per-k kernel usable
+    // k.p models (reference src/tbmodels/kdotp.py:51-82): kind = 1, the GEMM coefficients are the monomials
+    // prod_d k_d^{p_d} instead of [cos | sin] phases; Pw holds the integer powers [kchunks * 16][dim]
+    int kind = 0;
+    const int* Pw = nullptr;
 };
 
 // H(k) build on the FP64 tensor cores: Hp[k][0..n*n) (packed Hermitian, see tbk_math.cuh).

@@ -379,3 +379,24 @@ def test_size_boundaries_vs_oracle(tbk, n_orb):
     nk = 37 if n_orb <= 128 else 5
     k = np.random.default_rng(n_orb).uniform(-1, 1, size=(nk, 3))
     _check(tbk, p, k, None, orc.hamilton(p.R, p.hop, p.pos, k[:3], 2), orc.eigenval_array(p.R, p.hop, p.pos, k), f"N={n_orb}")
+
+
+@pytest.mark.parametrize("tag", ["toy", "si0", "si1", "si2", "si3"])
+def test_kdotp_models(tbk, tag):
+    """k.p models (reference src/tbmodels/kdotp.py:51-100) through the same GEMM + eigensolver kernels."""
+    d = load_golden("kdotp.npz")
+    tc = {tuple(int(x) for x in p): c for p, c in zip(d[f"{tag}_powers"], d[f"{tag}_coeff"])}
+    m = tbk.KdotpModel(tc)
+    k = d[f"{tag}_k"]
+    H = m.hamilton(k)
+    scale = max(np.abs(d[f"{tag}_H"]).max(), 1.0)
+    assert H.shape == d[f"{tag}_H"].shape and np.abs(H - d[f"{tag}_H"]).max() <= 1e-11 * scale
+    assert np.array_equal(H, H.conj().transpose(0, 2, 1))
+    e = m.eigenval(k)
+    assert isinstance(e, list)
+    assert_eig_close(np.array(e), d[f"{tag}_eig"], tag)
+    # single point: squeezed result (kdotp.py:80-82, :97-100)
+    assert m.hamilton(tuple(k[1])).shape == H.shape[1:]
+    assert np.array_equal(m.eigenval(tuple(k[1])), e[1])
+    with pytest.raises(ValueError):
+        tbk.KdotpModel({(0, 0): [[0, 1], [2, 0]]})  # tests/test_kdotp.py:40-46

@@ -189,3 +189,14 @@ def test_workload_generators_golden():
     assert g.shape == (64, 3) and g[1].tolist() == [0, 0, 0.25]
     v = wl.shortest_half_vectors(13)
     assert len({tuple(x) for x in v}) == 13 and all(next(c for c in x if c != 0) > 0 for x in v)
+
+
+def test_kdotp_mirror_rejects_non_hermitian_and_packs_in_dict_order():
+    import tbmodels_b200 as tbk
+
+    with pytest.raises(ValueError, match="not hermitian"):
+        tbk.KdotpModel({(0, 0): [[0, 1], [2, 0]]})
+    m = tbk.KdotpModel({(0, 0): np.eye(2), (1, 0): [[0, 1j], [-1j, 0]], (0, 2): [[0, 1], [1, 0]]})
+    powers, coeff = tbk.pack_kdotp(m.taylor_coefficients)
+    assert powers.tolist() == [[0, 0], [1, 0], [0, 2]] and coeff.shape == (3, 2, 2)
+    assert pickle.loads(pickle.dumps(m))._cache is None

@@ -124,3 +124,17 @@ def test_oracle_equals_live_reference():
         assert np.array_equal(m.hamilton(k, convention=conv), orc.hamilton(p.R, p.hop, p.pos, k, conv))
     assert np.array_equal(np.array(m.eigenval(k)), np.array(orc.eigenval(p.R, p.hop, p.pos, k)))
     assert np.array_equal(m.hamilton(k[0]), orc.hamilton(p.R, p.hop, p.pos, k[0]))
+
+
+def test_kdotp_golden():
+    """KdotpModel.hamilton / eigenval restatement against the reference (kdotp.py:51-100)."""
+    d = load_golden("kdotp.npz")
+    for tag in ("toy", "si0", "si1", "si2", "si3"):
+        tc = {tuple(int(x) for x in p): c for p, c in zip(d[f"{tag}_powers"], d[f"{tag}_coeff"])}
+        k = d[f"{tag}_k"]
+        np.testing.assert_allclose(orc.kdotp_hamilton(tc, k), d[f"{tag}_H"], rtol=0, atol=1e-13)
+        assert_eig_close(np.array(orc.kdotp_eigenval(tc, k)), d[f"{tag}_eig"], tag)
+    # reference tests/test_kdotp.py:27-37 known answers
+    tc = {tuple(int(x) for x in p): c for p, c in zip(d["toy_powers"], d["toy_coeff"])}
+    assert np.allclose(orc.kdotp_hamilton(tc, (0, 0.5)), [[1, 0.25], [0.25, 1]])
+    assert np.allclose(orc.kdotp_eigenval(tc, [(0, 0), (0, 0), (0, 0.5)]), [[1, 1], [1, 1], [0.75, 1.25]])
