@@ -99,6 +99,8 @@ double tbk_measure_fp64_peak(int kind, int iters);
 /* ---- host-side debug entry points: run the exact scalar code of the kernels on the CPU (tests only) ---- */
 /* In-place eigenvalues of a real symmetric tridiagonal matrix; d[n], e[n] (e[n-1] scratch). Returns #failures. */
 int tbk_host_tridiag_ql(int n, double* d, double* e);
+/* sin(pi t), cos(pi t) as the fused small-N kernel computes them (tbk_math.cuh sincospi_lean). */
+int tbk_host_sincospi(double t, double* s, double* c);
 /* Same result by bisection with Sturm counts (the large-N device path); e is not modified. */
 int tbk_host_tridiag_bisect(int n, double* d, const double* e);
 /* Packed Hermitian (n*n doubles, destroyed) -> d[n], e[n]. */

@@ -34,6 +34,7 @@ SYMBOLS = (
     "tbk_measure_fp64_peak",
     "tbk_host_tridiag_ql",
     "tbk_host_tridiag_bisect",
+    "tbk_host_sincospi",
     "tbk_host_hetrd",
     "tbk_host_pack_weights",
 )
@@ -104,6 +105,8 @@ def load() -> C.CDLL:
     lib.tbk_host_tridiag_ql.restype = C.c_int
     lib.tbk_host_tridiag_bisect.argtypes = [C.c_int, dp, dp]
     lib.tbk_host_tridiag_bisect.restype = C.c_int
+    lib.tbk_host_sincospi.argtypes = [C.c_double, dp, dp]
+    lib.tbk_host_sincospi.restype = C.c_int
     lib.tbk_host_hetrd.argtypes = [C.c_int, dp, dp, dp]
     lib.tbk_host_hetrd.restype = C.c_int
     lib.tbk_host_pack_weights.argtypes = [C.c_int, C.c_int, dp, dp]

@@ -28,7 +28,7 @@ __device__ __forceinline__ double2 pos_phase(const double* __restrict__ kp, cons
     double x = 0.0;
     for (int d = 0; d < dim; ++d) x = fma(kp[d], __ldg(pos + orb * dim + d), x);
     double sn, cs;
-    sincospi(2.0 * x, &sn, &cs);
+    sincospi_lean(2.0 * x, sn, cs);
     return make_double2(cs, sn);
 }
 

@@ -23,6 +23,7 @@
 // The reduction order over R is fixed by the tiling, so a k-point's result does not depend on its
 // position in the batch (the reference tests compare batched and per-k calls at rtol 1e-7, atol 0).
 #include "tbk_kernels.h"
+#include "tbk_math.cuh"
 
 namespace tbk {
 
@@ -136,7 +137,7 @@ hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restri
             double x = 0.0;
             for (int d = 0; d < dim; ++d) x = fma(ks[m * dim + d], __ldg(rv + d), x);
             double sn, cs;
-            sincospi(2.0 * x, &sn, &cs);
+            sincospi_lean(2.0 * x, sn, cs);
             *reinterpret_cast<double2*>(tile + m * SA + ((2 * rq) ^ ((m & 3) << 2))) = make_double2(cs, sn);
         }
     }

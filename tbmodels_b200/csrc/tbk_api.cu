@@ -626,6 +626,11 @@ double tbk_measure_fp64_peak(int kind, int iters) { return measure_fp64_peak(kin
 
 int tbk_host_tridiag_ql(int n, double* d, double* e) { return tridiag_ql(n, d, e, 1); }
 
+int tbk_host_sincospi(double t, double* s, double* c) {
+    sincospi_lean(t, *s, *c);
+    return TBK_OK;
+}
+
 int tbk_host_tridiag_bisect(int n, double* d, const double* e) {
     if (n < 1) return fail(TBK_E_INVALID, "n < 1");
     std::vector<double> dd(d, d + n), e2((size_t)n, 0.0);
