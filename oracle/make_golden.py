@@ -295,6 +295,49 @@ def main():
             assert np.allclose(kp.eigenval((0, 0, 0)), si.eigenval(KPT[0]))
     np.savez_compressed(os.path.join(GOLD, "kdotp.npz"), **kd)
 
+    # ---- reference regression goldens of tests/test_wannier.py (:18-46, :182-214) and tests/test_simple_model.py (:12-20) ----
+    wg = {}
+    cases = [
+        ("hr_only_w90", dict(hr_file="wannier90_hr.dat", occ=28), "test_wannier_hr_only[wannier90_hr.dat]"),
+        ("hr_only_w90v2", dict(hr_file="wannier90_hr_v2.dat", occ=28), "test_wannier_hr_only[wannier90_hr_v2.dat]"),
+        ("hr_only_si", dict(hr_file="silicon_hr.dat", occ=28), "test_wannier_hr_only[silicon_hr.dat]"),
+        ("hr_wsvec_si", dict(hr_file="silicon_hr.dat", wsvec_file="silicon_wsvec.dat"),
+         "test_wannier_hr_wsvec[silicon_hr.dat-silicon_wsvec.dat]"),
+        ("hr_wsvec_bi", dict(hr_file="bi_hr.dat", wsvec_file="bi_wsvec.dat"), "test_wannier_hr_wsvec[bi_hr.dat-bi_wsvec.dat]"),
+        ("all_si", dict(hr_file="silicon_hr.dat", wsvec_file="silicon_wsvec.dat", xyz_file="silicon_centres.xyz",
+                        win_file="silicon.win", pos_kind="wannier", distance_ratio_threshold=1.0),
+         "test_wannier_all[silicon_hr.dat-silicon_wsvec.dat-silicon_centres.xyz-silicon.win-pos0-uc0-reciprocal_lattice0-wannier]"),
+        ("all_bi", dict(hr_file="bi_hr.dat", wsvec_file="bi_wsvec.dat", xyz_file="bi_centres.xyz", win_file="bi.win",
+                        pos_kind="wannier", distance_ratio_threshold=1.0),
+         "test_wannier_all[bi_hr.dat-bi_wsvec.dat-bi_centres.xyz-bi.win-pos1-uc1-reciprocal_lattice1-wannier]"),
+        ("all_bi_nearest", dict(hr_file="bi_hr.dat", wsvec_file="bi_wsvec.dat", xyz_file="bi_centres.xyz", win_file="bi.win",
+                                pos_kind="nearest_atom", distance_ratio_threshold=1.0),
+         "test_wannier_all[bi_hr.dat-bi_wsvec.dat-bi_centres.xyz-bi.win-pos2-uc2-reciprocal_lattice2-nearest_atom]"),
+    ]
+    for tag, kw, fname in cases:
+        kw = {k: (os.path.join(SAMPLES, v) if k.endswith("_file") else v) for k, v in kw.items()}
+        m = tb.Model.from_wannier_files(**kw)
+        H = np.array([m.hamilton(k) for k in KPT])  # convention 2, as the reference test
+        raw = open(os.path.join(REGRESSION, "test_wannier", fname), "rb").read()
+        blk = find_scattered(raw, H, tol=1e-8)
+        assert blk is not None, f"golden values not found in {fname}"
+        for key, val in packed_arrays(m).items():
+            wg[f"{tag}_{key}"] = val
+        wg[f"{tag}_H2"] = blk
+    wg["kpt"] = np.array(KPT)
+    np.savez_compressed(os.path.join(GOLD, "ref_wannier.npz"), **wg)
+
+    sm = {}
+    for ti, (t1, t2) in enumerate(T_VALUES):
+        model = simple_model(tb, t1, t2)
+        for ki, kpt in enumerate(KPT):
+            for what, val in (("hamilton", model.hamilton(kpt)), ("eigenval", model.eigenval(kpt))):
+                raw = open(os.path.join(REGRESSION, "test_simple_model", f"test_simple[False-k{ki}-t1{ti}]{what}"), "rb").read()
+                blk = find_scattered(raw, val)
+                assert blk is not None, (ti, ki, what)
+                sm[f"{what}_t{ti}_k{ki}"] = blk
+    np.savez_compressed(os.path.join(GOLD, "ref_simple_model.npz"), **sm)
+
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print(f"wrote {len(os.listdir(GOLD))} files, {total / 1e6:.2f} MB, to {GOLD}")
 

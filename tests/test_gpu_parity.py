@@ -400,3 +400,28 @@ def test_kdotp_models(tbk, tag):
     assert np.array_equal(m.eigenval(tuple(k[1])), e[1])
     with pytest.raises(ValueError):
         tbk.KdotpModel({(0, 0): [[0, 1], [2, 0]]})  # tests/test_kdotp.py:40-46
+
+
+@pytest.mark.parametrize("tag", ["hr_only_w90", "hr_only_w90v2", "hr_only_si", "hr_wsvec_si", "hr_wsvec_bi", "all_si", "all_bi", "all_bi_nearest"])
+def test_reference_wannier_goldens(tbk, tag):
+    """The reference's own goldens for Wannier90-derived models (tests/test_wannier.py): N = 7, 8, 10."""
+    d = load_golden("ref_wannier.npz")
+    p = packed_from(d, tag + "_")
+    m = tbk.KModel.from_packed(p)
+    got = np.array([m.hamilton(tuple(k)) for k in d["kpt"]])  # per-k calls, exactly like the reference test
+    want = d[f"{tag}_H2"]
+    assert np.allclose(got, want)
+    assert_h_close(got, want, p, tag)
+    assert np.array_equal(got, m.hamilton(d["kpt"]))
+
+
+def test_reference_simple_model_goldens(tbk):
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("ref_simple_model.npz")
+    r = load_golden("ref_regression.npz")
+    for ti, (t1, t2) in enumerate(r["t_values"]):
+        m = tbk.KModel.from_packed(wl.simple_model(t1, t2))
+        for ki, kpt in enumerate(r["kpt"]):
+            assert np.abs(m.hamilton(tuple(kpt)) - d[f"hamilton_t{ti}_k{ki}"]).max() < 1e-11
+            assert np.abs(m.eigenval(tuple(kpt)) - d[f"eigenval_t{ti}_k{ki}"]).max() < 1e-10

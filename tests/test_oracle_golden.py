@@ -138,3 +138,29 @@ def test_kdotp_golden():
     tc = {tuple(int(x) for x in p): c for p, c in zip(d["toy_powers"], d["toy_coeff"])}
     assert np.allclose(orc.kdotp_hamilton(tc, (0, 0.5)), [[1, 0.25], [0.25, 1]])
     assert np.allclose(orc.kdotp_eigenval(tc, [(0, 0), (0, 0), (0, 0.5)]), [[1, 1], [1, 1], [0.75, 1.25]])
+
+
+WANNIER_TAGS = ["hr_only_w90", "hr_only_w90v2", "hr_only_si", "hr_wsvec_si", "hr_wsvec_bi", "all_si", "all_bi", "all_bi_nearest"]
+
+
+def test_reference_wannier_goldens():
+    """tests/regression_data/test_wannier/* (reference tests/test_wannier.py:18-46, :182-214): [hamilton(k) for k in KPT]."""
+    d = load_golden("ref_wannier.npz")
+    for tag in WANNIER_TAGS:
+        p = packed_from(d, tag + "_")
+        got = orc.hamilton(p.R, p.hop, p.pos, d["kpt"], 2)
+        want = d[f"{tag}_H2"]
+        assert np.allclose(got, want) and np.abs(got - want).max() < 1e-10, tag
+
+
+def test_reference_simple_model_goldens():
+    """tests/regression_data/test_simple_model/* (reference tests/test_simple_model.py:12-20)."""
+    from tbmodels_b200 import workloads as wl
+
+    d = load_golden("ref_simple_model.npz")
+    r = load_golden("ref_regression.npz")
+    for ti, (t1, t2) in enumerate(r["t_values"]):
+        p = wl.simple_model(t1, t2)
+        for ki, kpt in enumerate(r["kpt"]):
+            assert np.abs(orc.hamilton(p.R, p.hop, p.pos, kpt) - d[f"hamilton_t{ti}_k{ki}"]).max() < 1e-12
+            assert np.abs(orc.eigenval(p.R, p.hop, p.pos, kpt) - d[f"eigenval_t{ti}_k{ki}"]).max() < 1e-12
