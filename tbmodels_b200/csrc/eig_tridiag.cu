@@ -1,15 +1,17 @@
 // eig_tridiag.cu -- batched Hermitian -> real symmetric tridiagonal reduction (eigenvalues only).
 //
 // First half of the replacement for the per-k scipy.linalg.eigvalsh loop of Model.eigenval
-// (reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr with JOBZ='N', UPLO='L').
-// A group of G threads (8 .. 256, chosen from N only, never from the batch) reduces one packed
-// lower-triangular matrix with unblocked Householder reflections:
+// (reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr with JOBZ='N', UPLO='L'): unblocked Householder
+// reflections on the packed lower triangle,
 //     x = A[j+1:, j]  ->  (beta, tau, v);   p = tau A22 v;   w = p - (tau/2)(p^H v) v;   A22 -= v w^H + w v^H.
-// For N <= 160 the matrix is copied once into shared memory (packed: N^2 doubles) and never goes back to
-// HBM; above that the group works in place on the packed H(k) scratch in global memory (L2 resident per
-// chunk).  Every group executes exactly the same instruction sequence (no data-dependent early exits), so
-// sub-warp groups can share a warp and use __syncwarp().  Outputs: D[k][0..N) diagonal, E[k][0..N-1)
-// sub-diagonal, consumed by eig_ql.cu.
+// Four kernels, chosen from N only (never from the batch, so a k-point's bits do not depend on the batch):
+//   tridiag_smem_kernel<G, CS>  N <= 164: matrix in shared memory as interleaved complex packed rows, G threads per
+//                               matrix (8 .. 512) = row threads x CS column slices
+//   tridiag_big_kernel<MAXC>    165 <= N <= 640: 16 warps per matrix, in place in global memory, coalesced row sweeps
+//   tridiag_global_kernel       larger: thread-per-row fallback
+//   tridiag_mma_kernel          experimental tensor-core rank-2 update (opt-in, see below)
+// Every group executes exactly the same instruction sequence (no data-dependent early exits), so sub-warp groups can
+// share a warp and use __syncwarp().  Outputs: D[k][0..N) diagonal, E[k][0..N-1) sub-diagonal, consumed by eig_ql.cu.
 #include <cstdlib>
 
 #include "tbk_kernels.h"
@@ -58,41 +60,26 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* red, in
     }
 }
 
-template <int G>
+// Last-resort variant for matrices beyond the row-sweep kernel's limit (N > 640): one CTA of 256 threads per matrix,
+// in place on the packed planes in global memory, one thread per row.  Simple and slow; kept so that no size fails.
 __global__ void __launch_bounds__(TPB)
-tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E, int in_smem) {
-    const int MPB = blockDim.x / G;  // matrices per CTA (run time: bounded by shared memory)
-    constexpr int NW = G > 32 ? G / 32 : 1;
+tridiag_global_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    constexpr int G = TPB;
+    constexpr int NW = G / 32;
     extern __shared__ __align__(16) double sm[];
-    const int group = threadIdx.x / G;
-    const int t = threadIdx.x % G;
+    const int t = threadIdx.x;
     const long NN = (long)N * N;
     const long nre = tri(N);
-
-    const long kidx = (long)blockIdx.x * MPB + group;
-    const bool valid = kidx < nk;
-    const long kk = valid ? kidx : nk - 1;  // idle groups shadow the last matrix (smem mode only) and store nothing
-
-    // per-group shared-memory carve-up
-    const long per_group = (in_smem ? NN : 0) + 6L * N + 4 * NW + 2;
-    double* base = sm + group * per_group;
-    double* A = in_smem ? base : (Hp + kk * NN);
-    double* Vr = base + (in_smem ? NN : 0);
+    const long kk = blockIdx.x;
+    if (kk >= nk) return;
+    double* A = Hp + kk * NN;
+    double* Vr = sm;
     double* Vi = Vr + N;
     double* Pr = Vi + N;
     double* Pi = Pr + N;
     double* ds = Pi + N;
     double* es = ds + N;
     double* red = es + N;
-
-    if (!in_smem && !valid) return;  // MPB == 1 in global mode: whole CTA leaves together
-
-    if (in_smem) {
-        const double* src = Hp + kk * NN;
-        for (long e = t; e < NN; e += G) A[e] = src[e];
-    }
-    group_sync<G>(group);
-
     double* Ar = A;
     double* Ai = A + nre;
     int parity = 0;
@@ -100,7 +87,6 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
     for (int j = 0; j < N - 1; ++j) {
         const int m = N - 1 - j;
         const int r0 = j + 1;
-        // --- reflector from column j ---
         const double ar = Ar[tri(r0) + j];
         const double ai = Ai[trs(r0) + j];
         double xn = 0.0, dummy = 0.0;
@@ -109,7 +95,7 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
             const double xr = Ar[tri(I) + j], xi = Ai[trs(I) + j];
             xn += xr * xr + xi * xi;
         }
-        group_sum2<G>(xn, dummy, red, group, t, parity);
+        group_sum2<G>(xn, dummy, red, 0, t, parity);
         double beta, tr, ti, sr, si;
         householder_gen(ar, ai, xn, beta, tr, ti, sr, si);
         if (t == 0) {
@@ -127,15 +113,12 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
                 Vi[a] = xr * si + xi * sr;
             }
         }
-        group_sync<G>(group);
-        // --- p = tau * A22 v, dot = p^H v ---
+        group_sync<G>(0);
         double dr = 0.0, di = 0.0;
         for (int a = t; a < m; a += G) {
             const long I = r0 + a;
             double sumr = 0.0, sumi = 0.0;
             const long rowI = tri(I), rowIs = trs(I);
-            // one pass over the row of the full Hermitian matrix: left of the diagonal read the own packed
-            // row, right of it the conjugate of column I (same trip count for every lane of the group)
             long triJ = tri(r0), trsJ = trs(r0);
             for (int b = 0; b < m; ++b) {
                 const long J = r0 + b;
@@ -158,7 +141,7 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
             dr += pr * Vr[a] + pi * Vi[a];
             di += pr * Vi[a] - pi * Vr[a];
         }
-        group_sum2<G>(dr, di, red, group, t, parity);
+        group_sum2<G>(dr, di, red, 0, t, parity);
         const double alr = -0.5 * (tr * dr - ti * di);
         const double ali = -0.5 * (tr * di + ti * dr);
         for (int a = t; a < m; a += G) {
@@ -166,8 +149,7 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
             Pr[a] += alr * vr - ali * vi;
             Pi[a] += alr * vi + ali * vr;
         }
-        group_sync<G>(group);
-        // --- A22 -= v w^H + w v^H (lower triangle) ---
+        group_sync<G>(0);
         for (int a = t; a < m; a += G) {
             const long I = r0 + a;
             const double var = Vr[a], vai = Vi[a], war = Pr[a], wai = Pi[a];
@@ -180,18 +162,16 @@ tridiag_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, 
             }
             rowr[a] -= 2.0 * (var * war + vai * wai);
         }
-        group_sync<G>(group);
+        group_sync<G>(0);
     }
     if (t == 0) {
         ds[N - 1] = Ar[tri(N - 1) + (N - 1)];
         es[N - 1] = 0.0;
     }
-    group_sync<G>(group);
-    if (valid) {
-        for (int i = t; i < N; i += G) {
-            D[kidx * N + i] = ds[i];
-            E[kidx * N + i] = es[i];
-        }
+    group_sync<G>(0);
+    for (int i = t; i < N; i += G) {
+        D[kk * N + i] = ds[i];
+        E[kk * N + i] = es[i];
     }
 }
 
@@ -899,11 +879,12 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         if (n <= 32 * 20) return launch_big<20>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
     }
     const size_t smem = (size_t)(6L * n + 4 * 8 + 2) * 8;
-    cudaError_t err = cudaFuncSetAttribute(tridiag_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;  // N > ~4800
+    cudaError_t err = cudaFuncSetAttribute(tridiag_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_kernel<256><<<(unsigned)nk, 256, smem, st>>>(Hp, n, nk, D, E, 0);
+    tridiag_global_kernel<<<(unsigned)nk, TPB, smem, st>>>(Hp, n, nk, D, E);
     return cudaGetLastError();
 }
 

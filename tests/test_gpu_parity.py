@@ -425,3 +425,14 @@ def test_reference_simple_model_goldens(tbk):
         for ki, kpt in enumerate(r["kpt"]):
             assert np.abs(m.hamilton(tuple(kpt)) - d[f"hamilton_t{ti}_k{ki}"]).max() < 1e-11
             assert np.abs(m.eigenval(tuple(kpt)) - d[f"eigenval_t{ti}_k{ki}"]).max() < 1e-10
+
+
+def test_oversize_matrix_fallback(tbk):
+    """N = 650 is past the row-sweep kernel's limit (640): exercises the thread-per-row fallback and bisection."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(650, 2, seed=3)
+    k = np.array([[0.11, 0.52, -0.3], [0.0, 0.0, 0.0]])
+    got = tbk.Evaluator(p).eigenval_array(k)
+    assert_eig_close(got, orc.eigenval_array(p.R, p.hop, p.pos, k), "N=650")
