@@ -874,6 +874,7 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         return cudaGetLastError();
     }
     // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
+    if (!getenv("TBK_TRIDIAG_NOPANEL") && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st);
     if (!getenv("TBK_TRIDIAG_OLDBIG")) {
         if (n <= 32 * 16) return launch_big<16>(n, Hp, nk, D, E, st);
         if (n <= 32 * 20) return launch_big<20>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
@@ -895,6 +896,9 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     if (const char* e = getenv("TBK_TRIDIAG_G")) g = atoi(e);  // tuning hooks: threads per matrix / column slices
     if (const char* e = getenv("TBK_TRIDIAG_CS")) cs = atoi(e);
     if (g == 1) return launch_mma(n, Hp, nk, D, E, st);
+    if (const char* e = getenv("TBK_TRIDIAG_PANEL_MIN")) {  // tuning hook: blocked kernel from this size on
+        if (n >= atoi(e) && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st);
+    }
     // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
     //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
     if (g == 0) {  // defaults, from N only (never from the batch: results must not depend on the batch size)

@@ -1,0 +1,357 @@
+// eig_tridiag_panel.cu -- blocked (panel) Hermitian -> tridiagonal reduction for matrices that live in L2 / HBM.
+//
+// Same role as eig_tridiag.cu (first half of the replacement for the per-k scipy.linalg.eigvalsh loop of
+// Model.eigenval, reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr JOBZ='N', UPLO='L'), for sizes whose
+// matrix does not fit in shared memory (N > 164; C4: N = 512).  The unblocked kernel streams the trailing matrix three
+// times per Householder step (product: read; rank-2 update: read + write).  Here the update is deferred over panels of
+// NB = 8 columns (the textbook latrd/her2k organisation, restated):
+//   for every column c of the panel
+//       a      = A[c:, c] - V W[c,:]^H - W V[c,:]^H                    (column brought up to date, O(N NB))
+//       v, tau = reflector(a)                                           (same contract as tbk_math.cuh householder_gen)
+//       p      = A22 v - V (W^H v) - W (V^H v)                          (A22 = the STORED trailing matrix, read once)
+//       w      = tau p - (tau/2)((tau p)^H v) v
+//   A22 -= V W^H + W V^H   once per panel, on the FP64 tensor cores:
+//       Re(A) -= [vr vi wr wi].[wr wi vr vi]^T,  Im(A) -= [vi -vr wi -wr].[wr wi vr vi]^T   -> per 8x8 block and plane
+//       NB mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) accumulating in place on fragments loaded from / stored to the packed
+//       planes in global memory.
+// The matrix is therefore read (1 + 2/NB) times per step instead of 3.  One CTA per matrix; the Hermitian product is
+// organised as coalesced row sweeps over the lower triangle exactly like tridiag_big_kernel (row part reduced per row,
+// column part scattered into per-lane register accumulators and combined across warps in a fixed order: no atomics,
+// bits do not depend on the batch).
+#include "tbk_kernels.h"
+#include "tbk_math.cuh"
+
+namespace tbk {
+
+namespace {
+
+constexpr int NB = 8;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Sum (a, b) over the CTA; every thread gets the result.  Fixed order; double-buffered: one barrier per call.
+template <int WARPS>
+__device__ __forceinline__ void cta_sum2(double& a, double& b, double* red, int tid, int& parity) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    double* buf = red + parity * 2 * WARPS;
+    parity ^= 1;
+    if ((tid & 31) == 0) {
+        buf[2 * (tid >> 5)] = a;
+        buf[2 * (tid >> 5) + 1] = b;
+    }
+    __syncthreads();
+    a = 0.0;
+    b = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        a += buf[2 * w];
+        b += buf[2 * w + 1];
+    }
+}
+
+__host__ __device__ inline size_t panel_smem_doubles(int n, int warps) {
+    const int slots = warps / 4;
+    return (size_t)4 * NB * n + (size_t)2 * n * (3 + slots) + 2 * (size_t)n + 4 * NB + 4 * warps + 4;
+}
+
+template <int THREADS, int MAXC>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 2))
+tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int SLOTS = WARPS / 4;
+    extern __shared__ __align__(16) double smp[];
+    double* X = smp;                                              // [NB][N][4] = (vr, vi, wr, wi) of panel column p, row r
+    double2* V = reinterpret_cast<double2*>(X + (size_t)4 * NB * N);  // [N] current reflector, index i = row - r0
+    double2* P = V + N;                                           // [N] tau * p
+    double2* S = P + N;                                           // [N] row-part sums
+    double2* QW = S + N;                                          // [SLOTS][N] column-part partial sums
+    double* ds = reinterpret_cast<double*>(QW + (size_t)SLOTS * N);
+    double* es = ds + N;
+    double2* Y = reinterpret_cast<double2*>(es + N);              // [2 NB]: Y[2p] = W_p^H v, Y[2p+1] = V_p^H v
+    double* red = reinterpret_cast<double*>(Y + 2 * NB);          // [2][2 WARPS]
+    double* misc = red + 4 * WARPS;                               // alpha (re, im)
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long kk = blockIdx.x;
+    if (kk >= nk) return;
+    double* Ar = Hp + kk * (long)N * N;
+    double* Ai = Ar + tri(N);
+    int parity = 0;
+
+    for (int k0 = 0; k0 < N; k0 += NB) {
+        const int nb = (N - k0 < NB) ? (N - k0) : NB;
+        for (int j = 0; j < nb; ++j) {
+            const int c = k0 + j;
+            const int m = N - 1 - c;  // size of the trailing block below / right of column c
+            const int r0 = c + 1;
+            // --- (1) column c of the matrix, brought up to date with the panel's previous reflectors ---
+            double xn = 0.0, dummy = 0.0;
+            for (int i = tid; i <= m; i += THREADS) {  // row r = c + i; i = 0 is the diagonal
+                const long r = c + i;
+                double ax = Ar[tri(r) + c];
+                double ay = (i > 0) ? Ai[trs(r) + c] : 0.0;
+                for (int p = 0; p < j; ++p) {
+                    const double2 xv = *reinterpret_cast<const double2*>(X + ((size_t)p * N + r) * 4);
+                    const double2 xw = *reinterpret_cast<const double2*>(X + ((size_t)p * N + r) * 4 + 2);
+                    const double2 cv = *reinterpret_cast<const double2*>(X + ((size_t)p * N + c) * 4);
+                    const double2 cw = *reinterpret_cast<const double2*>(X + ((size_t)p * N + c) * 4 + 2);
+                    // a -= V[r,p] conj(W[c,p]) + W[r,p] conj(V[c,p])
+                    ax = fma(-xv.x, cw.x, fma(-xv.y, cw.y, fma(-xw.x, cv.x, fma(-xw.y, cv.y, ax))));
+                    ay = fma(-xv.y, cw.x, fma(xv.x, cw.y, fma(-xw.y, cv.x, fma(xw.x, cv.y, ay))));
+                }
+                if (i == 0) {
+                    ds[c] = ax;
+                } else {
+                    V[i - 1] = make_double2(ax, ay);  // raw column, scaled below
+                    if (i == 1) {
+                        misc[0] = ax;
+                        misc[1] = ay;
+                    } else {
+                        xn = fma(ax, ax, fma(ay, ay, xn));
+                    }
+                }
+            }
+            if (m == 0) {  // last column: only its diagonal entry
+                if (tid == 0) es[c] = 0.0;
+                __syncthreads();
+                continue;
+            }
+            cta_sum2<WARPS>(xn, dummy, red, tid, parity);
+            double beta, tr, ti, sr, si;
+            householder_gen(misc[0], misc[1], xn, beta, tr, ti, sr, si);
+            // --- (2) v = [1; scale * x]; kept in V (this step) and in X[j] (panel) ---
+            for (int i = tid; i < m; i += THREADS) {
+                double2 v = make_double2(1.0, 0.0);  // (alpha was read from misc, nobody reads the raw V[0])
+                if (i > 0) {
+                    const double2 x = V[i];
+                    v = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
+                }
+                V[i] = v;
+                *reinterpret_cast<double2*>(X + ((size_t)j * N + r0 + i) * 4) = v;
+            }
+            if (tid == 0) es[c] = beta;
+            __syncthreads();
+            // --- (2b) y1[p] = W_p^H v, y2[p] = V_p^H v for the previous panel columns: one warp per dot product ---
+            for (int q = w; q < 2 * j; q += WARPS) {
+                const int p = q >> 1;
+                const int off = (q & 1) ? 0 : 2;  // even q: W (y1), odd q: V (y2)
+                double yr = 0.0, yi = 0.0;
+                for (int i = lane; i < m; i += 32) {
+                    const double2 x = *reinterpret_cast<const double2*>(X + ((size_t)p * N + r0 + i) * 4 + off);
+                    const double2 v = V[i];
+                    yr = fma(x.x, v.x, fma(x.y, v.y, yr));
+                    yi = fma(x.x, v.y, fma(-x.y, v.x, yi));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    yr += __shfl_xor_sync(0xffffffffu, yr, o);
+                    yi += __shfl_xor_sync(0xffffffffu, yi, o);
+                }
+                if (lane == 0) Y[q] = make_double2(yr, yi);
+            }
+            // --- (3) Hermitian product with the stored trailing block: row sweeps over the lower triangle ---
+            double2 qacc[MAXC];
+#pragma unroll
+            for (int cc = 0; cc < MAXC; ++cc) qacc[cc] = make_double2(0.0, 0.0);
+            for (int a = w; a < m; a += WARPS) {
+                const long I = r0 + a;
+                const double* rre = Ar + tri(I) + r0;
+                const double* rim = Ai + trs(I) + r0;
+                const double2 va = V[a];
+                double sumr = 0.0, sumi = 0.0;
+#pragma unroll
+                for (int c0 = 0; c0 < MAXC; c0 += 4) {
+                    if (c0 * 32 < a) {  // warp-uniform; four 32-column chunks per batch: 8 loads in flight per lane
+                        double zr[4], zi[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int b = (c0 + q) * 32 + lane;
+                            const bool ok = b < a;
+                            zr[q] = ok ? rre[b] : 0.0;
+                            zi[q] = ok ? rim[b] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int b = (c0 + q) * 32 + lane;
+                            if (b < a) {
+                                const double2 vb = V[b];
+                                sumr = fma(zr[q], vb.x, fma(-zi[q], vb.y, sumr));
+                                sumi = fma(zr[q], vb.y, fma(zi[q], vb.x, sumi));
+                                qacc[c0 + q].x = fma(zr[q], va.x, fma(zi[q], va.y, qacc[c0 + q].x));  // conj(z) v_a
+                                qacc[c0 + q].y = fma(zr[q], va.y, fma(-zi[q], va.x, qacc[c0 + q].y));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sumr += __shfl_xor_sync(0xffffffffu, sumr, o);
+                    sumi += __shfl_xor_sync(0xffffffffu, sumi, o);
+                }
+                if (lane == 0) {
+                    const double dg = rre[a];  // real diagonal
+                    S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
+                }
+            }
+            // column parts: four rounds, warp w adds into slot w / 4 in round w % 4 (fixed order)
+#pragma unroll
+            for (int round = 0; round < 4; ++round) {
+                if ((w & 3) == round) {
+                    double2* slot = QW + (size_t)(w >> 2) * N;
+#pragma unroll
+                    for (int cc = 0; cc < MAXC; ++cc) {
+                        const int b = cc * 32 + lane;
+                        if (b < m) {
+                            if (round == 0) {
+                                slot[b] = qacc[cc];
+                            } else {
+                                double2 t2 = slot[b];
+                                t2.x += qacc[cc].x;
+                                t2.y += qacc[cc].y;
+                                slot[b] = t2;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // --- (4) p = A22 v - V y1 - W y2;  tau p;  dot = (tau p)^H v ---
+            double dr = 0.0, di = 0.0;
+            for (int a = tid; a < m; a += THREADS) {
+                double2 q = S[a];
+#pragma unroll
+                for (int sl = 0; sl < SLOTS; ++sl) {
+                    const double2 t2 = QW[(size_t)sl * N + a];
+                    q.x += t2.x;
+                    q.y += t2.y;
+                }
+                for (int p = 0; p < j; ++p) {
+                    const double2 xv = *reinterpret_cast<const double2*>(X + ((size_t)p * N + r0 + a) * 4);
+                    const double2 xw = *reinterpret_cast<const double2*>(X + ((size_t)p * N + r0 + a) * 4 + 2);
+                    const double2 y1 = Y[2 * p], y2 = Y[2 * p + 1];
+                    q.x = fma(-xv.x, y1.x, fma(xv.y, y1.y, fma(-xw.x, y2.x, fma(xw.y, y2.y, q.x))));
+                    q.y = fma(-xv.x, y1.y, fma(-xv.y, y1.x, fma(-xw.x, y2.y, fma(-xw.y, y2.x, q.y))));
+                }
+                const double pr = tr * q.x - ti * q.y;
+                const double pi = tr * q.y + ti * q.x;
+                P[a] = make_double2(pr, pi);
+                const double2 va = V[a];
+                dr += pr * va.x + pi * va.y;
+                di += pr * va.y - pi * va.x;
+            }
+            cta_sum2<WARPS>(dr, di, red, tid, parity);
+            const double alr = -0.5 * (tr * dr - ti * di);
+            const double ali = -0.5 * (tr * di + ti * dr);
+            for (int a = tid; a < m; a += THREADS) {
+                const double2 v = V[a];
+                const double2 pq = P[a];
+                *reinterpret_cast<double2*>(X + ((size_t)j * N + r0 + a) * 4 + 2) =
+                    make_double2(pq.x + alr * v.x - ali * v.y, pq.y + alr * v.y + ali * v.x);
+            }
+            __syncthreads();
+        }
+        // --- trailing update A22 -= V W^H + W V^H on the FP64 tensor cores (rows / columns >= k0 + NB) ---
+        const int rt = k0 + nb;
+        if (rt < N) {  // then nb == NB and rt is a multiple of 8
+            const int I0 = rt >> 3;
+            const int NBk = (N + 7) >> 3;
+            const int g = lane >> 2, tq = lane & 3;
+            const double sgn = (tq & 1) ? 1.0 : -1.0;
+            int I = I0, s = w;
+            for (;;) {
+                int ns = ((I - I0) >> 2) + 1;  // 8 x 32 strips in block row I
+                while (I < NBk && s >= ns) {
+                    s -= ns;
+                    ++I;
+                    ns = ((I - I0) >> 2) + 1;
+                }
+                if (I >= NBk) break;
+                const int row = 8 * I + g;
+                const bool row_ok = row < N;
+                const int rowc = row_ok ? row : N - 1;
+                double xr[NB], xi[NB];
+#pragma unroll
+                for (int p = 0; p < NB; ++p) {
+                    xr[p] = -X[((size_t)p * N + rowc) * 4 + tq];             // -(vr, vi, wr, wi)[tq]
+                    xi[p] = sgn * X[((size_t)p * N + rowc) * 4 + (tq ^ 1)];  // (-vi, vr, -wi, wr)[tq]
+                }
+                double* pre = Ar + tri((long)rowc);
+                double* pim = Ai + trs((long)rowc);
+                const int J0 = I0 + 4 * s;
+                double cre[4][2], cim[4][2];
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) {
+                    const int col = 8 * (J0 + jb) + 2 * tq;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        cre[jb][h] = (row_ok && col + h <= row) ? pre[col + h] : 0.0;
+                        cim[jb][h] = (row_ok && col + h < row) ? pim[col + h] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) {
+                    if (J0 + jb <= I) {  // warp-uniform
+                        int colg = 8 * (J0 + jb) + g;
+                        if (colg >= N) colg = N - 1;
+#pragma unroll
+                        for (int p = 0; p < NB; ++p) {
+                            const double y = X[((size_t)p * N + colg) * 4 + (tq ^ 2)];  // (wr, wi, vr, vi)[tq]
+                            dmma884(cre[jb][0], cre[jb][1], xr[p], y);
+                            dmma884(cim[jb][0], cim[jb][1], xi[p], y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) {
+                    const int col = 8 * (J0 + jb) + 2 * tq;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (row_ok && col + h <= row) pre[col + h] = cre[jb][h];
+                        if (row_ok && col + h < row) pim[col + h] = cim[jb][h];
+                    }
+                }
+                s += WARPS;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += THREADS) {
+        D[kk * N + i] = ds[i];
+        E[kk * N + i] = (i < N - 1) ? es[i] : 0.0;
+    }
+}
+
+template <int THREADS, int MAXC>
+cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    const size_t smem = panel_smem_doubles(n, THREADS / 32) * 8;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (nk <= 0) return cudaSuccess;
+    if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_panel_kernel<THREADS, MAXC><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tridiag_panel_fits(int n) { return n >= 2 && n <= 640 && panel_smem_doubles(n, 16) * 8 <= 227 * 1024; }
+
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+    if (n <= 128) return launch_panel_t<256, 4>(n, Hp, nk, D, E, st);
+    if (n <= 256) return launch_panel_t<256, 8>(n, Hp, nk, D, E, st);
+    if (n <= 512) return launch_panel_t<512, 16>(n, Hp, nk, D, E, st);
+    return launch_panel_t<512, 20>(n, Hp, nk, D, E, st);
+}
+
+}  // namespace tbk

@@ -47,6 +47,9 @@ cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp,
                           double* out, cudaStream_t st);
 // Batched Hermitian -> tridiagonal reduction (Hp is destroyed). D, E: [nk][n].
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
+// Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
+bool tridiag_panel_fits(int n);
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
 // Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st);
 // Matrices per full wave of the QL kernel on the current device (chunks are sized in whole waves); 0 if n/a.
