@@ -18,6 +18,8 @@
 // organised as coalesced row sweeps over the lower triangle exactly like tridiag_big_kernel (row part reduced per row,
 // column part scattered into per-lane register accumulators and combined across warps in a fixed order: no atomics,
 // bits do not depend on the batch).
+#include <cstdlib>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -31,6 +33,55 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }  // 32-bit: offsets inside one matrix
+__device__ __forceinline__ int itrs(int i) { return (i * (i - 1)) >> 1; }
+
+// Pull columns [c0, c0 + len) of row I of both planes into L2 (bulk prefetch: 16-byte granularity, no registers).
+__device__ __forceinline__ void prefetch_row(const double* Ar, const double* Ai, int I, int c0, int len) {
+    if (len <= 0) return;
+    const unsigned long long b0 = reinterpret_cast<unsigned long long>(Ar + itri(I) + c0);
+    const unsigned long long b1 = reinterpret_cast<unsigned long long>(Ai + itrs(I) + c0);
+    const unsigned long long s0 = b0 & ~15ull, s1 = b1 & ~15ull;
+    const unsigned n0 = (unsigned)(((b0 + 8ull * len + 15ull) & ~15ull) - s0);
+    const unsigned n1 = (unsigned)(((b1 + 8ull * len + 15ull) & ~15ull) - s1);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s0), "r"(n0) : "memory");
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s1), "r"(n1) : "memory");
+}
+
+// 8-byte global load at a compile-time byte offset from a materialised row pointer (keeps the address arithmetic of
+// the unrolled row sweep down to one pointer per row and plane).
+template <int OFF>
+__device__ __forceinline__ double ldg_off(unsigned long long gptr) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1+%2];" : "=d"(v) : "l"(gptr), "n"(OFF) : "memory");
+    return v;
+}
+
+// Four 32-column chunks of one row (both planes) starting OFF bytes past the row pointers; rem = columns left for this
+// lane (chunk q is inside the row iff 32 q < rem).
+template <int OFF>
+__device__ __forceinline__ void load4(unsigned long long pr, unsigned long long pi, int rem, double (&zr)[4],
+                                      double (&zi)[4]) {
+    zr[0] = zr[1] = zr[2] = zr[3] = 0.0;
+    zi[0] = zi[1] = zi[2] = zi[3] = 0.0;
+    if (0 < rem) {
+        zr[0] = ldg_off<OFF>(pr);
+        zi[0] = ldg_off<OFF>(pi);
+    }
+    if (32 < rem) {
+        zr[1] = ldg_off<OFF + 256>(pr);
+        zi[1] = ldg_off<OFF + 256>(pi);
+    }
+    if (64 < rem) {
+        zr[2] = ldg_off<OFF + 512>(pr);
+        zi[2] = ldg_off<OFF + 512>(pi);
+    }
+    if (96 < rem) {
+        zr[3] = ldg_off<OFF + 768>(pr);
+        zi[3] = ldg_off<OFF + 768>(pi);
+    }
 }
 
 // Sum (a, b) over the CTA; every thread gets the result.  Fixed order; double-buffered: one barrier per call.
@@ -57,22 +108,25 @@ __device__ __forceinline__ void cta_sum2(double& a, double& b, double* red, int 
     }
 }
 
-__host__ __device__ inline size_t panel_smem_doubles(int n, int warps) {
+__host__ __device__ inline size_t panel_smem_doubles(int n, int warps, int maxc) {
     const int slots = warps / 4;
-    return (size_t)4 * NB * n + (size_t)2 * n * (3 + slots) + 2 * (size_t)n + 4 * NB + 4 * warps + 4;
+    const int nsw = 1;
+    (void)maxc;
+    return (size_t)4 * NB * n + (size_t)2 * n * (2 + nsw + slots) + 2 * (size_t)n + 4 * NB + 4 * warps + 4;
 }
 
-template <int THREADS, int MAXC>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 1 : 2))
+template <int THREADS, int MAXC, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
     constexpr int WARPS = THREADS / 32;
     constexpr int SLOTS = WARPS / 4;
+    constexpr int NSW = 1;  // (row-part planes)
     extern __shared__ __align__(16) double smp[];
     double* X = smp;                                              // [NB][N][4] = (vr, vi, wr, wi) of panel column p, row r
     double2* V = reinterpret_cast<double2*>(X + (size_t)4 * NB * N);  // [N] current reflector, index i = row - r0
     double2* P = V + N;                                           // [N] tau * p
-    double2* S = P + N;                                           // [N] row-part sums
-    double2* QW = S + N;                                          // [SLOTS][N] column-part partial sums
+    double2* S = P + N;                                           // [NSW][N] row-part sums, one plane per column sweep
+    double2* QW = S + (size_t)NSW * N;                            // [SLOTS][N] column-part partial sums
     double* ds = reinterpret_cast<double*>(QW + (size_t)SLOTS * N);
     double* es = ds + N;
     double2* Y = reinterpret_cast<double2*>(es + N);              // [2 NB]: Y[2p] = W_p^H v, Y[2p+1] = V_p^H v
@@ -157,32 +211,36 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 }
                 if (lane == 0) Y[q] = make_double2(yr, yi);
             }
-            // --- (3) Hermitian product with the stored trailing block: row sweeps over the lower triangle ---
+            // --- (3) Hermitian product with the stored trailing block: row sweeps over the lower triangle.
+            //     A warp owns rows a = w, w + WARPS, ...; lane l owns columns l, l + 32, ... (one register accumulator
+            //     per 32-column chunk for the column part).  Rows two trips ahead are pulled into L2 by a bulk
+            //     prefetch, so the loads below see L2 latency even while the matrix streams from HBM. ---
             double2 qacc[MAXC];
 #pragma unroll
             for (int cc = 0; cc < MAXC; ++cc) qacc[cc] = make_double2(0.0, 0.0);
+            if (lane < 2) {
+                const int a1 = w + lane * WARPS;
+                if (a1 < m) prefetch_row(Ar, Ai, r0 + a1, r0, a1);
+            }
+            const double2* pv = V + lane;
             for (int a = w; a < m; a += WARPS) {
-                const long I = r0 + a;
-                const double* rre = Ar + tri(I) + r0;
-                const double* rim = Ai + trs(I) + r0;
+                const int I = r0 + a;
+                if (lane == 0 && a + 2 * WARPS < m) prefetch_row(Ar, Ai, I + 2 * WARPS, r0, a + 2 * WARPS);
+                const unsigned long long pr = (unsigned long long)__cvta_generic_to_global(Ar + (itri(I) + r0 + lane));
+                const unsigned long long pi = (unsigned long long)__cvta_generic_to_global(Ai + (itrs(I) + r0 + lane));
+                const int rem = a - lane;               // column b = 32 q + lane lies inside the row  <=>  32 q < rem
                 const double2 va = V[a];
+                const double dg = Ar[itri(I) + I];      // real diagonal (same address in every lane)
                 double sumr = 0.0, sumi = 0.0;
 #pragma unroll
                 for (int c0 = 0; c0 < MAXC; c0 += 4) {
                     if (c0 * 32 < a) {  // warp-uniform; four 32-column chunks per batch: 8 loads in flight per lane
                         double zr[4], zi[4];
+                        load4<0>(pr + c0 * 256, pi + c0 * 256, rem - c0 * 32, zr, zi);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int b = (c0 + q) * 32 + lane;
-                            const bool ok = b < a;
-                            zr[q] = ok ? rre[b] : 0.0;
-                            zi[q] = ok ? rim[b] : 0.0;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int b = (c0 + q) * 32 + lane;
-                            if (b < a) {
-                                const double2 vb = V[b];
+                            if ((c0 + q) * 32 < rem) {
+                                const double2 vb = pv[(c0 + q) * 32];
                                 sumr = fma(zr[q], vb.x, fma(-zi[q], vb.y, sumr));
                                 sumi = fma(zr[q], vb.y, fma(zi[q], vb.x, sumi));
                                 qacc[c0 + q].x = fma(zr[q], va.x, fma(zi[q], va.y, qacc[c0 + q].x));  // conj(z) v_a
@@ -196,27 +254,23 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                     sumr += __shfl_xor_sync(0xffffffffu, sumr, o);
                     sumi += __shfl_xor_sync(0xffffffffu, sumi, o);
                 }
-                if (lane == 0) {
-                    const double dg = rre[a];  // real diagonal
-                    S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
-                }
+                if (lane == 0) S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
             }
             // column parts: four rounds, warp w adds into slot w / 4 in round w % 4 (fixed order)
 #pragma unroll
             for (int round = 0; round < 4; ++round) {
                 if ((w & 3) == round) {
-                    double2* slot = QW + (size_t)(w >> 2) * N;
+                    double2* slot = QW + (size_t)(w >> 2) * N + lane;
 #pragma unroll
                     for (int cc = 0; cc < MAXC; ++cc) {
-                        const int b = cc * 32 + lane;
-                        if (b < m) {
+                        if (cc * 32 + lane < m) {
                             if (round == 0) {
-                                slot[b] = qacc[cc];
+                                slot[cc * 32] = qacc[cc];
                             } else {
-                                double2 t2 = slot[b];
+                                double2 t2 = slot[cc * 32];
                                 t2.x += qacc[cc].x;
                                 t2.y += qacc[cc].y;
-                                slot[b] = t2;
+                                slot[cc * 32] = t2;
                             }
                         }
                     }
@@ -277,12 +331,6 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 const int row = 8 * I + g;
                 const bool row_ok = row < N;
                 const int rowc = row_ok ? row : N - 1;
-                double xr[NB], xi[NB];
-#pragma unroll
-                for (int p = 0; p < NB; ++p) {
-                    xr[p] = -X[((size_t)p * N + rowc) * 4 + tq];             // -(vr, vi, wr, wi)[tq]
-                    xi[p] = sgn * X[((size_t)p * N + rowc) * 4 + (tq ^ 1)];  // (-vi, vr, -wi, wr)[tq]
-                }
                 double* pre = Ar + tri((long)rowc);
                 double* pim = Ai + trs((long)rowc);
                 const int J0 = I0 + 4 * s;
@@ -296,16 +344,23 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                         cim[jb][h] = (row_ok && col + h < row) ? pim[col + h] : 0.0;
                     }
                 }
+                int colg[4];
 #pragma unroll
                 for (int jb = 0; jb < 4; ++jb) {
-                    if (J0 + jb <= I) {  // warp-uniform
-                        int colg = 8 * (J0 + jb) + g;
-                        if (colg >= N) colg = N - 1;
+                    colg[jb] = 8 * (J0 + jb) + g;
+                    if (colg[jb] >= N) colg[jb] = N - 1;  // (blocks right of the diagonal block are never stored)
+                }
 #pragma unroll
-                        for (int p = 0; p < NB; ++p) {
-                            const double y = X[((size_t)p * N + colg) * 4 + (tq ^ 2)];  // (wr, wi, vr, vi)[tq]
-                            dmma884(cre[jb][0], cre[jb][1], xr[p], y);
-                            dmma884(cim[jb][0], cim[jb][1], xi[p], y);
+                for (int p = 0; p < NB; ++p) {
+                    const double* Xp = X + (size_t)p * N * 4;
+                    const double xr = -Xp[rowc * 4 + tq];             // -(vr, vi, wr, wi)[tq]
+                    const double xi = sgn * Xp[rowc * 4 + (tq ^ 1)];  // (-vi, vr, -wi, wr)[tq]
+#pragma unroll
+                    for (int jb = 0; jb < 4; ++jb) {
+                        if (J0 + jb <= I) {  // warp-uniform
+                            const double y = Xp[colg[jb] * 4 + (tq ^ 2)];  // (wr, wi, vr, vi)[tq]
+                            dmma884(cre[jb][0], cre[jb][1], xr, y);
+                            dmma884(cim[jb][0], cim[jb][1], xi, y);
                         }
                     }
                 }
@@ -330,28 +385,39 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
     }
 }
 
-template <int THREADS, int MAXC>
+template <int THREADS, int MAXC, int MINB>
 cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    const size_t smem = panel_smem_doubles(n, THREADS / 32) * 8;
+    const size_t smem = panel_smem_doubles(n, THREADS / 32, MAXC) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC>,
+    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_panel_kernel<THREADS, MAXC><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E);
+    tridiag_panel_kernel<THREADS, MAXC, MINB><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-bool tridiag_panel_fits(int n) { return n >= 2 && n <= 640 && panel_smem_doubles(n, 16) * 8 <= 227 * 1024; }
+bool tridiag_panel_fits(int n) {
+    return n >= 2 && n <= 640 && panel_smem_doubles(n, 16, n <= 512 ? 16 : 20) * 8 <= 227 * 1024;
+}
 
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    if (n <= 128) return launch_panel_t<256, 4>(n, Hp, nk, D, E, st);
-    if (n <= 256) return launch_panel_t<256, 8>(n, Hp, nk, D, E, st);
-    if (n <= 512) return launch_panel_t<512, 16>(n, Hp, nk, D, E, st);
-    return launch_panel_t<512, 20>(n, Hp, nk, D, E, st);
+    int t = 0;
+    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);  // tuning hook: threads per matrix for n <= 128
+    if (n <= 128) {
+        if (t == 128) return launch_panel_t<128, 4, 8>(n, Hp, nk, D, E, st);
+        if (t == 512) return launch_panel_t<512, 4, 2>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 4, 4>(n, Hp, nk, D, E, st);
+    }
+    if (n <= 256) {
+        if (t == 512) return launch_panel_t<512, 8, 1>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 8, 2>(n, Hp, nk, D, E, st);
+    }
+    if (n <= 512) return launch_panel_t<512, 16, 1>(n, Hp, nk, D, E, st);
+    return launch_panel_t<512, 20, 1>(n, Hp, nk, D, E, st);
 }
 
 }  // namespace tbk
