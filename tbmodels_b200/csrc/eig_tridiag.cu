@@ -901,6 +901,10 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     }
     // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
     //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
+    // blocked kernel (eig_tridiag_panel.cu) from N = 120 on: measured on B200, ms per 1000 matrices smem / blocked:
+    // N = 100: 1.47 / 1.95, 128: 3.65 / 3.31, 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125
+    if (g == 0 && n >= 120 && !getenv("TBK_TRIDIAG_NOPANEL") && tridiag_panel_fits(n))
+        return launch_tridiag_panel(n, Hp, nk, D, E, st);
     if (g == 0) {  // defaults, from N only (never from the batch: results must not depend on the batch size)
         if (n <= 10) g = 8;
         else if (n <= 20) g = 16;

@@ -369,16 +369,43 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
         _check(tbk, p, d[f"{tag}_k"], None, None, d[f"{tag}_eig"], f"{tag} G={g}")
 
 
-@pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 48, 49, 64, 65, 96, 97, 128, 129, 164, 165, 200, 300])
+@pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 48, 49, 64, 65, 96, 97, 119, 120, 121, 128, 129, 164, 165, 200, 257, 300, 513, 600, 601])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
     """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection)."""
     from tbmodels_b200 import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(n_orb, 4, seed=n_orb)
-    nk = 37 if n_orb <= 128 else 5
+    nk = 37 if n_orb <= 128 else (5 if n_orb <= 300 else 2)
     k = np.random.default_rng(n_orb).uniform(-1, 1, size=(nk, 3))
     _check(tbk, p, k, None, orc.hamilton(p.R, p.hop, p.pos, k[:3], 2), orc.eigenval_array(p.R, p.hop, p.pos, k), f"N={n_orb}")
+
+
+@pytest.mark.parametrize("threads", ["128", "256", "512"])
+def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads):
+    """The blocked (panel + tensor-core her2k) reduction forced onto small and ragged sizes: partial last panels,
+    sizes that are not multiples of the 8 x 8 blocks, every thread-count instantiation."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_PANEL_MIN", "2")
+    monkeypatch.setenv("TBK_PANEL_T", threads)
+    for n_orb in (9, 15, 16, 17, 24, 31, 33, 40, 63, 65, 100, 129, 200, 255, 256):
+        p = wl.synthetic(n_orb, 3, seed=1000 + n_orb)
+        k = np.random.default_rng(n_orb).uniform(-1, 1, size=(7 if n_orb <= 129 else 3, 3))
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads}")
+
+
+@pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
+def test_unblocked_large_kernels_still_agree(tbk, monkeypatch, n_orb):
+    """The shared-memory / row-sweep kernels the blocked one replaced stay reachable (sizes 601..640, tuning hook)."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_NOPANEL", "1")
+    p = wl.synthetic(n_orb, 3, seed=n_orb)
+    k = np.random.default_rng(n_orb).uniform(-1, 1, size=(3, 3))
+    _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"unblocked N={n_orb}")
 
 
 @pytest.mark.parametrize("tag", ["toy", "si0", "si1", "si2", "si3"])
