@@ -191,6 +191,203 @@ hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Trigonometric-product form for nearest-cell models with N <= 2 (C2: the 2-band Haldane model).
+// With every |R_d| <= 1,  e^{2 pi i k.R} = prod_d (c_d + i R_d s_d),  c_d = cos 2 pi k_d, s_d = sin 2 pi k_d, so
+//   H(k) = sum_b phi_b(k) B_b ,   phi_b = prod_d {1, c_d, s_d}[t_d] ,   b = sum_d t_d 3^d   (3^D real functions),
+// with the packed Hermitian coefficient matrices B_b accumulated once on the host (tbk_api.cu, tbk_model_create).
+// Per k-point: D sincospi, 3^D - 2 D - 1 products, (3^D - 1) N^2 FMAs whose second operand is a uniform-register /
+// constant-bank operand (the table is a kernel parameter): no shared memory, no loop over R, no selects.
+// Same sum as the reference's Fourier loop (src/tbmodels/_tb_model.py:1111-1123), reassociated.
+// KP k-points per thread and trip share the 64-bit immediates of the sincospi polynomials (two UMOVs each).
+// ---------------------------------------------------------------------------------------------------------
+template <int D>
+struct Pow3 {
+    static constexpr int value = 3 * Pow3<D - 1>::value;
+};
+template <>
+struct Pow3<0> {
+    static constexpr int value = 1;
+};
+
+template <int N, int D>
+struct BasisTable {
+    double w[Pow3<D>::value * N * N];
+};
+
+// sincospi_lean (tbk_math.cuh: same reduction, same polynomials) with a cheaper quadrant fix-up: one select per
+// output and the signs applied as integer XORs on the high words.
+__device__ __forceinline__ void sincospi_x(double t, double& s, double& c) {
+    const double n = rint(t + t);
+    const double r = fma(n, -0.5, t);
+    const unsigned q = (unsigned)(long long)n;  // low bits of the (exact) integer n
+    const double r2 = r * r;
+    double ps = 7.952054001475508e-07;
+    ps = fma(ps, r2, -2.1915353447830204e-05);
+    ps = fma(ps, r2, 0.00046630280576761234);
+    ps = fma(ps, r2, -0.007370430945714348);
+    ps = fma(ps, r2, 0.08214588661112819);
+    ps = fma(ps, r2, -0.5992645293207919);
+    ps = fma(ps, r2, 2.550164039877345);
+    ps = fma(ps, r2, -5.167712780049969);
+    double sv = fma(r * r2, ps, r * 1.2246467991473532e-16);  // pi = 3.141592653589793 + 1.2246467991473532e-16
+    sv = fma(r, 3.141592653589793, sv);
+    double pc = -1.387895246221376e-07;
+    pc = fma(pc, r2, 4.303069587032944e-06);
+    pc = fma(pc, r2, -0.00010463810492484565);
+    pc = fma(pc, r2, 0.001929574309403922);
+    pc = fma(pc, r2, -0.02580689139001405);
+    pc = fma(pc, r2, 0.23533063035889312);
+    pc = fma(pc, r2, -1.3352627688545893);
+    pc = fma(pc, r2, 4.058712126416768);
+    pc = fma(pc, r2, -4.934802200544679);
+    const double cv = fma(pc, r2, 1.0);
+    // q mod 4:  0 -> (s, c),  1 -> (c, -s),  2 -> (-s, -c),  3 -> (-c, s)
+    const bool odd = q & 1u;
+    const double a = odd ? cv : sv, b = odd ? sv : cv;
+    const unsigned qs = q << 30;  // bit 31 = bit 1 of q
+    s = __hiloint2double(__double2hiint(a) ^ (int)(qs & 0x80000000u), __double2loint(a));
+    c = __hiloint2double(__double2hiint(b) ^ (int)((qs + 0x40000000u) & 0x80000000u), __double2loint(b));
+}
+
+// sqrt(x) for finite x >= 0: hardware reciprocal-square-root seed, two coupled Newton steps and a final residual
+// correction (<= 1 ulp for normal x); x below 1e-290 (exact band degeneracy) returns 0.
+__device__ __forceinline__ double sqrt_nonneg(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    g = fma(d, h, g);
+    return (x > 1e-290) ? g : 0.0;
+}
+
+template <int N, int D, int KP>
+__device__ __forceinline__ void basis_kpoints(const double (&kv)[KP][D], const double* __restrict__ w,
+                                              double (&acc)[KP][N * N]) {
+    constexpr int NN = N * N;
+    constexpr int NB3 = Pow3<D>::value;
+    double phi[KP][NB3];
+    int n = 1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int p = 0; p < KP; ++p) {
+            double sd, cd;
+            sincospi_x(2.0 * kv[p][d], sd, cd);
+            phi[p][0] = 1.0;
+            phi[p][n] = cd;
+            phi[p][2 * n] = sd;
+#pragma unroll
+            for (int b = 1; b < n; ++b) {
+                phi[p][b + n] = phi[p][b] * cd;
+                phi[p][b + 2 * n] = phi[p][b] * sd;
+            }
+        }
+        n *= 3;
+    }
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+#pragma unroll
+        for (int e = 0; e < NN; ++e) acc[p][e] = w[e];
+#pragma unroll
+        for (int b = 1; b < NB3; ++b)
+#pragma unroll
+            for (int e = 0; e < NN; ++e) acc[p][e] = fma(phi[p][b], w[b * NN + e], acc[p][e]);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void basis_store(const double (&acc)[N * N], long idx, double* __restrict__ Hp,
+                                            double* __restrict__ eig) {
+    constexpr int NN = N * N;
+    if (Hp != nullptr) {
+#pragma unroll
+        for (int e = 0; e < NN; ++e) Hp[idx * NN + e] = acc[e];
+    }
+    if (eig != nullptr) {
+        if (N == 1) {
+            eig[idx] = acc[0];
+        } else {  // closed form (tbk_math.cuh eig2_closed) with the lean square root
+            const double mean = 0.5 * (acc[0] + acc[2 % NN]);
+            const double delta = 0.5 * (acc[0] - acc[2 % NN]);
+            const double rad = sqrt_nonneg(fma(delta, delta, fma(acc[1 % NN], acc[1 % NN], acc[3 % NN] * acc[3 % NN])));
+            *reinterpret_cast<double2*>(eig + idx * 2) = make_double2(mean - rad, mean + rad);
+        }
+    }
+}
+
+// A CTA trip covers KP * TPB consecutive k-points; thread t owns t, t + TPB, ... (immediate offsets from one pointer).
+template <int N, int D, int KP>
+__global__ void __launch_bounds__(TPB)
+hk_basis_kernel(const double* __restrict__ kpts, long nk, const __grid_constant__ BasisTable<N, D> T,
+                double* __restrict__ Hp, double* __restrict__ eig) {
+    constexpr int NN = N * N;
+    constexpr long TRIP = (long)KP * TPB;
+    const long step = (long)gridDim.x * TRIP;
+    long base = (long)blockIdx.x * TRIP;
+    for (; base + TRIP <= nk; base += step) {  // full trips: no bounds checks
+        const double* kp = kpts + (base + threadIdx.x) * D;
+        double kv[KP][D];
+#pragma unroll
+        for (int p = 0; p < KP; ++p) {
+            if (D == 2) {
+                const double2 v = *reinterpret_cast<const double2*>(kp + (long)p * TPB * D);
+                kv[p][0] = v.x;
+                kv[p][D - 1] = v.y;
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) kv[p][d] = kp[(long)p * TPB * D + d];
+            }
+        }
+        double acc[KP][NN];
+        basis_kpoints<N, D, KP>(kv, T.w, acc);
+#pragma unroll
+        for (int p = 0; p < KP; ++p) basis_store<N>(acc[p], base + threadIdx.x + (long)p * TPB, Hp, eig);
+    }
+    if (base < nk) {  // ragged last trip (at most one CTA gets here with work)
+        for (long idx = base + threadIdx.x; idx < nk; idx += TPB) {
+            double kv[1][D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) kv[0][d] = kpts[idx * D + d];
+            double acc[1][NN];
+            basis_kpoints<N, D, 1>(kv, T.w, acc);
+            basis_store<N>(acc[0], idx, Hp, eig);
+        }
+    }
+}
+
+template <int N, int D>
+cudaError_t launch_basis_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    constexpr int KP = (D <= 2) ? 4 : 2;
+    BasisTable<N, D> T;
+    for (int i = 0; i < Pow3<D>::value * N * N; ++i) T.w[i] = md.basis[i];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long blocks = (nk + KP * TPB - 1) / (KP * TPB);
+    const long cap = (long)sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks <= 0) return cudaSuccess;
+    hk_basis_kernel<N, D, KP><<<(unsigned)blocks, TPB, 0, st>>>(k, nk, T, Hp, eig);
+    return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_basis_n(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    switch (md.dim) {
+        case 1: return launch_basis_nd<N, 1>(md, k, nk, Hp, eig, st);
+        case 2: return launch_basis_nd<N, 2>(md, k, nk, Hp, eig, st);
+        case 3: return launch_basis_nd<N, 3>(md, k, nk, Hp, eig, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int N, int D>
 cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
     const size_t smem = hk_small_smem_bytes(N, md.dim, md.nR, TPB);
@@ -232,6 +429,10 @@ size_t hk_small_smem_bytes(int n, int dim, int nR, int threads) {
 }
 
 cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    if (md.basis_ok) {
+        if (md.n == 1) return launch_basis_n<1>(md, k, nk, Hp, eig, st);
+        if (md.n == 2) return launch_basis_n<2>(md, k, nk, Hp, eig, st);
+    }
     switch (md.n) {
         case 1: return launch_n<1>(md, k, nk, Hp, eig, st);
         case 2: return launch_n<2>(md, k, nk, Hp, eig, st);

@@ -431,6 +431,40 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
             Ri[r] = unit ? 1 : 0;
             if (unit) md.use_z = 1;
         }
+        // trigonometric-product table (hk_small.cu, hk_basis_kernel): N <= 2, dim <= 3, every R in {-1, 0, 1}^dim
+        bool all_unit = true;
+        for (int r = 0; r < n_R; ++r) all_unit = all_unit && Ri[r] == 1;
+        if (n_orb <= 2 && dim <= 3 && all_unit && !getenv("TBK_NO_BASIS")) {
+            int nb3 = 1;
+            for (int d = 0; d < dim; ++d) nb3 *= 3;
+            std::vector<double> cre((size_t)nb3), cim((size_t)nb3), tre((size_t)nb3), tim((size_t)nb3);
+            for (int r = 0; r < n_R; ++r) {
+                // expand prod_d (c_d + i R_d s_d) into the 3^dim products: complex coefficient per basis function
+                std::fill(cre.begin(), cre.end(), 0.0);
+                std::fill(cim.begin(), cim.end(), 0.0);
+                cre[0] = 1.0;
+                int stride3 = 1;
+                for (int d = 0; d < dim; ++d, stride3 *= 3) {
+                    const int v = R[(size_t)r * dim + d];
+                    if (v == 0) continue;
+                    std::fill(tre.begin(), tre.end(), 0.0);
+                    std::fill(tim.begin(), tim.end(), 0.0);
+                    for (int b = 0; b < stride3; ++b) {  // only dimensions < d have been expanded so far
+                        tre[b + stride3] += cre[b];            // * c_d
+                        tim[b + stride3] += cim[b];
+                        tre[b + 2 * stride3] += -v * cim[b];   // * i v s_d
+                        tim[b + 2 * stride3] += v * cre[b];
+                    }
+                    cre.swap(tre);
+                    cim.swap(tim);
+                }
+                for (int b = 0; b < nb3; ++b)
+                    for (long e = 0; e < NN; ++e)
+                        md.basis[(size_t)b * NN + e] +=
+                            cre[b] * W[(size_t)(2 * r) * NN + e] + cim[b] * W[(size_t)(2 * r + 1) * NN + e];
+            }
+            md.basis_ok = 1;
+        }
         CUB(cudaMalloc(&m->dRi, Ri.size() * sizeof(int)));
         CUB(cudaMemcpy(m->dRi, Ri.data(), Ri.size() * sizeof(int), cudaMemcpyHostToDevice));
         md.Ri = m->dRi;

@@ -27,6 +27,10 @@ struct ModelDev {
     int n_tiles = 0;   // GEMM: column tiles
     int kchunks = 0;   // GEMM: nRpad / 8
     int small_ok = 0;  // fused thread-per-k kernel usable
+    // N <= 2, dim <= 3, all |R_d| <= 1: H(k) as a linear combination of the 3^dim products of {1, cos 2 pi k_d,
+    // sin 2 pi k_d} (hk_small.cu, hk_basis_kernel); basis[b * n * n + e], b = sum_d t_d 3^d, t_d in {0: 1, 1: cos, 2: sin}
+    int basis_ok = 0;
+    double basis[27 * 4] = {0};
     // k.p models (reference src/tbmodels/kdotp.py:51-82): kind = 1, the GEMM coefficients are the monomials
     // prod_d k_d^{p_d} instead of [cos | sin] phases; Pw holds the integer powers [kchunks * 16][dim]
     int kind = 0;
