@@ -11,6 +11,8 @@
 //   N = 1, 2 : closed-form eigenvalues.
 //   N = 3..8 : per-thread Householder tridiagonalisation + implicit QL on a thread-strided shared-memory
 //              scratch (tbk_math.cuh), i.e. every lane works on its own matrix -- no idle lanes, no shuffles.
+#include <cstdlib>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -322,6 +324,21 @@ __device__ __forceinline__ void basis_store(const double (&acc)[N * N], long idx
     }
 }
 
+template <int D, int KP>
+__device__ __forceinline__ void load_trip(double (&k)[KP][D], const double* __restrict__ kp) {
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+        if (D == 2) {
+            const double2 v = *reinterpret_cast<const double2*>(kp + (long)p * TPB * D);
+            k[p][0] = v.x;
+            k[p][D - 1] = v.y;
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) k[p][d] = kp[(long)p * TPB * D + d];
+        }
+    }
+}
+
 // A CTA trip covers KP * TPB consecutive k-points; thread t owns t, t + TPB, ... (immediate offsets from one pointer).
 template <int N, int D, int KP>
 __global__ void __launch_bounds__(TPB)
@@ -331,20 +348,15 @@ hk_basis_kernel(const double* __restrict__ kpts, long nk, const __grid_constant_
     constexpr long TRIP = (long)KP * TPB;
     const long step = (long)gridDim.x * TRIP;
     long base = (long)blockIdx.x * TRIP;
+    double kn[KP][D];  // k-points of the next full trip (prefetched one trip ahead)
+    if (base + TRIP <= nk) load_trip<D, KP>(kn, kpts + (base + threadIdx.x) * D);
     for (; base + TRIP <= nk; base += step) {  // full trips: no bounds checks
-        const double* kp = kpts + (base + threadIdx.x) * D;
         double kv[KP][D];
 #pragma unroll
-        for (int p = 0; p < KP; ++p) {
-            if (D == 2) {
-                const double2 v = *reinterpret_cast<const double2*>(kp + (long)p * TPB * D);
-                kv[p][0] = v.x;
-                kv[p][D - 1] = v.y;
-            } else {
+        for (int p = 0; p < KP; ++p)
 #pragma unroll
-                for (int d = 0; d < D; ++d) kv[p][d] = kp[(long)p * TPB * D + d];
-            }
-        }
+            for (int d = 0; d < D; ++d) kv[p][d] = kn[p][d];
+        if (base + step + TRIP <= nk) load_trip<D, KP>(kn, kpts + (base + step + threadIdx.x) * D);
         double acc[KP][NN];
         basis_kpoints<N, D, KP>(kv, T.w, acc);
 #pragma unroll
@@ -362,9 +374,8 @@ hk_basis_kernel(const double* __restrict__ kpts, long nk, const __grid_constant_
     }
 }
 
-template <int N, int D>
-cudaError_t launch_basis_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
-    constexpr int KP = (D <= 2) ? 4 : 2;
+template <int N, int D, int KP>
+cudaError_t launch_basis_ndk(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
     BasisTable<N, D> T;
     for (int i = 0; i < Pow3<D>::value * N * N; ++i) T.w[i] = md.basis[i];
     int dev = 0, sms = 148;
@@ -376,6 +387,16 @@ cudaError_t launch_basis_nd(const ModelDev& md, const double* k, long nk, double
     if (blocks <= 0) return cudaSuccess;
     hk_basis_kernel<N, D, KP><<<(unsigned)blocks, TPB, 0, st>>>(k, nk, T, Hp, eig);
     return cudaGetLastError();
+}
+
+template <int N, int D>
+cudaError_t launch_basis_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+    if (D <= 2) {
+        if (const char* e = getenv("TBK_BASIS_KP"))  // tuning hook: k-points per thread and trip
+            if (atoi(e) == 2) return launch_basis_ndk<N, D, 2>(md, k, nk, Hp, eig, st);
+        return launch_basis_ndk<N, D, 4>(md, k, nk, Hp, eig, st);
+    }
+    return launch_basis_ndk<N, D, 2>(md, k, nk, Hp, eig, st);
 }
 
 template <int N>
