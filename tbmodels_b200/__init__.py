@@ -13,7 +13,10 @@ Public surface
     install / uninstall                      switch ``tbmodels.Model`` itself over to the GPU path
     sharded                                  one-process-per-GPU k-point sharding (torch.distributed)
     workloads                                the benchmark / parity model generators of BASELINE.json
+    io                                       HDF5 model / k-point / eigenvalue files of the `tbmodels eigenvals` CLI
+                                             (no h5py needed); `python -m tbmodels_b200 eigenvals` is that command
 """
+from . import io  # noqa: F401
 from ._capi import TbkError  # noqa: F401
 from ._evaluator import Evaluator, fp64_peaks, pinned_empty  # noqa: F401
 from ._kdotp import KdotpModel, pack_kdotp  # noqa: F401

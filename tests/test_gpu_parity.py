@@ -463,3 +463,25 @@ def test_oversize_matrix_fallback(tbk):
     k = np.array([[0.11, 0.52, -0.3], [0.0, 0.0, 0.0]])
     got = tbk.Evaluator(p).eigenval_array(k)
     assert_eig_close(got, orc.eigenval_array(p.R, p.hop, p.pos, k), "N=650")
+
+
+@pytest.mark.parametrize("verbosity", [[], ["-v"]])
+@pytest.mark.parametrize("kpoints_file_name", ["kpoints.hdf5", "silicon_eigenvals.hdf5"])
+def test_cli_eigenvals(tbk, tmp_path, capsys, kpoints_file_name, verbosity):
+    """The reference's tests/test_cli_eigenvals.py, same fixtures and the same 1e-10 bound, through
+    `python -m tbmodels_b200 eigenvals` (HDF5 in, GPU eigenvalues, HDF5 out)."""
+    from conftest import GOLDEN
+    from tbmodels_b200 import io
+    from tbmodels_b200.__main__ import main
+
+    samples_dir = os.path.join(GOLDEN, "cli_eigenvals")
+    out = str(tmp_path / "eigenvals.hdf5")
+    rc = main(["eigenvals", "-o", out, "-k", os.path.join(samples_dir, kpoints_file_name),
+               "-i", os.path.join(samples_dir, "silicon_model.hdf5")] + verbosity)
+    assert rc == 0
+    printed = capsys.readouterr().out
+    assert ("Calculating energy eigenvalues ..." in printed) == bool(verbosity)
+    k, e = io.load_eigenvals(out)
+    k_ref, e_ref = io.load_eigenvals(os.path.join(samples_dir, "silicon_eigenvals.hdf5"))
+    assert np.array_equal(k, k_ref)
+    np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-10)
