@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *ARCH, *FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *FLAGS, *os.environ.get("TBK_BUILD_DEFINES", "").split(), "-c", s, "-o", o]  # debug -D flags
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)

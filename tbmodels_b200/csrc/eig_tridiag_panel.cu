@@ -18,6 +18,7 @@
 // organised as coalesced row sweeps over the lower triangle exactly like tridiag_big_kernel (row part reduced per row,
 // column part scattered into per-lane register accumulators and combined across warps in a fixed order: no atomics,
 // bits do not depend on the batch).
+#include <cstdio>
 #include <cstdlib>
 
 #include "tbk_kernels.h"
@@ -115,9 +116,10 @@ __host__ __device__ inline size_t panel_smem_doubles(int n, int warps, int maxc)
     return (size_t)4 * NB * n + (size_t)2 * n * (2 + nsw + slots) + 2 * (size_t)n + 4 * NB + 4 * warps + 4;
 }
 
-template <int THREADS, int MAXC, int MINB>
+template <int THREADS, int MAXC, int MINB, int RPI>
 __global__ void __launch_bounds__(THREADS, MINB)
-tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E,
+                     int pfd /* L2 prefetch distance of the Hermitian product, in warp trips; 0 = off */) {
     constexpr int WARPS = THREADS / 32;
     constexpr int SLOTS = WARPS / 4;
     constexpr int NSW = 1;  // (row-part planes)
@@ -139,6 +141,26 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
     double* Ar = Hp + kk * (long)N * N;
     double* Ai = Ar + tri(N);
     int parity = 0;
+#ifdef TBK_PANEL_TIMING  // debug build: cycles per phase of CTA 0 (thread 0; phase 2 additionally as the max over warps)
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64(), twarp = 0;
+#define TICK(i)                                  \
+    do {                                         \
+        const long long now_ = clock64();        \
+        tacc[i] += now_ - tlast;                 \
+        tlast = now_;                            \
+    } while (0)
+#define TICKW(i)                                 \
+    do {                                         \
+        const long long now_ = clock64();        \
+        twarp += now_ - tlast;                   \
+        tacc[i] += now_ - tlast;                 \
+        tlast = now_;                            \
+    } while (0)
+#else
+#define TICK(i)
+#define TICKW(i)
+#endif
 
     for (int k0 = 0; k0 < N; k0 += NB) {
         const int nb = (N - k0 < NB) ? (N - k0) : NB;
@@ -179,6 +201,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 continue;
             }
             cta_sum2<WARPS>(xn, dummy, red, tid, parity);
+            TICK(0);  // column gather / update + norm reduction
             double beta, tr, ti, sr, si;
             householder_gen(misc[0], misc[1], xn, beta, tr, ti, sr, si);
             // --- (2) v = [1; scale * x]; kept in V (this step) and in X[j] (panel) ---
@@ -193,6 +216,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
             }
             if (tid == 0) es[c] = beta;
             __syncthreads();
+            TICK(1);  // reflector, v
             // --- (2b) y1[p] = W_p^H v, y2[p] = V_p^H v for the previous panel columns: one warp per dot product ---
             for (int q = w; q < 2 * j; q += WARPS) {
                 const int p = q >> 1;
@@ -218,44 +242,70 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
             double2 qacc[MAXC];
 #pragma unroll
             for (int cc = 0; cc < MAXC; ++cc) qacc[cc] = make_double2(0.0, 0.0);
-            if (lane < 2) {
+            if (lane < pfd * RPI) {
                 const int a1 = w + lane * WARPS;
                 if (a1 < m) prefetch_row(Ar, Ai, r0 + a1, r0, a1);
             }
             const double2* pv = V + lane;
-            for (int a = w; a < m; a += WARPS) {
-                const int I = r0 + a;
-                if (lane == 0 && a + 2 * WARPS < m) prefetch_row(Ar, Ai, I + 2 * WARPS, r0, a + 2 * WARPS);
-                const unsigned long long pr = (unsigned long long)__cvta_generic_to_global(Ar + (itri(I) + r0 + lane));
-                const unsigned long long pi = (unsigned long long)__cvta_generic_to_global(Ai + (itrs(I) + r0 + lane));
-                const int rem = a - lane;               // column b = 32 q + lane lies inside the row  <=>  32 q < rem
-                const double2 va = V[a];
-                const double dg = Ar[itri(I) + I];      // real diagonal (same address in every lane)
-                double sumr = 0.0, sumi = 0.0;
+            for (int a = w; a < m; a += RPI * WARPS) {  // RPI rows per trip: 8 RPI loads in flight per lane
+                if (lane < RPI && pfd > 0) {
+                    const int a2 = a + (pfd * RPI + lane) * WARPS;
+                    if (a2 < m) prefetch_row(Ar, Ai, r0 + a2, r0, a2);
+                }
+                unsigned long long pr[RPI], pi[RPI];
+                int rem[RPI];
+                double2 va[RPI];
+                double dg[RPI], sumr[RPI], sumi[RPI];
+                int alast = a;  // longest active row of the trip
+#pragma unroll
+                for (int r = 0; r < RPI; ++r) {
+                    const int ar = a + r * WARPS;
+                    const bool on = ar < m;
+                    const int ac = on ? ar : a;  // inactive rows shadow row a with every column masked off
+                    const int I = r0 + ac;
+                    if (on) alast = ar;
+                    pr[r] = (unsigned long long)__cvta_generic_to_global(Ar + (itri(I) + r0 + lane));
+                    pi[r] = (unsigned long long)__cvta_generic_to_global(Ai + (itrs(I) + r0 + lane));
+                    rem[r] = on ? ar - lane : 0;  // column b = 32 q + lane lies inside the row  <=>  32 q < rem
+                    va[r] = V[ac];
+                    dg[r] = Ar[itri(I) + I];      // real diagonal (same address in every lane)
+                    sumr[r] = 0.0;
+                    sumi[r] = 0.0;
+                }
 #pragma unroll
                 for (int c0 = 0; c0 < MAXC; c0 += 4) {
-                    if (c0 * 32 < a) {  // warp-uniform; four 32-column chunks per batch: 8 loads in flight per lane
-                        double zr[4], zi[4];
-                        load4<0>(pr + c0 * 256, pi + c0 * 256, rem - c0 * 32, zr, zi);
+                    if (c0 * 32 < alast) {  // warp-uniform; four 32-column chunks per row and batch
+                        double zr[RPI][4], zi[RPI][4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if ((c0 + q) * 32 < rem) {
-                                const double2 vb = pv[(c0 + q) * 32];
-                                sumr = fma(zr[q], vb.x, fma(-zi[q], vb.y, sumr));
-                                sumi = fma(zr[q], vb.y, fma(zi[q], vb.x, sumi));
-                                qacc[c0 + q].x = fma(zr[q], va.x, fma(zi[q], va.y, qacc[c0 + q].x));  // conj(z) v_a
-                                qacc[c0 + q].y = fma(zr[q], va.y, fma(-zi[q], va.x, qacc[c0 + q].y));
+                        for (int r = 0; r < RPI; ++r)
+                            load4<0>(pr[r] + c0 * 256, pi[r] + c0 * 256, rem[r] - c0 * 32, zr[r], zi[r]);
+#pragma unroll
+                        for (int r = 0; r < RPI; ++r) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if ((c0 + q) * 32 < rem[r]) {
+                                    const double2 vb = pv[(c0 + q) * 32];
+                                    sumr[r] = fma(zr[r][q], vb.x, fma(-zi[r][q], vb.y, sumr[r]));
+                                    sumi[r] = fma(zr[r][q], vb.y, fma(zi[r][q], vb.x, sumi[r]));
+                                    qacc[c0 + q].x = fma(zr[r][q], va[r].x, fma(zi[r][q], va[r].y, qacc[c0 + q].x));
+                                    qacc[c0 + q].y = fma(zr[r][q], va[r].y, fma(-zi[r][q], va[r].x, qacc[c0 + q].y));
+                                }
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sumr += __shfl_xor_sync(0xffffffffu, sumr, o);
-                    sumi += __shfl_xor_sync(0xffffffffu, sumi, o);
+                for (int r = 0; r < RPI; ++r) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        sumr[r] += __shfl_xor_sync(0xffffffffu, sumr[r], o);
+                        sumi[r] += __shfl_xor_sync(0xffffffffu, sumi[r], o);
+                    }
+                    if (lane == 0 && a + r * WARPS < m)
+                        S[a + r * WARPS] = make_double2(fma(dg[r], va[r].x, sumr[r]), fma(dg[r], va[r].y, sumi[r]));
                 }
-                if (lane == 0) S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
             }
+            TICKW(2);  // dots + own rows of the Hermitian product (per warp, before the barrier)
             // column parts: four rounds, warp w adds into slot w / 4 in round w % 4 (fixed order)
 #pragma unroll
             for (int round = 0; round < 4; ++round) {
@@ -277,6 +327,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 }
                 __syncthreads();
             }
+            TICK(3);  // QW rounds (includes waiting for the slowest warp of the product)
             // --- (4) p = A22 v - V y1 - W y2;  tau p;  dot = (tau p)^H v ---
             double dr = 0.0, di = 0.0;
             for (int a = tid; a < m; a += THREADS) {
@@ -302,6 +353,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 di += pr * va.y - pi * va.x;
             }
             cta_sum2<WARPS>(dr, di, red, tid, parity);
+            TICK(4);  // p, tau p, dot
             const double alr = -0.5 * (tr * dr - ti * di);
             const double ali = -0.5 * (tr * di + ti * dr);
             for (int a = tid; a < m; a += THREADS) {
@@ -311,6 +363,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                     make_double2(pq.x + alr * v.x - ali * v.y, pq.y + alr * v.y + ali * v.x);
             }
             __syncthreads();
+            TICK(5);  // w -> X
         }
         // --- trailing update A22 -= V W^H + W V^H on the FP64 tensor cores (rows / columns >= k0 + NB) ---
         const int rt = k0 + nb;
@@ -376,48 +429,63 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 s += WARPS;
             }
             __syncthreads();
+            TICK(6);  // her2k
         }
     }
     __syncthreads();
+#ifdef TBK_PANEL_TIMING
+    if (kk == 0 && lane == 0) printf("panel timing N=%d warp %2d: own product rows %.3f Mcyc\n", N, w, twarp * 1e-6);
+    if (kk == 0 && tid == 0)
+        printf("panel timing N=%d phases: colupd %.3f refl %.3f product(w0) %.3f rounds+wait %.3f p/dot %.3f w %.3f her2k %.3f Mcyc\n",
+               N, tacc[0] * 1e-6, tacc[1] * 1e-6, tacc[2] * 1e-6, tacc[3] * 1e-6, tacc[4] * 1e-6, tacc[5] * 1e-6,
+               tacc[6] * 1e-6);
+#endif
     for (int i = tid; i < N; i += THREADS) {
         D[kk * N + i] = ds[i];
         E[kk * N + i] = (i < N - 1) ? es[i] : 0.0;
     }
 }
 
-template <int THREADS, int MAXC, int MINB>
+template <int THREADS, int MAXC, int MINB, int RPI>
 cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
     const size_t smem = panel_smem_doubles(n, THREADS / 32, MAXC) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB>,
+    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB, RPI>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_panel_kernel<THREADS, MAXC, MINB><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E);
+    int pfd = 1;  // measured (C4, ms per 1184 matrices): off 167, 1 trip 154, 2 trips 156, 4 trips 167, 8 trips 175
+    if (const char* e = getenv("TBK_PANEL_PFD")) pfd = atoi(e);  // tuning hook
+    if (pfd < 0 || pfd > 8) pfd = 1;
+    tridiag_panel_kernel<THREADS, MAXC, MINB, RPI><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-bool tridiag_panel_fits(int n) {
+bool tridiag_panel_fits(int n) {  // (the 16-warp configuration has the largest shared-memory footprint)
+
     return n >= 2 && n <= 640 && panel_smem_doubles(n, 16, n <= 512 ? 16 : 20) * 8 <= 227 * 1024;
 }
 
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
     int t = 0;
-    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);  // tuning hook: threads per matrix for n <= 128
+    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);  // tuning hook: threads per matrix
+    // measured on B200 (ms per 1000 matrices): N = 128: 128 thr 3.57 / 256 thr 3.31 / 512 thr 4.12;
+    // N = 200: 256 thr 10.3 / 512 thr 12.5;  two rows per warp trip (RPI = 2) was slower at every size (register
+    // pressure: 16 accumulator pairs + 16 loads in flight do not fit 128 registers at 512 threads)
     if (n <= 128) {
-        if (t == 128) return launch_panel_t<128, 4, 8>(n, Hp, nk, D, E, st);
-        if (t == 512) return launch_panel_t<512, 4, 2>(n, Hp, nk, D, E, st);
-        return launch_panel_t<256, 4, 4>(n, Hp, nk, D, E, st);
+        if (t == 128) return launch_panel_t<128, 4, 8, 1>(n, Hp, nk, D, E, st);
+        if (t == 512) return launch_panel_t<512, 4, 2, 1>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 4, 4, 1>(n, Hp, nk, D, E, st);
     }
     if (n <= 256) {
-        if (t == 512) return launch_panel_t<512, 8, 1>(n, Hp, nk, D, E, st);
-        return launch_panel_t<256, 8, 2>(n, Hp, nk, D, E, st);
+        if (t == 512) return launch_panel_t<512, 8, 1, 1>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 8, 2, 1>(n, Hp, nk, D, E, st);
     }
-    if (n <= 512) return launch_panel_t<512, 16, 1>(n, Hp, nk, D, E, st);
-    return launch_panel_t<512, 20, 1>(n, Hp, nk, D, E, st);
+    if (n <= 512) return launch_panel_t<512, 16, 1, 1>(n, Hp, nk, D, E, st);
+    return launch_panel_t<512, 20, 1, 1>(n, Hp, nk, D, E, st);
 }
 
 }  // namespace tbk

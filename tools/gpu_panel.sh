@@ -19,7 +19,8 @@ except Exception as e: print("$name parse fail", e)
 PY
 }
 run c4_panel c4 2048 X=1
-run c5_p128 c5 16384 TBK_TRIDIAG_PANEL_MIN=100 TBK_PANEL_T=128
-run c5_p256 c5 16384 TBK_TRIDIAG_PANEL_MIN=100 TBK_PANEL_T=256
-run c5_p512 c5 16384 TBK_TRIDIAG_PANEL_MIN=100 TBK_PANEL_T=512
+run c4_rpi2 c4 2048 TBK_PANEL_RPI=2
+run c4_t384 c4 2048 TBK_PANEL_T=384
+run c5_panel c5 16384 X=1
+run c5_rpi2 c5 16384 TBK_PANEL_RPI=2
 echo "== done"
