@@ -381,6 +381,35 @@ def test_size_boundaries_vs_oracle(tbk, n_orb):
     _check(tbk, p, k, None, orc.hamilton(p.R, p.hop, p.pos, k[:3], 2), orc.eigenval_array(p.R, p.hop, p.pos, k), f"N={n_orb}")
 
 
+def test_trig_product_kernel_matches_general_small_kernel(tbk, monkeypatch):
+    """Nearest-cell N <= 2 models run on the trigonometric-product kernel; the generic fused kernel (TBK_NO_BASIS=1)
+    and the oracle must give the same H(k) and eigenvalues, for every (N, dim) instantiation and ragged batch sizes."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    rng = np.random.default_rng(7)
+    models = [wl.haldane(), wl.simple_model(0.3, -0.2, dim=2), wl.simple_model(-0.4, 0.15, dim=3),
+              wl.synthetic(1, 1, dim=1, seed=3), wl.synthetic(1, 3, dim=2, seed=4), wl.synthetic(1, 5, dim=3, seed=5),
+              wl.synthetic(2, 1, dim=1, seed=6), wl.synthetic(2, 4, dim=2, seed=8), wl.synthetic(2, 13, dim=3, seed=9)]
+    for p in models:
+        assert np.abs(p.R).max() <= 1
+        for nk in (1, 511, 1024, 2500):
+            k = rng.uniform(-2.0, 2.0, size=(nk, p.dim))
+            monkeypatch.delenv("TBK_NO_BASIS", raising=False)
+            ev = tbk.Evaluator(p)
+            e_new, h_new = ev.eigenval_array(k), ev.hamilton(k[:64], convention=2)
+            ev.close()
+            monkeypatch.setenv("TBK_NO_BASIS", "1")
+            ev = tbk.Evaluator(p)
+            e_old, h_old = ev.eigenval_array(k), ev.hamilton(k[:64], convention=2)
+            ev.close()
+            want = orc.eigenval_array(p.R, p.hop, p.pos, k)
+            assert_eig_close(e_new, want, f"product kernel N={p.size} D={p.dim} nk={nk}")
+            assert_eig_close(e_old, want, f"generic kernel N={p.size} D={p.dim} nk={nk}")
+            assert_h_close(h_new, orc.hamilton(p.R, p.hop, p.pos, k[:64], 2), p, "product kernel H")
+            assert np.abs(h_new - h_old).max() <= 1e-13 * h_scale(p)
+
+
 @pytest.mark.parametrize("threads", ["128", "256", "512"])
 def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads):
     """The blocked (panel + tensor-core her2k) reduction forced onto small and ragged sizes: partial last panels,

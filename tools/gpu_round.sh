@@ -42,7 +42,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_c3.csv \
    python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu --no-peaks --no-extra --nk 262144 > $OUT/${TAG}_ncu_c3.log 2>&1
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:hk_small -s 3 -c 1 -f -o $OUT/${TAG}_prof_hk_small \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hk_small|hk_basis" -s 3 -c 1 -f -o $OUT/${TAG}_prof_hk_small \
    python bench.py --steps 2 --warmup 3 --no-cpu --no-peaks --no-extra --nk 20000000 > $OUT/${TAG}_ncu_full_c2.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"hk_gemm|hk_phase|tridiag|ql_" -s 12 -c 4 -f -o $OUT/${TAG}_prof_c3 \
    python bench.py --workload c3 --steps 2 --warmup 3 --no-cpu --no-peaks --no-extra --nk 131072 > $OUT/${TAG}_ncu_full_c3.log 2>&1

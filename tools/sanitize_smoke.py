@@ -19,8 +19,16 @@ cases = [
     ("n70", wl.synthetic(70, 5), 9),
     ("n130", wl.synthetic(130, 3), 3),
     ("n170", wl.synthetic(170, 2), 2),
+    ("simple3d", wl.simple_model(0.3, -0.2), 100),      # N = 2, D = 3: trigonometric-product kernel, 27 functions
+    ("n1", wl.synthetic(1, 3, dim=2), 100),             # N = 1
+    ("blocked n36", wl.synthetic(36, 5), 5),            # blocked tridiagonalisation forced onto small sizes
+    ("blocked n70", wl.synthetic(70, 3), 3),
 ]
 for name, p, nk in cases:
+    if name.startswith("blocked"):
+        os.environ["TBK_TRIDIAG_PANEL_MIN"] = "2"
+    else:
+        os.environ.pop("TBK_TRIDIAG_PANEL_MIN", None)
     ev = tbk.Evaluator(p, device=0)
     k = rng.random((nk, p.dim))
     e = ev.eigenval_array(k)
