@@ -238,13 +238,14 @@ def measured_hbm_peak():
 # DRAM bytes per k-point of the dominant kernels, from the ncu --set full captures summarised in
 # profiles/r01g_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its k-points).
 NCU_TRAFFIC_PER_K = {
-    ("c2", "hk_small"): (320.022016e6 + 279.227904e6) / 2.0e7,   # hk_small_kernel<2,2>, 2e7 k-points per launch
-    ("c3", "hk_gemm"): (76.866048e6 + 132.542464e6) / 17408.0,   # hk_gemm_kernel<9>, 17408 k-points per launch
-    ("c3", "tridiag"): (180.515584e6 + 9.398272e6) / 17408.0,    # tridiag_smem_kernel<32,1>
-    ("c5", "hk_gemm"): (7.695033e9 + 529.375232e6) / 4096.0,     # hk_gemm_kernel<8>
-    ("c4", "tridiag"): (187.473670e9 + 97.022675e9) / 296.0,     # tridiag_big_kernel<16>
+    ("c2", "hk_small"): (320.026880e6 + 278.184448e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
+    ("c3", "hk_gemm"): (77.287680e6 + 133.717504e6) / 17408.0,   # hk_gemm_kernel<9>, 17408 k-points per launch
+    ("c3", "tridiag"): (181.105152e6 + 9.167360e6) / 17408.0,    # tridiag_smem_kernel<32,1>
+    ("c5", "hk_gemm"): (7.699046e9 + 0.530098e9) / 4096.0,       # hk_gemm_kernel<8>
+    ("c5", "tridiag"): (0.594571e9 + 1.301204e9) / 4096.0,       # tridiag_panel_kernel<256,...> (matrices stay in L2)
+    ("c4", "tridiag"): (104.783182e9 + 11.816581e9) / 296.0,     # tridiag_panel_kernel<512,16,...>
 }
-NCU_TRAFFIC_SOURCE = "profiles/r01g_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
+NCU_TRAFFIC_SOURCE = "profiles/r01h_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
 
 
 def flops_per_k(packed):

@@ -60,28 +60,28 @@ __device__ __forceinline__ double ldg_off(unsigned long long gptr) {
     return v;
 }
 
-// Four 32-column chunks of one row (both planes) starting OFF bytes past the row pointers; rem = columns left for this
-// lane (chunk q is inside the row iff 32 q < rem).
-template <int OFF>
+// Four LPR-column chunks of one row (both planes) starting at the row pointers; rem = columns left for this lane
+// (chunk q is inside the row iff LPR q < rem).
+template <int LPR>
 __device__ __forceinline__ void load4(unsigned long long pr, unsigned long long pi, int rem, double (&zr)[4],
                                       double (&zi)[4]) {
     zr[0] = zr[1] = zr[2] = zr[3] = 0.0;
     zi[0] = zi[1] = zi[2] = zi[3] = 0.0;
     if (0 < rem) {
-        zr[0] = ldg_off<OFF>(pr);
-        zi[0] = ldg_off<OFF>(pi);
+        zr[0] = ldg_off<0>(pr);
+        zi[0] = ldg_off<0>(pi);
     }
-    if (32 < rem) {
-        zr[1] = ldg_off<OFF + 256>(pr);
-        zi[1] = ldg_off<OFF + 256>(pi);
+    if (LPR < rem) {
+        zr[1] = ldg_off<LPR * 8>(pr);
+        zi[1] = ldg_off<LPR * 8>(pi);
     }
-    if (64 < rem) {
-        zr[2] = ldg_off<OFF + 512>(pr);
-        zi[2] = ldg_off<OFF + 512>(pi);
+    if (2 * LPR < rem) {
+        zr[2] = ldg_off<LPR * 16>(pr);
+        zi[2] = ldg_off<LPR * 16>(pi);
     }
-    if (96 < rem) {
-        zr[3] = ldg_off<OFF + 768>(pr);
-        zi[3] = ldg_off<OFF + 768>(pi);
+    if (3 * LPR < rem) {
+        zr[3] = ldg_off<LPR * 24>(pr);
+        zi[3] = ldg_off<LPR * 24>(pi);
     }
 }
 
@@ -116,7 +116,7 @@ __host__ __device__ inline size_t panel_smem_doubles(int n, int warps, int maxc)
     return (size_t)4 * NB * n + (size_t)2 * n * (2 + nsw + slots) + 2 * (size_t)n + 4 * NB + 4 * warps + 4;
 }
 
-template <int THREADS, int MAXC, int MINB, int RPI>
+template <int THREADS, int MAXC, int MINB, int LPR>
 __global__ void __launch_bounds__(THREADS, MINB)
 tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E,
                      int pfd /* L2 prefetch distance of the Hermitian product, in warp trips; 0 = off */) {
@@ -236,91 +236,87 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                 if (lane == 0) Y[q] = make_double2(yr, yi);
             }
             // --- (3) Hermitian product with the stored trailing block: row sweeps over the lower triangle.
-            //     A warp owns rows a = w, w + WARPS, ...; lane l owns columns l, l + 32, ... (one register accumulator
-            //     per 32-column chunk for the column part).  Rows two trips ahead are pulled into L2 by a bulk
-            //     prefetch, so the loads below see L2 latency even while the matrix streams from HBM. ---
+            //     LPR lanes share a row (a warp works on 32 / LPR adjacent rows per trip); lane l of a row group owns
+            //     columns l, l + LPR, ... with one register accumulator per LPR-column chunk for the column part.
+            //     The rows of the next trip are pulled into L2 by a bulk prefetch. ---
+            constexpr int RPW = 32 / LPR;
+            const int l = lane % LPR, sub = lane / LPR;
             double2 qacc[MAXC];
 #pragma unroll
             for (int cc = 0; cc < MAXC; ++cc) qacc[cc] = make_double2(0.0, 0.0);
-            if (lane < pfd * RPI) {
-                const int a1 = w + lane * WARPS;
-                if (a1 < m) prefetch_row(Ar, Ai, r0 + a1, r0, a1);
+            if (l == 0) {
+                for (int t = 0; t < pfd; ++t) {
+                    const int a1 = RPW * (w + t * WARPS) + sub;
+                    if (a1 < m) prefetch_row(Ar, Ai, r0 + a1, r0, a1);
+                }
             }
-            const double2* pv = V + lane;
-            for (int a = w; a < m; a += RPI * WARPS) {  // RPI rows per trip: 8 RPI loads in flight per lane
-                if (lane < RPI && pfd > 0) {
-                    const int a2 = a + (pfd * RPI + lane) * WARPS;
+            const double2* pv = V + l;
+            for (int a0 = RPW * w; a0 < m; a0 += RPW * WARPS) {
+                const int a = a0 + sub;
+                if (l == 0 && pfd > 0) {
+                    const int a2 = a + pfd * RPW * WARPS;
                     if (a2 < m) prefetch_row(Ar, Ai, r0 + a2, r0, a2);
                 }
-                unsigned long long pr[RPI], pi[RPI];
-                int rem[RPI];
-                double2 va[RPI];
-                double dg[RPI], sumr[RPI], sumi[RPI];
-                int alast = a;  // longest active row of the trip
-#pragma unroll
-                for (int r = 0; r < RPI; ++r) {
-                    const int ar = a + r * WARPS;
-                    const bool on = ar < m;
-                    const int ac = on ? ar : a;  // inactive rows shadow row a with every column masked off
-                    const int I = r0 + ac;
-                    if (on) alast = ar;
-                    pr[r] = (unsigned long long)__cvta_generic_to_global(Ar + (itri(I) + r0 + lane));
-                    pi[r] = (unsigned long long)__cvta_generic_to_global(Ai + (itrs(I) + r0 + lane));
-                    rem[r] = on ? ar - lane : 0;  // column b = 32 q + lane lies inside the row  <=>  32 q < rem
-                    va[r] = V[ac];
-                    dg[r] = Ar[itri(I) + I];      // real diagonal (same address in every lane)
-                    sumr[r] = 0.0;
-                    sumi[r] = 0.0;
-                }
+                const bool on = a < m;
+                const int ac = on ? a : a0;  // row groups past the end shadow row a0 with every column masked off
+                const int I = r0 + ac;
+                const unsigned long long pr = (unsigned long long)__cvta_generic_to_global(Ar + (itri(I) + r0 + l));
+                const unsigned long long pi = (unsigned long long)__cvta_generic_to_global(Ai + (itrs(I) + r0 + l));
+                const int rem = on ? a - l : 0;    // column b = LPR q + l lies inside the row  <=>  LPR q < rem
+                const double2 va = V[ac];
+                const double dg = Ar[itri(I) + I];  // real diagonal (same address in every lane of the row group)
+                const int alast = (a0 + RPW - 1 < m) ? a0 + RPW - 1 : m - 1;  // longest row of the trip (warp-uniform)
+                double sumr = 0.0, sumi = 0.0;
 #pragma unroll
                 for (int c0 = 0; c0 < MAXC; c0 += 4) {
-                    if (c0 * 32 < alast) {  // warp-uniform; four 32-column chunks per row and batch
-                        double zr[RPI][4], zi[RPI][4];
+                    if (c0 * LPR < alast) {  // warp-uniform; four chunks per batch: 8 loads in flight per lane
+                        double zr[4], zi[4];
+                        load4<LPR>(pr + c0 * LPR * 8, pi + c0 * LPR * 8, rem - c0 * LPR, zr, zi);
 #pragma unroll
-                        for (int r = 0; r < RPI; ++r)
-                            load4<0>(pr[r] + c0 * 256, pi[r] + c0 * 256, rem[r] - c0 * 32, zr[r], zi[r]);
-#pragma unroll
-                        for (int r = 0; r < RPI; ++r) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if ((c0 + q) * 32 < rem[r]) {
-                                    const double2 vb = pv[(c0 + q) * 32];
-                                    sumr[r] = fma(zr[r][q], vb.x, fma(-zi[r][q], vb.y, sumr[r]));
-                                    sumi[r] = fma(zr[r][q], vb.y, fma(zi[r][q], vb.x, sumi[r]));
-                                    qacc[c0 + q].x = fma(zr[r][q], va[r].x, fma(zi[r][q], va[r].y, qacc[c0 + q].x));
-                                    qacc[c0 + q].y = fma(zr[r][q], va[r].y, fma(-zi[r][q], va[r].x, qacc[c0 + q].y));
-                                }
+                        for (int q = 0; q < 4; ++q) {
+                            if (c0 + q < MAXC && (c0 + q) * LPR < rem) {
+                                const double2 vb = pv[(c0 + q) * LPR];
+                                sumr = fma(zr[q], vb.x, fma(-zi[q], vb.y, sumr));
+                                sumi = fma(zr[q], vb.y, fma(zi[q], vb.x, sumi));
+                                qacc[(c0 + q) % MAXC].x = fma(zr[q], va.x, fma(zi[q], va.y, qacc[(c0 + q) % MAXC].x));
+                                qacc[(c0 + q) % MAXC].y = fma(zr[q], va.y, fma(-zi[q], va.x, qacc[(c0 + q) % MAXC].y));
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < RPI; ++r) {
+                for (int o = LPR / 2; o > 0; o >>= 1) {
+                    sumr += __shfl_xor_sync(0xffffffffu, sumr, o);
+                    sumi += __shfl_xor_sync(0xffffffffu, sumi, o);
+                }
+                if (l == 0 && on) S[a] = make_double2(fma(dg, va.x, sumr), fma(dg, va.y, sumi));
+            }
+            if (RPW > 1) {  // the row groups of a warp hold partial column sums for the same columns
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        sumr[r] += __shfl_xor_sync(0xffffffffu, sumr[r], o);
-                        sumi[r] += __shfl_xor_sync(0xffffffffu, sumi[r], o);
+                for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+                    for (int cc = 0; cc < MAXC; ++cc) {
+                        qacc[cc].x += __shfl_xor_sync(0xffffffffu, qacc[cc].x, o);
+                        qacc[cc].y += __shfl_xor_sync(0xffffffffu, qacc[cc].y, o);
                     }
-                    if (lane == 0 && a + r * WARPS < m)
-                        S[a + r * WARPS] = make_double2(fma(dg[r], va[r].x, sumr[r]), fma(dg[r], va[r].y, sumi[r]));
                 }
             }
             TICKW(2);  // dots + own rows of the Hermitian product (per warp, before the barrier)
             // column parts: four rounds, warp w adds into slot w / 4 in round w % 4 (fixed order)
 #pragma unroll
             for (int round = 0; round < 4; ++round) {
-                if ((w & 3) == round) {
-                    double2* slot = QW + (size_t)(w >> 2) * N + lane;
+                if ((w & 3) == round && sub == 0) {
+                    double2* slot = QW + (size_t)(w >> 2) * N + l;
 #pragma unroll
                     for (int cc = 0; cc < MAXC; ++cc) {
-                        if (cc * 32 + lane < m) {
+                        if (cc * LPR + l < m) {
                             if (round == 0) {
-                                slot[cc * 32] = qacc[cc];
+                                slot[cc * LPR] = qacc[cc];
                             } else {
-                                double2 t2 = slot[cc * 32];
+                                double2 t2 = slot[cc * LPR];
                                 t2.x += qacc[cc].x;
                                 t2.y += qacc[cc].y;
-                                slot[cc * 32] = t2;
+                                slot[cc * LPR] = t2;
                             }
                         }
                     }
@@ -446,11 +442,11 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
     }
 }
 
-template <int THREADS, int MAXC, int MINB, int RPI>
+template <int THREADS, int MAXC, int MINB, int LPR>
 cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
     const size_t smem = panel_smem_doubles(n, THREADS / 32, MAXC) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB, RPI>,
+    cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB, LPR>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
@@ -458,7 +454,7 @@ cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cud
     int pfd = 1;  // measured (C4, ms per 1184 matrices): off 167, 1 trip 154, 2 trips 156, 4 trips 167, 8 trips 175
     if (const char* e = getenv("TBK_PANEL_PFD")) pfd = atoi(e);  // tuning hook
     if (pfd < 0 || pfd > 8) pfd = 1;
-    tridiag_panel_kernel<THREADS, MAXC, MINB, RPI><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd);
+    tridiag_panel_kernel<THREADS, MAXC, MINB, LPR><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd);
     return cudaGetLastError();
 }
 
@@ -470,22 +466,27 @@ bool tridiag_panel_fits(int n) {  // (the 16-warp configuration has the largest 
 }
 
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    int t = 0;
-    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);  // tuning hook: threads per matrix
-    // measured on B200 (ms per 1000 matrices): N = 128: 128 thr 3.57 / 256 thr 3.31 / 512 thr 4.12;
-    // N = 200: 256 thr 10.3 / 512 thr 12.5;  two rows per warp trip (RPI = 2) was slower at every size (register
-    // pressure: 16 accumulator pairs + 16 loads in flight do not fit 128 registers at 512 threads)
+    int t = 0, lpr = 0;
+    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);      // tuning hooks: threads per matrix,
+    if (const char* e = getenv("TBK_PANEL_LPR")) lpr = atoi(e);  // lanes per row of the Hermitian product
+    // template arguments: threads, column chunks (n <= chunks * lanes per row), min CTAs per SM, lanes per row
     if (n <= 128) {
-        if (t == 128) return launch_panel_t<128, 4, 8, 1>(n, Hp, nk, D, E, st);
-        if (t == 512) return launch_panel_t<512, 4, 2, 1>(n, Hp, nk, D, E, st);
-        return launch_panel_t<256, 4, 4, 1>(n, Hp, nk, D, E, st);
+        if (lpr == 32) {
+            if (t == 128) return launch_panel_t<128, 4, 8, 32>(n, Hp, nk, D, E, st);
+            if (t == 512) return launch_panel_t<512, 4, 2, 32>(n, Hp, nk, D, E, st);
+            return launch_panel_t<256, 4, 4, 32>(n, Hp, nk, D, E, st);
+        }
+        if (t == 128) return launch_panel_t<128, 8, 8, 16>(n, Hp, nk, D, E, st);
+        if (getenv("TBK_PANEL_MINB4")) return launch_panel_t<256, 8, 4, 16>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 8, 3, 16>(n, Hp, nk, D, E, st);
     }
     if (n <= 256) {
-        if (t == 512) return launch_panel_t<512, 8, 1, 1>(n, Hp, nk, D, E, st);
-        return launch_panel_t<256, 8, 2, 1>(n, Hp, nk, D, E, st);
+        if (lpr == 16) return launch_panel_t<256, 16, 2, 16>(n, Hp, nk, D, E, st);
+        if (t == 512) return launch_panel_t<512, 8, 1, 32>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 8, 2, 32>(n, Hp, nk, D, E, st);
     }
-    if (n <= 512) return launch_panel_t<512, 16, 1, 1>(n, Hp, nk, D, E, st);
-    return launch_panel_t<512, 20, 1, 1>(n, Hp, nk, D, E, st);
+    if (n <= 512) return launch_panel_t<512, 16, 1, 32>(n, Hp, nk, D, E, st);
+    return launch_panel_t<512, 20, 1, 32>(n, Hp, nk, D, E, st);
 }
 
 }  // namespace tbk

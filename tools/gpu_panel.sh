@@ -19,8 +19,12 @@ except Exception as e: print("$name parse fail", e)
 PY
 }
 run c4_panel c4 2048 X=1
-run c4_rpi2 c4 2048 TBK_PANEL_RPI=2
-run c4_t384 c4 2048 TBK_PANEL_T=384
-run c5_panel c5 16384 X=1
-run c5_rpi2 c5 16384 TBK_PANEL_RPI=2
+run c5_lpr16 c5 16384 X=1
+run c5_lpr16_minb4 c5 16384 TBK_PANEL_MINB4=1
+run c5_lpr16_t128 c5 16384 TBK_PANEL_T=128
+run c5_lpr32 c5 16384 TBK_PANEL_LPR=32
+PYTHONPATH=. python tools/tridiag_sweep.py 120:8192 164:4096 200:2048 256:2048 2>&1 | tail -4
+TBK_PANEL_LPR=16 PYTHONPATH=. python tools/tridiag_sweep.py 200:2048 256:2048 2>&1 | tail -2
+echo "== bench c1 large batch"
+timeout 600 python bench.py --workload c1 --nk 2000000 --no-extra --no-cpu --no-peaks --steps 3 --warmup 2 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('c1 2e6', d['value'], d['kernel_ms_per_step'])"
 echo "== done"
