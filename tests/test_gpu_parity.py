@@ -410,8 +410,9 @@ def test_trig_product_kernel_matches_general_small_kernel(tbk, monkeypatch):
             assert np.abs(h_new - h_old).max() <= 1e-13 * h_scale(p)
 
 
+@pytest.mark.parametrize("lpr", ["16", "32"])
 @pytest.mark.parametrize("threads", ["128", "256", "512"])
-def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads):
+def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
     """The blocked (panel + tensor-core her2k) reduction forced onto small and ragged sizes: partial last panels,
     sizes that are not multiples of the 8 x 8 blocks, every thread-count instantiation."""
     from tbmodels_b200 import workloads as wl
@@ -419,10 +420,11 @@ def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads):
     orc = _oracle()
     monkeypatch.setenv("TBK_TRIDIAG_PANEL_MIN", "2")
     monkeypatch.setenv("TBK_PANEL_T", threads)
+    monkeypatch.setenv("TBK_PANEL_LPR", lpr)
     for n_orb in (9, 15, 16, 17, 24, 31, 33, 40, 63, 65, 100, 129, 200, 255, 256):
         p = wl.synthetic(n_orb, 3, seed=1000 + n_orb)
         k = np.random.default_rng(n_orb).uniform(-1, 1, size=(7 if n_orb <= 129 else 3, 3))
-        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads}")
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads} LPR={lpr}")
 
 
 @pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
