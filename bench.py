@@ -253,11 +253,11 @@ def flops_per_k(packed):
     return {"F_H": 8.0 * nR * n * n + 2.0 * n * n, "F_eig": (16.0 / 3.0) * n**3, "bytes": 8.0 * packed.dim + 8.0 * n}
 
 
-def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None):
+def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None, step=None):
     import torch
 
     for _ in range(warmup):
-        ev.eigenval_device(k_dev, out=out_dev)
+        (step or (lambda: ev.eigenval_device(k_dev, out=out_dev)))()
     ev.check()
     ev.profile_read()  # drop warm-up records
     if dist is not None:
@@ -270,7 +270,7 @@ def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None):
     l0 = ev.launch_count
     e0.record()
     for _ in range(steps):
-        ev.eigenval_device(k_dev, out=out_dev)
+        (step or (lambda: ev.eigenval_device(k_dev, out=out_dev)))()
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -330,7 +330,25 @@ def run_gpu_arm(args) -> None:
         g = torch.Generator(device=dev).manual_seed(1234 + rank)
         k_dev = torch.rand((n_k, packed.dim), dtype=torch.float64, device=dev, generator=g)
     out_dev = torch.empty((n_k, packed.size), dtype=torch.float64, device=dev)
-    ms, launches, prof = time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler)
+    step = None
+    mesh_cfg = None
+    if args.mesh:
+        # the workload's k-grid through the mesh entry point: this rank's lines of the (world * L, n, n) mesh
+        if packed.dim != 3:
+            raise SystemExit("--mesh: only the 3-D k-grid workloads (c3, c5)")
+        n_last = 256 if n_k % (256 * 256) == 0 else 64
+        lines = n_k // n_last
+        if lines * n_last != n_k or lines % n_last != 0:
+            raise SystemExit(f"--mesh: n_k = {n_k} is not a whole number of {n_last} x {n_last} mesh planes")
+        planes = lines // n_last
+        dims = (world * planes, n_last, n_last)
+        mesh_cfg = {"dims": list(dims), "lines_per_gpu": lines, "factorised": bool(ev.mesh_factorised(dims))}
+        step = lambda: ev.eigenval_mesh_device(dims, first_line=rank * lines, n_lines=lines, out=out_dev)  # noqa: E731
+        # the same mesh points as an explicit array, for the end-to-end (host buffer) arm and the cross-check
+        idx = torch.arange(rank * n_k, (rank + 1) * n_k, device=dev, dtype=torch.int64)
+        k_dev = torch.stack([(idx // (n_last * n_last)).double() / dims[0], ((idx // n_last) % n_last).double() / n_last,
+                             (idx % n_last).double() / n_last], dim=1).contiguous()
+    ms, launches, prof = time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler, step)
     value = world * n_k * steps / (ms * 1e-3)
 
     # spot parity inside the bench itself (tiny): sorted output, finite
@@ -406,7 +424,11 @@ def run_gpu_arm(args) -> None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    assert np.array_equal(out_host[:64], out_dev[:64].cpu().numpy()), "host and device entry points disagree"
+    if args.mesh:  # explicit k-points (e2e arm) vs the mesh entry point: same values to rounding, not the same bits
+        scale = float(np.abs(out_host[:64]).max())
+        assert np.abs(out_host[:64] - out_dev[:64].cpu().numpy()).max() <= 1e-10 * scale, "mesh and explicit paths disagree"
+    else:
+        assert np.array_equal(out_host[:64], out_dev[:64].cpu().numpy()), "host and device entry points disagree"
     e2e = {
         "value": world * e2e_nk * e2e_steps / e2e_s,
         "unit": UNIT,
@@ -507,6 +529,7 @@ def run_gpu_arm(args) -> None:
                 "path": ev.path,
                 "parallelism": f"k-shards x{world}, no data-path collective",
                 "l2": "inputs+outputs per step exceed the 126 MB L2" if n_k * fl["bytes"] > 2 * 126e6 else "L2 not flushed: batch smaller than L2 (latency-bound parity config)",
+                **({"mesh": mesh_cfg} if mesh_cfg else {}),
             },
             "clocks": clocks,
             "e2e": e2e,
@@ -535,6 +558,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
+    ap.add_argument("--mesh", action="store_true", help="c3 / c5: evaluate the workload's k-grid through eigenval_mesh")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

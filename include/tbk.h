@@ -70,6 +70,19 @@ int tbk_hamilton(tbk_model* m, const double* k_dev, int64_t n_k, int convention,
  *   out_dev [n_k][n_orb] f64 device */
 int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* stream);
 
+/* Model.eigenval on a regular k-mesh without an explicit k array: the mesh has dims[d]
+ * points in dimension d, k_d = (i_d + shift_d) / dims[d] (shift may be NULL), ordered like
+ * numpy.meshgrid(..., indexing="ij") flattened in C order -- the layout of the reference's k-grid workloads.  A LINE
+ * is the run of dims[dim-1] consecutive mesh points along the last dimension; the call evaluates lines
+ * [first_line, first_line + n_lines) (for sharding across GPUs) and writes
+ *   out_dev [n_lines * dims[dim-1]][n_orb] f64 device, ascending per k-point.
+ * Same results as tbk_eigenval on the explicit k-points within the parity bounds (the Fourier sum is factorised over
+ * the last dimension where the model allows it, otherwise the k-points are generated on the device and the ordinary
+ * path runs).  tbk_mesh_factorised reports which of the two will be used (1 / 0). */
+int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
+                      double* out_dev, void* stream);
+int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims);
+
 /* Same two operations with HOST buffers (copies inside, synchronous on return). */
 int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host);
 int tbk_eigenval_host(tbk_model* m, const double* k_host, int64_t n_k, double* out_host);
@@ -83,7 +96,7 @@ int64_t tbk_launch_count(const tbk_model* m);
  * 5 phase tiles for the GEMM.
  * tbk_profile(m, 1) starts recording; tbk_profile_read synchronises, returns the accumulated milliseconds
  * and launch counts per class since the last read (arrays of TBK_PROFILE_CLASSES) and resets them. */
-#define TBK_PROFILE_CLASSES 6
+#define TBK_PROFILE_CLASSES 7
 int tbk_profile(tbk_model* m, int enable);
 int tbk_profile_read(tbk_model* m, double* ms, int64_t* count);
 /* Bytes of device scratch currently held by the handle. */

@@ -22,6 +22,8 @@ SYMBOLS = (
     "tbk_model_info",
     "tbk_hamilton",
     "tbk_eigenval",
+    "tbk_eigenval_mesh",
+    "tbk_mesh_factorised",
     "tbk_hamilton_host",
     "tbk_eigenval_host",
     "tbk_model_check",
@@ -81,6 +83,10 @@ def load() -> C.CDLL:
     lib.tbk_hamilton.restype = C.c_int
     lib.tbk_eigenval.argtypes = [vp, vp, C.c_int64, vp, vp]
     lib.tbk_eigenval.restype = C.c_int
+    lib.tbk_eigenval_mesh.argtypes = [vp, C.POINTER(C.c_int64), dp, C.c_int64, C.c_int64, vp, vp]
+    lib.tbk_eigenval_mesh.restype = C.c_int
+    lib.tbk_mesh_factorised.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.tbk_mesh_factorised.restype = C.c_int
     lib.tbk_hamilton_host.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
     lib.tbk_hamilton_host.restype = C.c_int
     lib.tbk_eigenval_host.argtypes = [vp, vp, C.c_int64, vp]

@@ -140,7 +140,7 @@ class Evaluator:
     def workspace_bytes(self) -> int:
         return int(self._lib.tbk_workspace_bytes(self._handle))
 
-    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase")
+    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase", "mesh_lines")
 
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on its stream (read back with :meth:`profile_read`)."""
@@ -148,10 +148,59 @@ class Evaluator:
 
     def profile_read(self) -> dict:
         """``{class: (total_ms, launches)}`` accumulated since the last read (synchronises the device)."""
-        ms = (C.c_double * 6)()
-        cnt = (C.c_int64 * 6)()
+        ms = (C.c_double * len(self.PROFILE_CLASSES))()
+        cnt = (C.c_int64 * len(self.PROFILE_CLASSES))()
         _capi.check(self._lib.tbk_profile_read(self._handle, ms, cnt))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES)}
+
+    # ------------------------------------------------------------------ regular k-meshes (no explicit k array)
+    def _mesh_args(self, dims, shift):
+        dims = [int(x) for x in np.atleast_1d(dims)]
+        if len(dims) != self.dim or any(x < 1 for x in dims):
+            raise ValueError(f"dims must hold {self.dim} positive mesh sizes")
+        c_dims = (C.c_int64 * self.dim)(*dims)
+        c_shift = None
+        if shift is not None:
+            shift = [float(x) for x in np.atleast_1d(shift)]
+            if len(shift) != self.dim:
+                raise ValueError(f"shift must hold {self.dim} values")
+            c_shift = (C.c_double * self.dim)(*shift)
+        n_lines_total = int(np.prod(dims[:-1])) if self.dim > 1 else 1
+        return dims, c_dims, c_shift, n_lines_total
+
+    def mesh_factorised(self, dims) -> bool:
+        """True if :meth:`eigenval_mesh` will factorise the Fourier sum over the last mesh dimension for this model."""
+        _, c_dims, _, _ = self._mesh_args(dims, None)
+        return bool(self._lib.tbk_mesh_factorised(self._handle, c_dims))
+
+    def eigenval_mesh_device(self, dims, shift=None, first_line=0, n_lines=None, out=None):
+        """Eigenvalues on the regular mesh ``k_d = (i_d + shift_d) / dims[d]`` (``numpy.meshgrid(..., indexing="ij")``
+        order), without an explicit k array: ``[n_lines * dims[-1], N]`` float64 CUDA tensor, asynchronous.
+
+        ``first_line`` / ``n_lines`` select a contiguous range of lines (runs along the last dimension) for sharding.
+        Same values as ``eigenval_device`` on the explicit mesh points, within the parity bounds."""
+        import torch
+
+        dims, c_dims, c_shift, total = self._mesh_args(dims, shift)
+        if n_lines is None:
+            n_lines = total - first_line
+        n_k = int(n_lines) * dims[-1]
+        if out is None:
+            out = torch.empty((n_k, self.size), dtype=torch.float64, device=f"cuda:{self.device}")
+        elif tuple(out.shape) != (n_k, self.size) or out.dtype != torch.float64 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float64 tensor [n_lines * dims[-1], N]")
+        _capi.check(
+            self._lib.tbk_eigenval_mesh(
+                self._handle, c_dims, c_shift, int(first_line), int(n_lines), C.c_void_p(out.data_ptr()), self._stream()
+            )
+        )
+        return out
+
+    def eigenval_mesh(self, dims, shift=None) -> np.ndarray:
+        """Host copy of :meth:`eigenval_mesh_device` for the whole mesh: ``[prod(dims), N]``."""
+        res = self.eigenval_mesh_device(dims, shift)
+        self.check()
+        return res.cpu().numpy()
 
     def close(self) -> None:
         self._finalizer()

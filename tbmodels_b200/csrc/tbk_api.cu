@@ -105,6 +105,13 @@ struct tbk_model {
     double* wsH = nullptr;  // [chunk][n*n] packed H(k)
     double* wsE = nullptr;  // [chunk][n]   sub-diagonals
     double* wsQ = nullptr;  // phase tiles of the chunk (GEMM path only)
+    // regular k-mesh entry point (tbk_eigenval_mesh)
+    int* dRc = nullptr;       // [nRpad] class (last component) of every stored R
+    double* dZc = nullptr;    // [nclass]
+    double* wsAB = nullptr;   // [lines][2 nclass][n*n] line coefficients (stage A output)
+    double* wsQz = nullptr;   // [n_z][2 nclass] cos / sin along the last mesh dimension
+    double* wsK = nullptr;    // explicit k-points of a mesh range (ordinary-path fallback)
+    size_t ab_bytes = 0, qz_bytes = 0, k_bytes = 0;
     long chunk = 0;
     size_t ws_bytes = 0;
     size_t model_bytes = 0;
@@ -122,8 +129,8 @@ struct tbk_model {
         int cls;
     };
     std::vector<ProfRec> prof;
-    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
-    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0};
+    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0, 0};
+    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the launch stream.
@@ -240,6 +247,68 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
         double* D = out + c0 * md.n;
         LAUNCH(5, st, launch_hk_phase(md, k + c0 * md.dim, cn, m->wsQ, st));
         LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
+        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
+        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
+    }
+    return TBK_OK;
+}
+
+int grow(double** p, size_t* have, size_t want) {
+    if (want <= *have) return TBK_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    CU(cudaMalloc(p, want));
+    *have = want;
+    return TBK_OK;
+}
+
+// Lines of a regular mesh can be factorised when the model runs on the GEMM path, has at least two dimensions, a line
+// fits one workspace chunk and the 2 C pseudo k-points of a line are fewer than its mesh points.
+bool mesh_factorised(const tbk_model* m, const int64_t* dims) {
+    const ModelDev& md = m->md;
+    if (md.small_ok || md.kind != 0 || md.nclass <= 0 || md.dim < 2) return false;
+    if (getenv("TBK_NO_MESH_FACTOR")) return false;  // test hook: explicit k-points through the ordinary path
+    const long nz = (long)dims[md.dim - 1];
+    if (2L * md.nclass > nz || 2 * md.nclass > 256) return false;
+    if (mesh_lines_smem_bytes(2 * md.nclass) > 200 * 1024) return false;
+    return nz <= pick_chunk(m);
+}
+
+int run_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, long line0, long n_lines, double* out,
+                      cudaStream_t st) {
+    const ModelDev& md = m->md;
+    const long nz = (long)dims[md.dim - 1];
+    if (n_lines <= 0 || nz <= 0) return TBK_OK;
+    if (!mesh_factorised(m, dims)) {
+        // ordinary path on k-points generated on the device, one workspace chunk at a time
+        const long total = n_lines * nz;
+        const long kchunk = std::min<long>(total, 1L << 22);
+        if (int rc = grow(&m->wsK, &m->k_bytes, (size_t)kchunk * md.dim * 8)) return rc;
+        for (long c0 = 0; c0 < total; c0 += kchunk) {
+            const long cn = std::min(kchunk, total - c0);
+            LAUNCH(5, st, launch_mesh_kpoints(md.dim, dims, shift, line0 * nz + c0, cn, m->wsK, st));
+            if (int rc = run_eigenval(m, m->wsK, cn, out + c0 * md.n, st)) return rc;
+        }
+        return TBK_OK;
+    }
+    const int K2 = 2 * md.nclass;
+    const long NN = (long)md.n * md.n;
+    if (int rc = ensure_workspace(m, n_lines * nz)) return rc;
+    const long lchunk = std::max<long>(1, m->chunk / nz);  // whole lines per chunk (nz <= chunk was checked)
+    const long lmax = std::min(lchunk, n_lines);
+    if (int rc = grow(&m->wsAB, &m->ab_bytes, (size_t)lmax * K2 * NN * 8)) return rc;
+    if (int rc = grow(&m->wsQz, &m->qz_bytes, (size_t)nz * K2 * 8)) return rc;
+    LAUNCH(5, st, launch_mesh_qz(md, nz, shift ? shift[md.dim - 1] : 0.0, m->wsQz, st));
+    for (long l0 = 0; l0 < n_lines; l0 += lchunk) {
+        const long ln = std::min(lchunk, n_lines - l0);
+        const long cn = ln * nz;
+        double* D = out + l0 * nz * md.n;
+        // stage A: the 2 C line coefficients of every line as pseudo k-points through the DMMA GEMM
+        LAUNCH(5, st, launch_mesh_phase(md, dims, shift, line0 + l0, ln, m->wsQ, st));
+        LAUNCH(0, st, launch_hk_gemm(md, ln * K2, m->wsQ, m->wsAB, st));
+        // stage B: expand every line along the last mesh dimension
+        LAUNCH(6, st, launch_mesh_lines(md, m->wsAB, m->wsQz, nz, ln, m->wsH, st));
         LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
         LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
     }
@@ -470,6 +539,24 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
         md.Ri = m->dRi;
     } else {
         if (int rc = upload_gemm_weights(m, W, 2 * n_R)) return bail(rc);
+        if (dim >= 2 && n_R > 0) {  // classes of the stored R by their last component (hk_mesh.cu)
+            std::vector<int> zs;
+            for (int r = 0; r < n_R; ++r) zs.push_back(R[(size_t)r * dim + dim - 1]);
+            std::vector<int> uniq(zs);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            std::vector<int> Rc((size_t)md.kchunks * 8, -1);
+            for (int r = 0; r < n_R; ++r)
+                Rc[r] = (int)(std::lower_bound(uniq.begin(), uniq.end(), zs[r]) - uniq.begin());
+            std::vector<double> zc(uniq.begin(), uniq.end());
+            CUB(cudaMalloc(&m->dRc, Rc.size() * sizeof(int)));
+            CUB(cudaMemcpy(m->dRc, Rc.data(), Rc.size() * sizeof(int), cudaMemcpyHostToDevice));
+            CUB(cudaMalloc(&m->dZc, zc.size() * 8));
+            CUB(cudaMemcpy(m->dZc, zc.data(), zc.size() * 8, cudaMemcpyHostToDevice));
+            md.Rc = m->dRc;
+            md.zc = m->dZc;
+            md.nclass = (int)uniq.size();
+        }
     }
 #undef CUB
     *out = m;
@@ -543,6 +630,11 @@ int tbk_model_destroy(tbk_model* m) {
     cudaFree(m->wsH);
     cudaFree(m->wsE);
     cudaFree(m->wsQ);
+    cudaFree(m->dRc);
+    cudaFree(m->dZc);
+    cudaFree(m->wsAB);
+    cudaFree(m->wsQz);
+    cudaFree(m->wsK);
     for (int b = 0; b < 2; ++b) {
         cudaFree(m->hk[b]);
         cudaFree(m->ho[b]);
@@ -582,6 +674,29 @@ int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
     return run_eigenval(m, k_dev, (long)n_k, out_dev, (cudaStream_t)stream);
+}
+
+int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
+                      double* out_dev, void* stream) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigenval_mesh: null handle");
+    if (!dims) return fail(TBK_E_INVALID, "tbk_eigenval_mesh: dims is null");
+    int64_t lines = 1;
+    for (int d = 0; d < m->md.dim; ++d) {
+        if (dims[d] < 1) return fail(TBK_E_INVALID, "tbk_eigenval_mesh: dims[%d] = %lld must be >= 1", d, (long long)dims[d]);
+        if (d < m->md.dim - 1) lines *= dims[d];
+    }
+    if (first_line < 0 || n_lines < 0 || first_line + n_lines > lines)
+        return fail(TBK_E_INVALID, "tbk_eigenval_mesh: lines [%lld, %lld) outside the mesh (%lld lines)",
+                    (long long)first_line, (long long)(first_line + n_lines), (long long)lines);
+    if (n_lines > 0 && !out_dev) return fail(TBK_E_INVALID, "tbk_eigenval_mesh: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    return run_eigenval_mesh(m, dims, shift, (long)first_line, (long)n_lines, out_dev, (cudaStream_t)stream);
+}
+
+int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims) {
+    if (!m || !dims) return 0;
+    return mesh_factorised(m, dims) ? 1 : 0;
 }
 
 int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host) {

@@ -31,6 +31,10 @@ struct ModelDev {
     // sin 2 pi k_d} (hk_small.cu, hk_basis_kernel); basis[b * n * n + e], b = sum_d t_d 3^d, t_d in {0: 1, 1: cos, 2: sin}
     int basis_ok = 0;
     double basis[27 * 4] = {0};
+    // regular k-meshes (hk_mesh.cu): stored R vectors sorted into classes by their last component
+    int nclass = 0;               // 0: mesh factorisation not available (fused path, k.p model, dim < 2)
+    const int* Rc = nullptr;      // [nRpad] class of every R vector (-1 for the padding rows)
+    const double* zc = nullptr;   // [nclass] last component of the class
     // k.p models (reference src/tbmodels/kdotp.py:51-82): kind = 1, the GEMM coefficients are the monomials
     // prod_d k_d^{p_d} instead of [cos | sin] phases; Pw holds the integer powers [kchunks * 16][dim]
     int kind = 0;
@@ -49,6 +53,15 @@ size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);
 // packed H -> full complex128 [nk][n][n]; convention 1 applies the orbital-position phases.
 cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention,
                           double* out, cudaStream_t st);
+// Regular k-mesh path (hk_mesh.cu): lines along the last mesh dimension; see the file header.
+cudaError_t launch_mesh_phase(const ModelDev& m, const int64_t* dims, const double* shift, long line0, long n_lines,
+                              double* Qt, cudaStream_t st);
+cudaError_t launch_mesh_qz(const ModelDev& m, long nz, double shift, double* Qz, cudaStream_t st);
+cudaError_t launch_mesh_lines(const ModelDev& m, const double* AB, const double* Qz, long nz, long n_lines, double* Hp,
+                              cudaStream_t st);
+cudaError_t launch_mesh_kpoints(int dim, const int64_t* dims, const double* shift, long first, long count, double* k,
+                                cudaStream_t st);
+size_t mesh_lines_smem_bytes(int K2);
 // Batched Hermitian -> tridiagonal reduction (Hp is destroyed). D, E: [nk][n].
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).

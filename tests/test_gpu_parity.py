@@ -516,3 +516,86 @@ def test_cli_eigenvals(tbk, tmp_path, capsys, kpoints_file_name, verbosity):
     k_ref, e_ref = io.load_eigenvals(os.path.join(samples_dir, "silicon_eigenvals.hdf5"))
     assert np.array_equal(k, k_ref)
     np.testing.assert_allclose(e, e_ref, rtol=0, atol=1e-10)
+
+
+def _mesh_points(dims, shift=None):
+    axes = [(np.arange(n) + (0.0 if shift is None else shift[d])) / n for d, n in enumerate(dims)]
+    return np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, len(dims))
+
+
+@pytest.mark.parametrize("case", ["c3-like", "ragged", "2d", "n50", "shifted", "fallback-small", "fallback-short-lines", "4d"])
+def test_eigenval_mesh_matches_explicit_kpoints(tbk, case):
+    """tbk_eigenval_mesh: factorised over the last mesh dimension where the model allows it, explicit
+    device-generated k-points otherwise; either way the oracle's eigenvalues on the explicit mesh points."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    shift = None
+    if case == "c3-like":
+        p, dims, fact = wl.synthetic(36, 60, seed=11), (3, 5, 40), True
+    elif case == "ragged":
+        p, dims, fact = wl.synthetic(13, 30, seed=12), (2, 7, 67), True       # odd N: scalar stores, partial tiles
+    elif case == "2d":
+        p, dims, fact = wl.synthetic(20, 12, dim=2, seed=13), (9, 33), True
+    elif case == "n50":
+        p, dims, fact = wl.synthetic(50, 8, seed=14), (2, 2, 130), True       # two 64-point steps + remainder
+    elif case == "shifted":
+        p, dims, fact, shift = wl.synthetic(24, 20, seed=15), (4, 3, 32), True, (0.5, 0.25, 0.125)
+    elif case == "fallback-small":
+        p, dims, fact = wl.synthetic(6, 20, seed=16), (3, 4, 50), False       # fused small-N path: no factorisation
+    elif case == "fallback-short-lines":
+        p, dims, fact = wl.synthetic(24, 60, seed=17), (6, 6, 4), False       # 2 C > points per line
+    else:
+        p, dims, fact = wl.synthetic(12, 10, dim=4, seed=18), (2, 3, 2, 24), True
+    k = _mesh_points(dims, shift)
+    want = orc.eigenval_array(p.R, p.hop, p.pos, k)
+    ev = tbk.Evaluator(p)
+    try:
+        assert ev.mesh_factorised(dims) == fact, case
+        got = ev.eigenval_mesh(dims, shift)
+        assert_eig_close(got, want, f"mesh {case}")
+        assert np.all(np.diff(got, axis=1) >= 0)
+        # a range of lines (what a rank of a sharded run evaluates) is the matching slice, bit for bit
+        n_lines = int(np.prod(dims[:-1]))
+        lo, cnt = n_lines // 3, max(1, n_lines // 2)
+        cnt = min(cnt, n_lines - lo)
+        part = ev.eigenval_mesh_device(dims, shift, first_line=lo, n_lines=cnt).cpu().numpy()
+        assert np.array_equal(part, got[lo * dims[-1]:(lo + cnt) * dims[-1]])
+        # and the ordinary entry point on the explicit mesh points agrees to rounding
+        explicit = ev.eigenval_array(k)
+        assert np.abs(explicit - got).max() <= 1e-12 * max(np.abs(want).max(), 1.0)
+    finally:
+        ev.close()
+
+
+def test_eigenval_mesh_small_workspace_chunks_lines(tbk, monkeypatch):
+    """Several workspace chunks of whole lines give the bits of one chunk (the line is the unit of the factorisation)."""
+    from tbmodels_b200 import workloads as wl
+
+    p = wl.synthetic(36, 40, seed=21)
+    dims = (7, 9, 48)
+    ev = tbk.Evaluator(p)
+    ref = ev.eigenval_mesh(dims)
+    ev.close()
+    monkeypatch.setenv("TBK_WORKSPACE_MB", "8")  # ~ 600 matrices of 36 x 36 per chunk -> 12 lines per chunk
+    ev2 = tbk.Evaluator(p)
+    try:
+        assert ev2.mesh_factorised(dims)
+        assert np.array_equal(ev2.eigenval_mesh(dims), ref)
+    finally:
+        ev2.close()
+
+
+def test_eigenval_mesh_argument_errors(tbk):
+    from tbmodels_b200 import workloads as wl
+
+    ev = tbk.Evaluator(wl.synthetic(12, 5, seed=3))
+    try:
+        with pytest.raises(ValueError):
+            ev.eigenval_mesh((4, 4))
+        with pytest.raises(ValueError):
+            ev.eigenval_mesh((4, 0, 4))
+        with pytest.raises(tbk.TbkError):
+            ev.eigenval_mesh_device((4, 4, 4), first_line=10, n_lines=10)
+    finally:
+        ev.close()
