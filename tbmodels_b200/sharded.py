@@ -93,6 +93,15 @@ class ShardedEvaluator:
         lo, hi = self.bounds(k_all.shape[0])
         return lo, hi, self.local.eigenval_device(k_all[lo:hi].contiguous())
 
+    def eigenval_mesh_local(self, dims, shift=None):
+        """This rank's contiguous range of LINES (runs along the last dimension) of the regular mesh ``dims``
+        -> ``(first_point, last_point, eig)``; see :meth:`Evaluator.eigenval_mesh_device`.  No collective."""
+        dims = [int(x) for x in dims]
+        n_lines = int(np.prod(dims[:-1])) if len(dims) > 1 else 1
+        lo, hi = self.bounds(n_lines)
+        eig = self.local.eigenval_mesh_device(dims, shift, first_line=lo, n_lines=hi - lo)
+        return lo * dims[-1], hi * dims[-1], eig
+
     def hamilton_local(self, k_all, convention=2):
         lo, hi = self.bounds(k_all.shape[0])
         return lo, hi, self.local.hamilton_device(k_all[lo:hi].contiguous(), convention=convention)

@@ -183,6 +183,13 @@ def kgrid(n: int, dim: int = 3) -> np.ndarray:
     return np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, dim)
 
 
+def kgrid_points(dims, shift=None) -> np.ndarray:
+    """Explicit points of the regular mesh ``k_d = (i_d + shift_d) / dims[d]`` in 'ij' / C order: what
+    ``Evaluator.eigenval_mesh`` evaluates without the array."""
+    axes = [(np.arange(int(n)) + (0.0 if shift is None else float(shift[d]))) / int(n) for d, n in enumerate(dims)]
+    return np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, len(dims))
+
+
 def load_packed(path) -> PackedModel:
     """Load a packed model saved with ``np.savez(path, R=..., hop=..., pos=...)``."""
     with np.load(path) as f:
