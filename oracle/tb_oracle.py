@@ -143,3 +143,30 @@ def hamilton_longdouble(R, hop, pos, k, convention=2):
         pe = np.cos(2 * pi_l * x) + 1j * np.sin(2 * pi_l * x)
         H = pe.conjugate()[:, :, None] * H * pe[:, None, :]
     return H
+
+
+def hamilton_mesh_factorised(R, hop, pos, dims, shift=None):
+    """Convention-2 H(k) on the regular mesh ``k_d = (i_d + shift_d) / dims[d]`` ('ij' order), evaluated the way
+    ``tbk_eigenval_mesh`` does it (tbmodels_b200/csrc/hk_mesh.cu): stored R sorted into classes by their last component,
+    per mesh line the class sums ``G_c = sum_{r in c} e^{2 pi i kappa.R_r} T_r`` over the leading coordinates, then
+    ``H = sum_c e^{2 pi i k_z z_c} G_c + h.c.`` along the line.  A restatement of the device algorithm's ALGEBRA (to be
+    compared with :func:`hamilton` on the explicit mesh points), not of reference code: the reference has no mesh path.
+    """
+    R = np.asarray(R)
+    hop = np.asarray(hop)
+    dims = [int(n) for n in dims]
+    dim = len(dims)
+    size = np.asarray(pos).shape[0]
+    shift = [0.0] * dim if shift is None else [float(x) for x in shift]
+    axes = [(np.arange(n) + shift[d]) / n for d, n in enumerate(dims)]
+    kz = axes[-1]
+    lines = np.stack(np.meshgrid(*axes[:-1], indexing="ij"), axis=-1).reshape(-1, dim - 1) if dim > 1 else np.zeros((1, 0))
+    classes = sorted(set(int(z) for z in R[:, -1])) if len(R) else []
+    H = np.zeros((lines.shape[0], dims[-1], size, size), dtype=complex)
+    for z in classes:
+        sel = R[:, -1] == z
+        phases = np.exp(2j * np.pi * (lines @ R[sel, :-1].T))              # [n_lines, n_r]
+        G = np.einsum("lr,rij->lij", phases, hop[sel])                     # [n_lines, N, N]
+        H += np.exp(2j * np.pi * kz * z)[None, :, None, None] * G[:, None, :, :]
+    H = H.reshape(-1, size, size)
+    return H + H.conjugate().transpose((0, 2, 1))

@@ -164,3 +164,22 @@ def test_reference_simple_model_goldens():
         for ki, kpt in enumerate(r["kpt"]):
             assert np.abs(orc.hamilton(p.R, p.hop, p.pos, kpt) - d[f"hamilton_t{ti}_k{ki}"]).max() < 1e-12
             assert np.abs(orc.eigenval(p.R, p.hop, p.pos, kpt) - d[f"eigenval_t{ti}_k{ki}"]).max() < 1e-12
+
+
+def test_mesh_factorisation_algebra_matches_the_fourier_sum():
+    """The identity behind tbk_eigenval_mesh (class sums over the leading mesh coordinates, then one phase per class
+    along the last one), restated in numpy, against the pinned restatement of Model.hamilton on the explicit points."""
+    from oracle import tb_oracle as orc
+    from tbmodels_b200 import workloads as wl
+
+    for p, dims, shift in (
+        (wl.synthetic(5, 40, seed=1), (3, 4, 6), None),
+        (wl.synthetic(3, 12, dim=2, seed=2), (5, 7), (0.5, 0.25)),
+        (wl.synthetic(4, 9, dim=4, seed=3), (2, 2, 3, 4), None),
+        (wl.synthetic(2, 3, dim=1, seed=4), (9,), (0.125,)),
+    ):
+        k = wl.kgrid_points(dims, shift)
+        want = orc.hamilton(p.R, p.hop, p.pos, k, 2)
+        got = orc.hamilton_mesh_factorised(p.R, p.hop, p.pos, dims, shift)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(p.hop).max() * p.n_R
