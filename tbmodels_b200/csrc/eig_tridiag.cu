@@ -13,6 +13,7 @@
 // Every group executes exactly the same instruction sequence (no data-dependent early exits), so sub-warp groups can
 // share a warp and use __syncwarp().  Outputs: D[k][0..N) diagonal, E[k][0..N-1) sub-diagonal, consumed by eig_ql.cu.
 #include <cstdlib>
+#include <cstring>
 
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
@@ -189,7 +190,12 @@ __device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }
 // matrix, shorter serial loops -- the kernel is latency bound, shared memory caps the number of resident matrices.
 template <int G, int CS>
 __global__ void __launch_bounds__((G > 512 ? G : 512))
-tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+tridiag_smem_kernel(double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D, double* __restrict__ E,
+                    int ldo, int off, int nsteps) {
+    // Staged reduction (launch_tridiag): the matrix of this launch is the trailing N x N block of a larger one that sits
+    // at Hp + k * mstride; the launch performs nsteps Householder steps (all N - 1 if nsteps >= N - 1), writes the
+    // diagonal / sub-diagonal entries it produces to D / E [k * ldo + off + i] and, if steps remain, stores the
+    // remaining (N - nsteps)^2 trailing block back in packed form at the head of the same slot for the next launch.
     constexpr int NW = G > 32 ? G / 32 : 1;
     constexpr int RT = G / CS;
     static_assert(CS == 1 || (RT % 32 == 0), "column slices must be whole warps");
@@ -199,7 +205,8 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     const int t = threadIdx.x % G;
     const int rr = t % RT, cs = t / RT;
     const int ntri = itri(N);
-    const long NN = (long)N * N;
+    const long NN = mstride;
+    const int nst = nsteps < N - 1 ? nsteps : N - 1;
 
     const long kidx = (long)blockIdx.x * MPB + group;
     const bool valid = kidx < nk;
@@ -234,7 +241,7 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     group_sync<G>(group);
 
     int parity = 0;
-    for (int j = 0; j < N - 1; ++j) {
+    for (int j = 0; j < nst; ++j) {
         const int m = N - 1 - j;
         const int r0 = j + 1;
         // --- reflector from column j ---
@@ -351,6 +358,28 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
         }
         group_sync<G>(group);
     }
+    if (nst < N - 1) {
+        // stage boundary: emit the entries produced so far and hand the trailing block to the next launch
+        if (valid) {
+            for (int i = t; i < nst; i += G) {
+                D[kidx * ldo + off + i] = ds[i];
+                E[kidx * ldo + off + i] = es[i];
+            }
+            const int M = N - nst;
+            double* dst = Hp + kk * NN;
+            const int mtri = itri(M);
+            for (int e = t; e < mtri; e += G) {  // packed element e of the M x M block = (i, c), c <= i
+                int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                while (itri(i) > e) --i;
+                while (itri(i + 1) <= e) ++i;
+                const int c = e - itri(i);
+                const double2 z = A[itri(nst + i) + nst + c];
+                dst[e] = z.x;
+                if (c < i) dst[mtri + ((i * (i - 1)) >> 1) + c] = z.y;
+            }
+        }
+        return;
+    }
     if (t == 0) {
         ds[N - 1] = A[itri(N - 1) + (N - 1)].x;
         es[N - 1] = 0.0;
@@ -358,8 +387,8 @@ tridiag_smem_kernel(const double* __restrict__ Hp, int N, long nk, double* __res
     group_sync<G>(group);
     if (valid) {
         for (int i = t; i < N; i += G) {
-            D[kidx * N + i] = ds[i];
-            E[kidx * N + i] = es[i];
+            D[kidx * ldo + off + i] = ds[i];
+            E[kidx * ldo + off + i] = es[i];
         }
     }
 }
@@ -840,7 +869,10 @@ cudaError_t launch_big(int n, double* Hp, long nk, double* D, double* E, cudaStr
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int G, int CS>
-cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride = 0, int ldo = 0,
+                     int off = 0, int nsteps = 1 << 30) {
+    if (mstride == 0) mstride = (long)n * n;
+    if (ldo == 0) ldo = n;
     constexpr int NW = G > 32 ? G / 32 : 1;
     constexpr int CTA = G > TPB ? G : TPB;
     const long ntri = (long)n * (n + 1) / 2;
@@ -870,7 +902,7 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         const long blocks = (nk + best_mpb - 1) / best_mpb;
         if (blocks <= 0) return cudaSuccess;
         if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
-        tridiag_smem_kernel<G, CS><<<(unsigned)blocks, G * best_mpb, smem, st>>>(Hp, n, nk, D, E);
+        tridiag_smem_kernel<G, CS><<<(unsigned)blocks, G * best_mpb, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off, nsteps);
         return cudaGetLastError();
     }
     // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
@@ -905,32 +937,54 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     // N = 100: 1.47 / 1.95, 128: 3.65 / 3.31, 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125
     if (g == 0 && n >= 120 && !getenv("TBK_TRIDIAG_NOPANEL") && tridiag_panel_fits(n))
         return launch_tridiag_panel(n, Hp, nk, D, E, st);
-    if (g == 0) {  // defaults, from N only (never from the batch: results must not depend on the batch size)
-        if (n <= 10) g = 8;
-        else if (n <= 20) g = 16;
-        else if (n <= 48) g = 32;
-        else if (n <= 96) g = 128;
-        else g = 256;
-        cs = n <= 48 ? 1 : (n <= 96 ? 2 : 4);  // measured on B200: N = 36 best at (32, 1), N = 128 at (256, 4)
-    }
+    // Staged reduction (shared-memory kernels, 25 <= N < 120): the trailing block shrinks, so after every stage the
+    // remaining (smaller) problem is relaunched with several times more matrices resident per SM -- shared memory per
+    // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
+    // on the batch): N -> ratio * N -> ... until <= 16.  TBK_TRIDIAG_STAGES="0" disables, "p" sets the ratio in percent.
+    int ratio = 67;
+    if (const char* e = getenv("TBK_TRIDIAG_STAGES")) ratio = atoi(e);
+    const bool staged = g == 0 && n >= 25 && n < 120 && ratio > 0 && ratio < 100;
+    const long ms = (long)n * n;
+    int cur = n, done = 0;
+    for (;;) {
+        int next = 0;
+        if (staged && cur > 16) {
+            next = (cur * ratio + 50) / 100;
+            if (next < 12) next = 12;
+            if (next >= cur) next = 0;
+        }
+        const int nsteps = next ? cur - next : (1 << 30);
+        int gg = g, cc = cs;
+        if (gg == 0) {  // defaults, from the size only
+            if (cur <= 10) gg = 8;
+            else if (cur <= 20) gg = 16;
+            else if (cur <= 48) gg = 32;
+            else if (cur <= 96) gg = 128;
+            else gg = 256;
+            cc = cur <= 48 ? 1 : (cur <= 96 ? 2 : 4);  // measured on B200: N = 36 best at (32, 1), N = 128 at (256, 4)
+        }
+        cudaError_t err = cudaErrorInvalidValue;
 #define TBK_CASE(G_, CS_) \
-    if (g == G_ && cs == CS_) return launch_g<G_, CS_>(n, Hp, nk, D, E, st)
-    TBK_CASE(8, 1);
-    TBK_CASE(16, 1);
-    TBK_CASE(32, 1);
-    TBK_CASE(64, 1);
-    TBK_CASE(64, 2);
-    TBK_CASE(128, 1);
-    TBK_CASE(128, 2);
-    TBK_CASE(128, 4);
-    TBK_CASE(256, 1);
-    TBK_CASE(256, 2);
-    TBK_CASE(256, 4);
-    TBK_CASE(256, 8);
-    TBK_CASE(512, 4);
-    TBK_CASE(512, 8);
+    if (gg == G_ && cc == CS_) err = launch_g<G_, CS_>(cur, Hp, nk, D, E, st, ms, n, done, nsteps)
+        TBK_CASE(8, 1);
+        TBK_CASE(16, 1);
+        TBK_CASE(32, 1);
+        TBK_CASE(64, 1);
+        TBK_CASE(64, 2);
+        TBK_CASE(128, 1);
+        TBK_CASE(128, 2);
+        TBK_CASE(128, 4);
+        TBK_CASE(256, 1);
+        TBK_CASE(256, 2);
+        TBK_CASE(256, 4);
+        TBK_CASE(256, 8);
+        TBK_CASE(512, 4);
+        TBK_CASE(512, 8);
 #undef TBK_CASE
-    return cudaErrorInvalidValue;
+        if (err != cudaSuccess || !next) return err;
+        done += cur - next;
+        cur = next;
+    }
 }
 
 }  // namespace tbk

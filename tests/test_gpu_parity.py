@@ -427,6 +427,20 @@ def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads} LPR={lpr}")
 
 
+@pytest.mark.parametrize("ratio", ["0", "50", "80"])
+def test_staged_tridiag_ratios(tbk, monkeypatch, ratio):
+    """Staged shared-memory reduction (trailing block relaunched at a smaller size): every stage boundary the default
+    and two other ratios produce, against the oracle; "0" is the single-launch kernel."""
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_STAGES", ratio)
+    for n_orb in (25, 36, 47, 49, 64, 97, 119):
+        p = wl.synthetic(n_orb, 3, seed=500 + n_orb)
+        k = np.random.default_rng(n_orb).uniform(-1, 1, size=(11, 3))
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"staged N={n_orb} ratio={ratio}")
+
+
 @pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
 def test_unblocked_large_kernels_still_agree(tbk, monkeypatch, n_orb):
     """The shared-memory / row-sweep kernels the blocked one replaced stay reachable (sizes 601..640, tuning hook)."""
