@@ -238,14 +238,16 @@ def measured_hbm_peak():
 # DRAM bytes per k-point of the dominant kernels, from the ncu --set full captures summarised in
 # profiles/r01g_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its k-points).
 NCU_TRAFFIC_PER_K = {
-    ("c2", "hk_small"): (320.026880e6 + 278.184448e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
-    ("c3", "hk_gemm"): (77.287680e6 + 133.717504e6) / 17408.0,   # hk_gemm_kernel<9>, 17408 k-points per launch
-    ("c3", "tridiag"): (181.105152e6 + 9.167360e6) / 17408.0,    # tridiag_smem_kernel<32,1>
-    ("c5", "hk_gemm"): (7.699046e9 + 0.530098e9) / 4096.0,       # hk_gemm_kernel<8>
-    ("c5", "tridiag"): (0.594571e9 + 1.301204e9) / 4096.0,       # tridiag_panel_kernel<256,...> (matrices stay in L2)
-    ("c4", "tridiag"): (104.783182e9 + 11.816581e9) / 296.0,     # tridiag_panel_kernel<512,16,...>
+    ("c2", "hk_small"): (320.026624e6 + 276.478720e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
+    ("c3", "hk_gemm"): (0.472420e9 + 1.127511e9) / 113664.0,     # hk_gemm_kernel<9>, 113664 k-points per launch
+    # staged tridiag_smem_kernel<32,1>: stage 36 -> 24 (1.179 + 0.509 GB) + stage 24 -> 16 (0.524 + 0.209 GB) captured;
+    # the last stage (16 x 16 blocks, ~2.3 KB per matrix) estimated from its algorithmic bytes
+    ("c3", "tridiag"): (1.179486e9 + 0.509268e9 + 0.523830e9 + 0.208934e9) / 113664.0 + 2.3e3,
+    ("c5", "hk_gemm"): (7.805435e9 + 0.530372e9) / 4096.0,       # hk_gemm_kernel<8>
+    ("c5", "tridiag"): (0.867716e9 + 1.796464e9) / 4096.0,       # tridiag_panel_kernel<256,8,4,16> (matrices stay in L2)
+    ("c4", "tridiag"): (104.782606e9 + 11.810924e9) / 296.0,     # tridiag_panel_kernel<512,16,1,32>
 }
-NCU_TRAFFIC_SOURCE = "profiles/r01h_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
+NCU_TRAFFIC_SOURCE = "profiles/r01j_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
 
 
 def flops_per_k(packed):
@@ -371,7 +373,8 @@ def run_gpu_arm(args) -> None:
     if dom == "hk_small" or dom == "expand":
         achieved = fl["bytes"] * k_per_launch / per_launch_s / 1e9
         roofline = {
-            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "kernel": "hk_basis (profile class hk_small)" if ev.path == "fused-product" else dom,
+            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
             "algorithmic_bytes_per_kpoint": fl["bytes"],
             "note": "fp64 sincospi/FMA work per k-point is co-limiting; see DESIGN.md",

@@ -58,7 +58,8 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
 int tbk_kdotp_create(int dim, int n_orb, int n_terms, const int32_t* powers, const double* coeff, int device,
                      tbk_model** out);
 int tbk_model_destroy(tbk_model* m);
-/* path: 0 = fused thread-per-k kernel (N <= 8), 1 = DMMA GEMM + batched tridiagonal/QL eigensolver. */
+/* path: 0 = fused thread-per-k kernel (N <= 8), 1 = DMMA GEMM + batched tridiagonal/QL eigensolver,
+ *       2 = fused trigonometric-product kernel (N <= 2, dim <= 3, nearest-cell lattice vectors). */
 int tbk_model_info(const tbk_model* m, int* n_orb, int* dim, int* n_R, int* path);
 
 /* Model.hamilton for a batch (replaces _tb_model.py:1109-1128).

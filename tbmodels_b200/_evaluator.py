@@ -130,7 +130,7 @@ class Evaluator:
     def path(self) -> str:
         p = C.c_int()
         _capi.check(self._lib.tbk_model_info(self._handle, None, None, None, C.byref(p)))
-        return "fused-small" if p.value == 0 else "gemm+tridiag-ql"
+        return {0: "fused-small", 1: "gemm+tridiag-ql", 2: "fused-product"}[p.value]
 
     @property
     def launch_count(self) -> int:

@@ -654,7 +654,7 @@ int tbk_model_info(const tbk_model* m, int* n_orb, int* dim, int* n_R, int* path
     if (n_orb) *n_orb = m->md.n;
     if (dim) *dim = m->md.dim;
     if (n_R) *n_R = m->md.nR;
-    if (path) *path = m->md.small_ok ? 0 : 1;
+    if (path) *path = m->md.small_ok ? (m->md.basis_ok ? 2 : 0) : 1;
     return TBK_OK;
 }
 
