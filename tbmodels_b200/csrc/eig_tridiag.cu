@@ -66,7 +66,6 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* red, in
 __global__ void __launch_bounds__(TPB)
 tridiag_global_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
     constexpr int G = TPB;
-    constexpr int NW = G / 32;
     extern __shared__ __align__(16) double sm[];
     const int t = threadIdx.x;
     const long NN = (long)N * N;

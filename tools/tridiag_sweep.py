@@ -1,7 +1,8 @@
 """Eigensolver timing sweep over N with the dispatch overridden through the tuning environment variables.
 
     python tools/tridiag_sweep.py N:nk ...      (GPU box)
-Prints ms per 1000 matrices for: default dispatch, blocked kernel with 128 / 256 / 512 threads per matrix.
+Prints ms per 1000 matrices for: default dispatch, the unblocked single-launch kernels, the blocked kernel with
+128 / 256 / 512 threads per matrix.
 """
 import os
 import sys
@@ -15,7 +16,7 @@ from tbmodels_b200 import workloads as wl
 
 VARIANTS = {
     "default": {},
-    "smem/old": {"TBK_TRIDIAG_NOPANEL": "1", "TBK_TRIDIAG_PANEL_MIN": "100000"},
+    "smem/old": {"TBK_TRIDIAG_NOPANEL": "1", "TBK_TRIDIAG_PANEL_MIN": "100000", "TBK_TRIDIAG_STAGES": "0"},
     "panel128": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "128"},
     "panel256": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "256"},
     "panel512": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "512"},
