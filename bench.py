@@ -490,7 +490,20 @@ def run_gpu_arm(args) -> None:
                 "peak_source": "tbk_measure_fp64_peak (DMMA register loop, this GPU, this run)",
             },
         }
-        launches_extra = l3
+        # the same model on its k-grid (this rank's 8 planes of a 256 x 256-per-plane mesh) through the mesh entry point
+        dims3 = (world * 8, 256, 256)
+        lines3 = 8 * 256
+        step3 = lambda: ev3.eigenval_mesh_device(dims3, first_line=rank * lines3, n_lines=lines3, out=o3)  # noqa: E731
+        ms3m, l3m, prof3m = time_device_steps(ev3, k3, o3, 3, 3, dist, None, step3)
+        extra["c3_kgrid"] = {
+            "workload": f"c3 model on a {dims3} k-grid via eigenval_mesh (factorised over the last dimension), "
+                        f"{nk3} k-points per GPU per step",
+            "value": world * nk3 * 3 / (ms3m * 1e-3),
+            "unit": UNIT,
+            "ms_per_step": ms3m / 3,
+            "kernel_ms": {c: v[0] / 3 for c, v in prof3m.items() if v[1]},
+        }
+        launches_extra = l3 + l3m
         ev3.close()
     sampler.mark("run_end")
     clocks = sampler.stop()
