@@ -613,3 +613,43 @@ def test_eigenval_mesh_argument_errors(tbk):
             ev.eigenval_mesh_device((4, 4, 4), first_line=10, n_lines=10)
     finally:
         ev.close()
+
+
+@pytest.mark.parametrize("n_orb", [36, 64, 130, 200])
+def test_degenerate_matrix_structures(tbk, n_orb):
+    """Structures that make reflectors trivial or the spectrum highly degenerate, through every tridiagonalisation
+    regime (staged shared-memory kernels, blocked kernel): diagonal H, decoupled blocks, rank-one hopping, zero model."""
+    from tbmodels_b200 import pack_arrays
+
+    orc = _oracle()
+    rng = np.random.default_rng(n_orb)
+    k = rng.uniform(-1, 1, size=(5, 3))
+    pos = rng.random((n_orb, 3))
+    R = np.array([[0, 0, 0], [1, 0, 0], [0, 1, -1]], dtype=np.int32)
+
+    def model(h0, h1, h2):
+        return pack_arrays(R, np.stack([0.5 * h0, h1, h2]), pos)
+
+    z = np.zeros((n_orb, n_orb), dtype=complex)
+    diag = np.diag(rng.normal(size=n_orb)).astype(complex)
+    blocks = z.copy()
+    h = n_orb // 2
+    a = rng.normal(size=(h, h)) + 1j * rng.normal(size=(h, h))
+    blocks[:h, :h] = a + a.conj().T
+    blocks[h:, h:] = np.diag(np.full(n_orb - h, 2.0))
+    u = rng.normal(size=n_orb) + 1j * rng.normal(size=n_orb)
+    rank1 = np.outer(u, u.conj())
+    hop_blocks = z.copy()
+    hop_blocks[:h, :h] = rng.normal(size=(h, h)) * 0.1
+    cases = {
+        "diagonal": model(diag, z, z),
+        "diagonal + diagonal hopping": model(diag, np.diag(rng.normal(size=n_orb)).astype(complex), z),
+        "decoupled blocks": model(blocks, hop_blocks, z),
+        "rank one": model(rank1, 0.3 * rank1, z),
+        "identity": model(np.eye(n_orb, dtype=complex), z, z),
+    }
+    for name, p in cases.items():
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"{name} N={n_orb}")
+    empty = pack_arrays(np.zeros((0, 3), dtype=np.int32), np.zeros((0, n_orb, n_orb), dtype=complex), pos)
+    got = tbk.Evaluator(empty).eigenval_array(k)
+    assert got.shape == (5, n_orb) and not got.any()
