@@ -99,6 +99,20 @@ bisect_kernel(double* __restrict__ D, const double* __restrict__ E, int N, long 
         hi = fmax(hi, red[1][w]);
         emax = fmax(emax, red[2][w]);
     }
+    if (emax == 0.0) {
+        // already diagonal (e.g. the empty model: the reference returns exact zeros): the eigenvalues are the diagonal
+        // entries, sorted by rank -- exact, where bisection would return values within pivmin of them
+        for (int i = tid; i < N; i += TPB_BISECT) {
+            const double di = ds[i];
+            int rank = 0;
+            for (int q = 0; q < N; ++q) {
+                const double dq = ds[q];
+                rank += (dq < di || (dq == di && q < i)) ? 1 : 0;
+            }
+            D[kk * N + rank] = di;
+        }
+        return;
+    }
     const double pivmin = DBL_MIN * fmax(1.0, emax);
     const double span = fmax(fabs(lo), fabs(hi));
     const double gl = lo - 2.0 * DBL_EPSILON * span * N - 2.0 * pivmin;
