@@ -436,20 +436,37 @@ class _Writer:
         heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, heap_data))
         cap = 2 * self.LEAF_K
         chunks = [names[i:i + cap] for i in range(0, len(names), cap)] or [[]]
-        if len(chunks) > 2 * self.INTERNAL_K:
-            raise H5Error("too many links in one group for the single-level B-tree this writer emits")
-        children = []
+        children = []  # (address, heap offset of the largest name below it)
         for ch in chunks:
             snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(ch))
             for n in ch:
                 snod += struct.pack("<QQII16x", offs[n], entries[n], 0, 0)
             snod += b"\0" * (40 * (cap - len(ch)))
             children.append((self.alloc(snod), offs[ch[-1]] if ch else 0))
-        tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(children), _UNDEF, _UNDEF) + struct.pack("<Q", 0)
-        for addr, last_key in children:
-            tree += struct.pack("<QQ", addr, last_key)
-        tree += b"\0" * (16 * (2 * self.INTERNAL_K - len(children)))
-        tree_addr = self.alloc(tree)
+        # v1 B-tree over the symbol nodes: as many levels as needed, 2 K children per node, siblings linked
+        fan = 2 * self.INTERNAL_K
+        level = 0
+        while True:
+            nodes = []
+            prev_key = 0   # key 0 of the leftmost node: the empty string at heap offset 0
+            prev_addr = None
+            for i in range(0, len(children), fan):
+                grp = children[i:i + fan]
+                tree = b"TREE" + struct.pack("<BBHQQ", 0, level, len(grp), prev_addr if prev_addr is not None else _UNDEF,
+                                             _UNDEF) + struct.pack("<Q", prev_key)
+                for addr, last_key in grp:
+                    tree += struct.pack("<QQ", addr, last_key)
+                tree += b"\0" * (16 * (fan - len(grp)))
+                addr = self.alloc(tree)
+                if prev_addr is not None:
+                    struct.pack_into("<Q", self.buf, prev_addr + 16, addr)  # right sibling of the previous node
+                prev_addr, prev_key = addr, grp[-1][1]
+                nodes.append((addr, prev_key))
+            if len(nodes) == 1:
+                tree_addr = nodes[0][0]
+                break
+            children = nodes
+            level += 1
         header = self._object_header([(0x0011, struct.pack("<QQ", tree_addr, heap_addr))])
         return header, tree_addr, heap_addr
 

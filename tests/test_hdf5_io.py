@@ -203,3 +203,31 @@ def test_reader_agrees_with_committed_regression_goldens():
     for k in keys[:16]:
         for x in np.asarray(d[k]).ravel():
             assert np.any(flat == x), k
+
+
+@pytest.mark.parametrize("n_links", [0, 8, 9, 256, 257, 1001, 8200])
+def test_writer_large_groups_use_multi_level_btrees(tmp_path, n_links):
+    """Groups beyond one B-tree node (256 links) -- e.g. the hop group of the C5 model, 1001 entries -- get the two- /
+    three-level v1 B-trees h5py writes (separator keys = first key of the child, siblings linked)."""
+    tree = {"hop": {str(i): {"R": np.array([i, 0, -i])} for i in range(n_links)}, "size": np.int64(3)}
+    path = str(tmp_path / "big.hdf5")
+    _h5lite.save(tree, path)
+    back = _h5lite.load(path)
+    assert set(back["hop"]) == set(tree["hop"])
+    assert all(np.array_equal(back["hop"][k]["R"], tree["hop"][k]["R"]) for k in tree["hop"])
+    data = open(path, "rb").read()
+    r = _h5lite._Reader(data)
+    hop = r.links(r.messages(r.root_header))["hop"]
+    bt = next(struct.unpack_from("<Q", data, b)[0] for t, b, _ in r.messages(hop) if t == 0x0011)
+    level, used = struct.unpack_from("<BH", data, bt + 5)
+    want_level = 0 if n_links <= 256 else (1 if n_links <= 8192 else 2)
+    assert level == want_level and used <= 32
+    if level > 0:  # children: key 0 of child i equals the parent's key i, siblings chained left to right
+        prev = None
+        for i in range(used):
+            key, child = struct.unpack_from("<QQ", data, bt + 24 + 16 * i)
+            left, right = struct.unpack_from("<QQ", data, child + 8)
+            assert struct.unpack_from("<Q", data, child + 24)[0] == key
+            assert left == (prev if prev is not None else 0xFFFFFFFFFFFFFFFF)
+            prev = child
+        assert right == 0xFFFFFFFFFFFFFFFF
