@@ -231,3 +231,41 @@ def test_writer_large_groups_use_multi_level_btrees(tmp_path, n_links):
             assert left == (prev if prev is not None else 0xFFFFFFFFFFFFFFFF)
             prev = child
         assert right == 0xFFFFFFFFFFFFFFFF
+
+
+def test_loader_reads_csr_hoppings(tmp_path):
+    """`sparse=True` files (reference to_hdf5 :1052-1056: data / indices / indptr / shape per R) load to the same packed
+    model as the dense form."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(3)
+    mats = {(0, 0): None, (1, 0): None, (0, 1): None, (1, -1): None}
+    dense = {}
+    for R in mats:
+        m = (rng.random((5, 5)) < 0.3) * (rng.normal(size=(5, 5)) + 1j * rng.normal(size=(5, 5)))
+        if R == (0, 0):
+            m = 0.25 * (m + m.conj().T)
+        dense[R] = m
+    pos = rng.random((5, 2))
+
+    def tree(sparse):
+        hop = {}
+        for i, (R, m) in enumerate(dense.items()):
+            g = {"R": np.array(R)}
+            if sparse:
+                c = sp.csr_matrix(m)
+                g.update(data=c.data, indices=c.indices.astype(np.int64), indptr=c.indptr.astype(np.int64),
+                         shape=np.array(c.shape))
+            else:
+                g["mat"] = m
+            hop[str(i)] = g
+        return {"type_tag": io.MODEL_TAG, "size": np.int64(5), "dim": np.int64(2), "pos": pos,
+                "sparse": np.bool_(sparse), "hop": hop, "occ": np.int64(2)}
+
+    pa, pb = str(tmp_path / "dense.hdf5"), str(tmp_path / "csr.hdf5")
+    _h5lite.save(tree(False), pa)
+    _h5lite.save(tree(True), pb)
+    a, (b, meta) = io.load_model(pa), io.load_model(pb, with_meta=True)
+    assert meta["sparse"] is True and meta["occ"] == 2
+    assert np.array_equal(a.R, b.R) and np.array_equal(a.hop, b.hop) and np.array_equal(a.pos, b.pos)
+    assert {tuple(r) for r in a.R} == set(dense)
