@@ -653,3 +653,34 @@ def test_degenerate_matrix_structures(tbk, n_orb):
     empty = pack_arrays(np.zeros((0, 3), dtype=np.int32), np.zeros((0, n_orb, n_orb), dtype=complex), pos)
     got = tbk.Evaluator(empty).eigenval_array(k)
     assert got.shape == (5, n_orb) and not got.any()
+
+
+def test_eigenval_mesh_edge_shapes(tbk):
+    """Mesh entry point corner cases: unit dimensions, a single class of lattice vectors (planar model in 3-D), the empty
+    model, line lengths around the 64-point step of the line kernel, large and negative shifts."""
+    from tbmodels_b200 import pack_arrays
+    from tbmodels_b200 import workloads as wl
+
+    orc = _oracle()
+    rng = np.random.default_rng(77)
+    p = wl.synthetic(17, 25, seed=31)
+    planar = pack_arrays(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, -1, 0]]),
+                         np.stack([0.5 * np.eye(9), *(rng.normal(size=(3, 9, 9)) + 1j * rng.normal(size=(3, 9, 9)))]),
+                         rng.random((9, 3)))
+    empty = pack_arrays(np.zeros((0, 3), dtype=np.int32), np.zeros((0, 11, 11), dtype=complex), rng.random((11, 3)))
+    for model, dims, shift in (
+        (p, (1, 1, 40), None),
+        (p, (1, 3, 64), None),
+        (p, (2, 1, 65), (0.0, 0.0, 0.5)),
+        (p, (1, 2, 1000), (-3.25, 17.5, 1e3)),
+        (planar, (3, 4, 16), None),
+        (empty, (2, 2, 8), None),
+    ):
+        k = wl.kgrid_points(dims, shift)
+        want = orc.eigenval_array(model.R, model.hop, model.pos, k)
+        ev = tbk.Evaluator(model)
+        try:
+            got = ev.eigenval_mesh(dims, shift)
+        finally:
+            ev.close()
+        assert_eig_close(got, want, f"mesh {dims} shift {shift} N={model.size}")
