@@ -222,20 +222,26 @@ tridiag_smem_kernel(double* __restrict__ Hp, int N, long mstride, long nk, doubl
 
     {   // load + interleave.  The real plane has the same packed order as the complex rows (flat copy); an imag
         // plane entry f = trs(i) + j lands at f + i.  Flat loops keep many independent loads in flight.
+        // asynchronous 8-byte copies (cp.async, SASS LDGSTS): every element of the matrix is in flight at once, no
+        // register staging -- the CTAs of a wave all start in this phase, so it is otherwise pure load latency
         const double* src = Hp + kk * NN;
         const double* srci = src + ntri;
         double* Ad = reinterpret_cast<double*>(A);
+        const unsigned sA = (unsigned)__cvta_generic_to_shared(Ad);
 #pragma unroll 4
-        for (int e = t; e < ntri; e += G) Ad[2 * e] = src[e];
+        for (int e = t; e < ntri; e += G)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sA + 16u * e), "l"(src + e) : "memory");
         const int nim = ntri - N;
 #pragma unroll 4
         for (int f = t; f < nim; f += G) {
             int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)f)) * 0.5f);  // row of strict-lower entry f (approx.)
             while ((i * (i - 1)) / 2 > f) --i;
             while ((i * (i + 1)) / 2 <= f) ++i;
-            Ad[2 * (f + i) + 1] = srci[f];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sA + 16u * (f + i) + 8u), "l"(srci + f)
+                         : "memory");
         }
         for (int i = t; i < N; i += G) Ad[2 * (itri(i) + i) + 1] = 0.0;
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     group_sync<G>(group);
 
