@@ -314,11 +314,14 @@ class _Reader:
             arr = arr.astype(arr.dtype.newbyteorder("="), copy=True)
         return arr[()] if shape == () else arr
 
-    def node(self, addr: int) -> Any:
+    def node(self, addr: int, _seen=None) -> Any:
+        seen = set() if _seen is None else _seen
+        if addr in seen or addr + self.base + 16 > len(self.b):
+            raise H5Error("corrupt file: object header address outside the file or visited twice on one path")
         msgs = self.messages(addr)
         links = self.links(msgs)
         if links is not None:
-            return {name: self.node(a) for name, a in links.items()}
+            return {name: self.node(a, seen | {addr}) for name, a in links.items()}
         return self.dataset(msgs)
 
 
@@ -327,7 +330,12 @@ def load(path: str) -> Dict[str, Any]:
     with open(path, "rb") as f:
         data = f.read()
     r = _Reader(data)
-    tree = r.node(r.root_header)
+    try:
+        tree = r.node(r.root_header)
+    except H5Error:
+        raise
+    except (struct.error, IndexError, RecursionError, ValueError, UnicodeDecodeError) as exc:  # truncated / corrupt
+        raise H5Error(f"'{path}': corrupt or truncated HDF5 structures ({exc})") from exc
     if not isinstance(tree, dict):
         raise H5Error("root object is not a group")
     return tree

@@ -269,3 +269,23 @@ def test_loader_reads_csr_hoppings(tmp_path):
     assert meta["sparse"] is True and meta["occ"] == 2
     assert np.array_equal(a.R, b.R) and np.array_equal(a.hop, b.hop) and np.array_equal(a.pos, b.pos)
     assert {tuple(r) for r in a.R} == set(dense)
+
+
+def test_truncated_and_corrupt_files_raise_h5error(tmp_path):
+    data = open(os.path.join(CLI, "kpoints.hdf5"), "rb").read()
+    for cut in (100, 700, 2100, len(data) - 3000):
+        f = tmp_path / f"cut{cut}.hdf5"
+        f.write_bytes(data[:cut])
+        with pytest.raises(_h5lite.H5Error):
+            _h5lite.load(str(f))
+    # a group whose only link points back at the root object header
+    r = _h5lite._Reader(data)
+    links = r.links(r.messages(r.root_header))
+    bad = bytearray(data)
+    snod = data.index(b"SNOD")
+    struct.pack_into("<Q", bad, snod + 8 + 8, r.root_header)  # first entry's object header address -> root
+    f = tmp_path / "cycle.hdf5"
+    f.write_bytes(bytes(bad))
+    with pytest.raises(_h5lite.H5Error):
+        _h5lite.load(str(f))
+    assert links  # (the untouched file still parses)
