@@ -238,16 +238,16 @@ def measured_hbm_peak():
 # DRAM bytes per k-point of the dominant kernels, from the ncu --set full captures summarised in
 # profiles/r01g_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its k-points).
 NCU_TRAFFIC_PER_K = {
-    ("c2", "hk_small"): (320.026624e6 + 276.478720e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
-    ("c3", "hk_gemm"): (0.472420e9 + 1.127511e9) / 113664.0,     # hk_gemm_kernel<9>, 113664 k-points per launch
+    ("c2", "hk_small"): (320.024576e6 + 275.497984e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
+    ("c3", "hk_gemm"): (0.472531e9 + 1.130096e9) / 113664.0,     # hk_gemm_kernel<9>, 113664 k-points per launch
     # staged tridiag_smem_kernel<32,1>: stage 36 -> 24 (1.179 + 0.509 GB) + stage 24 -> 16 (0.524 + 0.209 GB) captured;
     # the last stage (16 x 16 blocks, ~2.3 KB per matrix) estimated from its algorithmic bytes
-    ("c3", "tridiag"): (1.179486e9 + 0.509268e9 + 0.523830e9 + 0.208934e9) / 113664.0 + 2.3e3,
+    ("c3", "tridiag"): (1.178607e9 + 0.506849e9 + 0.523854e9 + 0.208934e9) / 113664.0 + 2.3e3,
     ("c5", "hk_gemm"): (7.805435e9 + 0.530372e9) / 4096.0,       # hk_gemm_kernel<8>
-    ("c5", "tridiag"): (0.867716e9 + 1.796464e9) / 4096.0,       # tridiag_panel_kernel<256,8,4,16> (matrices stay in L2)
-    ("c4", "tridiag"): (104.782606e9 + 11.810924e9) / 296.0,     # tridiag_panel_kernel<512,16,1,32>
+    ("c5", "tridiag"): (0.834399e9 + 1.809944e9) / 4096.0,       # tridiag_panel_kernel<256,8,4,16> (matrices stay in L2)
+    ("c4", "tridiag"): (104.832851e9 + 11.813608e9) / 296.0,     # tridiag_panel_kernel<512,16,1,32>
 }
-NCU_TRAFFIC_SOURCE = "profiles/r01j_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
+NCU_TRAFFIC_SOURCE = "profiles/r01l_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
 
 
 def flops_per_k(packed):
