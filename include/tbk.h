@@ -94,7 +94,7 @@ int tbk_model_check(tbk_model* m);
 int64_t tbk_launch_count(const tbk_model* m);
 /* Per-kernel-class device timing with CUDA events recorded on the launching stream.
  * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand, 3 tridiagonalisation, 4 tridiagonal QL,
- * 5 phase tiles for the GEMM.
+ * 5 phase tiles for the GEMM (and the small mesh helper kernels), 6 line expansion of the regular-mesh path.
  * tbk_profile(m, 1) starts recording; tbk_profile_read synchronises, returns the accumulated milliseconds
  * and launch counts per class since the last read (arrays of TBK_PROFILE_CLASSES) and resets them. */
 #define TBK_PROFILE_CLASSES 7
