@@ -183,3 +183,20 @@ def test_mesh_factorisation_algebra_matches_the_fourier_sum():
         got = orc.hamilton_mesh_factorised(p.R, p.hop, p.pos, dims, shift)
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 1e-12 * np.abs(p.hop).max() * p.n_R
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 16, 17, 40, 129])
+def test_blocked_and_staged_reductions_match_lapack(n):
+    """The numpy restatements of the device tridiagonalisation schedules (blocked panels for N >= 120, staged relaunch on
+    the trailing block below) give LAPACK's spectrum -- incl. sizes that are not multiples of the panel width."""
+    import scipy.linalg as la
+
+    from oracle import blocked_hetrd as bh
+
+    rng = np.random.default_rng(n)
+    M = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    H = M + M.conj().T
+    ref = la.eigvalsh(H)
+    for d, e in (bh.blocked_tridiagonalise(H, nb=8), bh.blocked_tridiagonalise(H, nb=3), bh.staged_tridiagonalise(H)):
+        got = la.eigvalsh_tridiagonal(d, e) if n > 1 else d
+        assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
