@@ -224,24 +224,20 @@ __device__ __forceinline__ void sincospi_x(double t, double& s, double& c) {
     const double r = fma(n, -0.5, t);
     const unsigned q = (unsigned)(long long)n;  // low bits of the (exact) integer n
     const double r2 = r * r;
-    double ps = 7.952054001475508e-07;
-    ps = fma(ps, r2, -2.1915353447830204e-05);
-    ps = fma(ps, r2, 0.00046630280576761234);
-    ps = fma(ps, r2, -0.007370430945714348);
-    ps = fma(ps, r2, 0.08214588661112819);
-    ps = fma(ps, r2, -0.5992645293207919);
-    ps = fma(ps, r2, 2.550164039877345);
+    double ps = 0.00046221129498806536;
+    ps = fma(ps, r2, -0.0073701436737117);
+    ps = fma(ps, r2, 0.08214587730806341);
+    ps = fma(ps, r2, -0.5992645291845754);
+    ps = fma(ps, r2, 2.550164039876616);
     ps = fma(ps, r2, -5.167712780049969);
     double sv = fma(r * r2, ps, r * 1.2246467991473532e-16);  // pi = 3.141592653589793 + 1.2246467991473532e-16
     sv = fma(r, 3.141592653589793, sv);
-    double pc = -1.387895246221376e-07;
-    pc = fma(pc, r2, 4.303069587032944e-06);
-    pc = fma(pc, r2, -0.00010463810492484565);
-    pc = fma(pc, r2, 0.001929574309403922);
-    pc = fma(pc, r2, -0.02580689139001405);
-    pc = fma(pc, r2, 0.23533063035889312);
-    pc = fma(pc, r2, -1.3352627688545893);
-    pc = fma(pc, r2, 4.058712126416768);
+    double pc = -0.00010370086335346046;
+    pc = fma(pc, r2, 0.0019294938812021883);
+    pc = fma(pc, r2, -0.025806887965145374);
+    pc = fma(pc, r2, 0.2353306302840066);
+    pc = fma(pc, r2, -1.3352627688538097);
+    pc = fma(pc, r2, 4.058712126416765);
     pc = fma(pc, r2, -4.934802200544679);
     const double cv = fma(pc, r2, 1.0);
     // q mod 4:  0 -> (s, c),  1 -> (c, -s),  2 -> (-s, -c),  3 -> (-c, s)

@@ -200,3 +200,37 @@ def test_kdotp_mirror_rejects_non_hermitian_and_packs_in_dict_order():
     powers, coeff = tbk.pack_kdotp(m.taylor_coefficients)
     assert powers.tolist() == [[0, 0], [1, 0], [0, 2]] and coeff.shape == (3, 2, 2)
     assert pickle.loads(pickle.dumps(m))._cache is None
+
+
+def test_sincospi_lean_accuracy_in_ulps():
+    """The device phase function (tbk_math.cuh sincospi_lean, compiled for the host): <= 1.5 ulp against an 80-bit
+    reference after the exact argument reduction, exact at multiples of 1/2, large arguments keep their quadrant."""
+    import ctypes as C
+
+    lib = _lib()
+    ld = np.longdouble
+    if np.finfo(ld).nmant < 63:
+        pytest.skip("no extended-precision long double on this platform")
+    pi = ld("3.14159265358979323846264338327950288")
+
+    def sc(t):
+        s, c = C.c_double(), C.c_double()
+        assert lib.tbk_host_sincospi(float(t), C.byref(s), C.byref(c)) == 0
+        return s.value, c.value
+
+    rng = np.random.default_rng(0)
+    ts = np.concatenate([rng.uniform(-4, 4, 20000), rng.uniform(-1e6, 1e6, 4000), np.linspace(-0.25, 0.25, 2001),
+                         np.linspace(0.24, 0.26, 1001)])
+    worst = 0.0
+    for t in ts:
+        s, c = sc(t)
+        n = np.rint(2 * t)
+        r = ld(t) - ld(n) / 2
+        sv, cv = np.sin(pi * r), np.cos(pi * r)
+        rs, rc = [(sv, cv), (cv, -sv), (-sv, -cv), (-cv, sv)][int(n) % 4]
+        for got, ref in ((s, rs), (c, rc)):
+            if ref != 0:
+                worst = max(worst, float(abs(ld(got) - ref) / np.spacing(abs(np.float64(ref)))))
+    assert worst <= 1.5, worst
+    assert sc(0.5) == (1.0, 0.0) and sc(1.0)[1] == -1.0 and sc(-0.5)[0] == -1.0 and sc(0.0) == (0.0, 1.0)
+    assert sc(2.0 ** 40 + 0.5) == (1.0, 0.0) and abs(sc(0.25)[0] - np.sqrt(0.5)) < 2e-16
