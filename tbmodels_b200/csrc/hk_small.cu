@@ -248,16 +248,14 @@ __device__ __forceinline__ void sincospi_x(double t, double& s, double& c) {
     c = __hiloint2double(__double2hiint(b) ^ (int)((qs + 0x40000000u) & 0x80000000u), __double2loint(b));
 }
 
-// sqrt(x) for finite x >= 0: hardware reciprocal-square-root seed, two coupled Newton steps and a final residual
-// correction (<= 1 ulp for normal x); x below 1e-290 (exact band degeneracy) returns 0.
+// sqrt(x) for finite x >= 0: hardware reciprocal-square-root seed (~2^-22), one coupled Newton step for g ~ sqrt(x) and
+// h ~ 1 / (2 sqrt(x)) (~2^-44) and a residual correction g += (x - g^2) h (quadratic again: rounding-level error); x below
+// 1e-290 (exact band degeneracy) returns 0.
 __device__ __forceinline__ double sqrt_nonneg(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double g = x * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
+    const double r = fma(-g, h, 0.5);
     g = fma(g, r, g);
     h = fma(h, r, h);
     const double d = fma(-g, g, x);
@@ -303,17 +301,25 @@ __device__ __forceinline__ void basis_kpoints(const double (&kv)[KP][D], const d
 template <int N>
 __device__ __forceinline__ void basis_store(const double (&acc)[N * N], long idx, double* __restrict__ Hp,
                                             double* __restrict__ eig) {
+    // N = 2: the table was rotated on the host so that acc = (mean, Re h10, delta, Im h10) with mean = (h00 + h11) / 2,
+    // delta = (h00 - h11) / 2 -- the closed form (tbk_math.cuh eig2_closed) needs exactly these
     constexpr int NN = N * N;
     if (Hp != nullptr) {
+        if (N == 2) {
+            Hp[idx * NN] = acc[0] + acc[2 % NN];
+            Hp[idx * NN + 1] = acc[1 % NN];
+            Hp[idx * NN + 2] = acc[0] - acc[2 % NN];
+            Hp[idx * NN + 3] = acc[3 % NN];
+        } else {
 #pragma unroll
-        for (int e = 0; e < NN; ++e) Hp[idx * NN + e] = acc[e];
+            for (int e = 0; e < NN; ++e) Hp[idx * NN + e] = acc[e];
+        }
     }
     if (eig != nullptr) {
         if (N == 1) {
             eig[idx] = acc[0];
-        } else {  // closed form (tbk_math.cuh eig2_closed) with the lean square root
-            const double mean = 0.5 * (acc[0] + acc[2 % NN]);
-            const double delta = 0.5 * (acc[0] - acc[2 % NN]);
+        } else {
+            const double mean = acc[0], delta = acc[2 % NN];
             const double rad = sqrt_nonneg(fma(delta, delta, fma(acc[1 % NN], acc[1 % NN], acc[3 % NN] * acc[3 % NN])));
             *reinterpret_cast<double2*>(eig + idx * 2) = make_double2(mean - rad, mean + rad);
         }
@@ -374,6 +380,13 @@ template <int N, int D, int KP>
 cudaError_t launch_basis_ndk(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
     BasisTable<N, D> T;
     for (int i = 0; i < Pow3<D>::value * N * N; ++i) T.w[i] = md.basis[i];
+    if (N == 2) {  // accumulate (mean, delta) of the diagonal instead of (h00, h11): see basis_store
+        for (int b = 0; b < Pow3<D>::value; ++b) {
+            const double h00 = md.basis[b * 4], h11 = md.basis[b * 4 + 2];
+            T.w[b * (N * N)] = 0.5 * (h00 + h11);
+            T.w[b * (N * N) + 2 % (N * N)] = 0.5 * (h00 - h11);
+        }
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
