@@ -263,39 +263,46 @@ __device__ __forceinline__ double sqrt_nonneg(double x) {
     return (x > 1e-290) ? g : 0.0;
 }
 
+// (Guarding the FMAs of exact-zero table entries -- 24 of 32 for the Haldane model -- with uniform predicates was measured
+//  5 % slower than running them all: the kernel is issue bound as much as FP64-pipe bound.)
 template <int N, int D, int KP>
-__device__ __forceinline__ void basis_kpoints(const double (&kv)[KP][D], const double* __restrict__ w,
+__device__ __forceinline__ void basis_kpoints(const double (&kv)[KP][D], const BasisTable<N, D>& T,
                                               double (&acc)[KP][N * N]) {
     constexpr int NN = N * N;
     constexpr int NB3 = Pow3<D>::value;
+    const double* __restrict__ w = T.w;
     double phi[KP][NB3];
     int n = 1;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
+        double sd[KP], cd[KP];
 #pragma unroll
         for (int p = 0; p < KP; ++p) {
-            double sd, cd;
-            sincospi_x(2.0 * kv[p][d], sd, cd);
+            sincospi_x(2.0 * kv[p][d], sd[p], cd[p]);
             phi[p][0] = 1.0;
-            phi[p][n] = cd;
-            phi[p][2 * n] = sd;
+            phi[p][n] = cd[p];
+            phi[p][2 * n] = sd[p];
+        }
 #pragma unroll
-            for (int b = 1; b < n; ++b) {
-                phi[p][b + n] = phi[p][b] * cd;
-                phi[p][b + 2 * n] = phi[p][b] * sd;
+        for (int b = 1; b < n; ++b) {
+#pragma unroll
+            for (int p = 0; p < KP; ++p) {
+                phi[p][b + n] = phi[p][b] * cd[p];
+                phi[p][b + 2 * n] = phi[p][b] * sd[p];
             }
         }
         n *= 3;
     }
 #pragma unroll
-    for (int p = 0; p < KP; ++p) {
+    for (int p = 0; p < KP; ++p)
 #pragma unroll
         for (int e = 0; e < NN; ++e) acc[p][e] = w[e];
 #pragma unroll
-        for (int b = 1; b < NB3; ++b)
+    for (int b = 1; b < NB3; ++b)  // table entry outermost: one uniform operand feeds the KP k-points of the trip
 #pragma unroll
-            for (int e = 0; e < NN; ++e) acc[p][e] = fma(phi[p][b], w[b * NN + e], acc[p][e]);
-    }
+        for (int e = 0; e < NN; ++e)
+#pragma unroll
+            for (int p = 0; p < KP; ++p) acc[p][e] = fma(phi[p][b], w[b * NN + e], acc[p][e]);
 }
 
 template <int N>
@@ -360,7 +367,7 @@ hk_basis_kernel(const double* __restrict__ kpts, long nk, const __grid_constant_
             for (int d = 0; d < D; ++d) kv[p][d] = kn[p][d];
         if (base + step + TRIP <= nk) load_trip<D, KP>(kn, kpts + (base + step + threadIdx.x) * D);
         double acc[KP][NN];
-        basis_kpoints<N, D, KP>(kv, T.w, acc);
+        basis_kpoints<N, D, KP>(kv, T, acc);
 #pragma unroll
         for (int p = 0; p < KP; ++p) basis_store<N>(acc[p], base + threadIdx.x + (long)p * TPB, Hp, eig);
     }
@@ -370,7 +377,7 @@ hk_basis_kernel(const double* __restrict__ kpts, long nk, const __grid_constant_
 #pragma unroll
             for (int d = 0; d < D; ++d) kv[0][d] = kpts[idx * D + d];
             double acc[1][NN];
-            basis_kpoints<N, D, 1>(kv, T.w, acc);
+            basis_kpoints<N, D, 1>(kv, T, acc);
             basis_store<N>(acc[0], idx, Hp, eig);
         }
     }
