@@ -238,7 +238,7 @@ def measured_hbm_peak():
 # DRAM bytes per k-point of the dominant kernels, from the ncu --set full captures summarised in
 # profiles/r01g_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its k-points).
 NCU_TRAFFIC_PER_K = {
-    ("c2", "hk_small"): (320.024576e6 + 275.497984e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch
+    ("c2", "hk_small"): (320.040704e6 + 279.324160e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch (r01m2_ncu_hk_basis_final.txt)
     ("c3", "hk_gemm"): (0.472531e9 + 1.130096e9) / 113664.0,     # hk_gemm_kernel<9>, 113664 k-points per launch
     # staged tridiag_smem_kernel<32,1>: stage 36 -> 24 (1.179 + 0.509 GB) + stage 24 -> 16 (0.524 + 0.209 GB) captured;
     # the last stage (16 x 16 blocks, ~2.3 KB per matrix) estimated from its algorithmic bytes
