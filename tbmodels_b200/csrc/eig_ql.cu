@@ -153,8 +153,9 @@ cudaError_t launch_t(int n, double* D, double* E, long nk, int* fail_count, cuda
 
 constexpr int kBisectMinN = 129;
 
-cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave) {
-    if (n >= kBisectMinN && (size_t)2 * n * 8 <= 200 * 1024) {
+cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave, const Tuning& tune) {
+    const int bisect_min = tune.ql_bisect_min > 0 ? tune.ql_bisect_min : kBisectMinN;
+    if (n >= bisect_min && (size_t)2 * n * 8 <= 200 * 1024) {
         if (wave) {
             *wave = 0;  // one CTA per matrix: no wave quantisation to respect
             return cudaSuccess;
@@ -186,16 +187,16 @@ cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cuda
 
 }  // namespace
 
-long ql_wave_matrices(int n) {
+long ql_wave_matrices(int n, const Tuning& tune) {
     // matrices one full wave of the shared-memory QL kernel processes (0: not applicable)
     long wave = 0;
-    if (n <= 0 || dispatch(n, nullptr, nullptr, 0, nullptr, nullptr, &wave) != cudaSuccess) return 0;
+    if (n <= 0 || dispatch(n, nullptr, nullptr, 0, nullptr, nullptr, &wave, tune) != cudaSuccess) return 0;
     return wave;
 }
 
-cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st) {
+cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, const Tuning& tune) {
     if (nk <= 0 || n <= 0) return cudaSuccess;
-    return dispatch(n, D, E, nk, fail_count, st, nullptr);
+    return dispatch(n, D, E, nk, fail_count, st, nullptr, tune);
 }
 
 }  // namespace tbk

@@ -874,8 +874,8 @@ cudaError_t launch_big(int n, double* Hp, long nk, double* D, double* E, cudaStr
 constexpr size_t kSmemLimit = 220 * 1024;
 
 template <int G, int CS>
-cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride = 0, int ldo = 0,
-                     int off = 0, int nsteps = 1 << 30) {
+cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune, long mstride = 0,
+                     int ldo = 0, int off = 0, int nsteps = 1 << 30) {
     if (mstride == 0) mstride = (long)n * n;
     if (ldo == 0) ldo = n;
     constexpr int NW = G > 32 ? G / 32 : 1;
@@ -896,8 +896,8 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
                 best_mpb = mpb;
             }
         }
-        if (const char* e = getenv("TBK_TRIDIAG_MPB")) {  // tuning hook: matrices per CTA
-            const int v = atoi(e);
+        {   // tuning hook: matrices per CTA
+            const int v = tune.tridiag_mpb;
             if (v >= 1 && v <= 15 && (size_t)v * G <= 1024 && per_mat * v <= kSmemLimit) best_mpb = v;
         }
         const size_t smem = per_mat * best_mpb;
@@ -911,8 +911,8 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         return cudaGetLastError();
     }
     // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
-    if (!getenv("TBK_TRIDIAG_NOPANEL") && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st);
-    if (!getenv("TBK_TRIDIAG_OLDBIG")) {
+    if (!tune.tridiag_nopanel && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
+    if (!tune.tridiag_oldbig) {
         if (n <= 32 * 16) return launch_big<16>(n, Hp, nk, D, E, st);
         if (n <= 32 * 20) return launch_big<20>(n, Hp, nk, D, E, st);  // shared memory: (3 + 16) * 16 N bytes <= 227 KB
     }
@@ -928,26 +928,29 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
 
 }  // namespace
 
-cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    int g = 0, cs = 1;
-    if (const char* e = getenv("TBK_TRIDIAG_G")) g = atoi(e);  // tuning hooks: threads per matrix / column slices
-    if (const char* e = getenv("TBK_TRIDIAG_CS")) cs = atoi(e);
+cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
+    const int g = tune.tridiag_g, cs = tune.tridiag_cs;  // tuning hooks: threads per matrix / column slices
     if (g == 1) return launch_mma(n, Hp, nk, D, E, st);
-    if (const char* e = getenv("TBK_TRIDIAG_PANEL_MIN")) {  // tuning hook: blocked kernel from this size on
-        if (n >= atoi(e) && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st);
+    if (tune.tridiag_panel_min > 0) {  // tuning hook: blocked kernel from this size on
+        if (n >= tune.tridiag_panel_min && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
     }
     // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
     //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
     // blocked kernel (eig_tridiag_panel.cu) from N = 120 on: measured on B200, ms per 1000 matrices smem / blocked:
     // N = 100: 1.47 / 1.95, 128: 3.65 / 3.31, 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125
-    if (g == 0 && n >= 120 && !getenv("TBK_TRIDIAG_NOPANEL") && tridiag_panel_fits(n))
-        return launch_tridiag_panel(n, Hp, nk, D, E, st);
+    if (g == 0 && n >= 120 && !tune.tridiag_nopanel && tridiag_panel_fits(n))
+        return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
+    // register-resident warp-per-matrix kernel (eig_tridiag_reg.cu): the whole reduction in one launch
+    const auto use_reg = [&](int m) {
+        return g == 0 && tune.tridiag_reg_max > 0 && m >= tune.tridiag_reg_min && m <= tune.tridiag_reg_max &&
+               tridiag_reg_fits(m);
+    };
+    if (use_reg(n)) return launch_tridiag_reg(n, Hp, nk, D, E, st, 0, 0, 0);
     // Staged reduction (shared-memory kernels, 25 <= N < 120): the trailing block shrinks, so after every stage the
     // remaining (smaller) problem is relaunched with several times more matrices resident per SM -- shared memory per
     // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
     // on the batch): N -> ratio * N -> ... until <= 16.  TBK_TRIDIAG_STAGES="0" disables, "p" sets the ratio in percent.
-    int ratio = 67;
-    if (const char* e = getenv("TBK_TRIDIAG_STAGES")) ratio = atoi(e);
+    const int ratio = tune.tridiag_stages;
     const bool staged = g == 0 && n >= 25 && n < 120 && ratio > 0 && ratio < 100;
     const long ms = (long)n * n;
     int cur = n, done = 0;
@@ -957,7 +960,12 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
             next = (cur * ratio + 50) / 100;
             if (next < 12) next = 12;
             if (next >= cur) next = 0;
+            // hand over to the register kernel at its largest size instead of staging past it
+            const int rm = tune.tridiag_reg_max;
+            if (g == 0 && rm > 0 && cur > rm && next > 0 && next <= rm + rm / 5 && use_reg(rm)) next = rm;
         }
+        // a trailing block the register kernel serves is finished there (same lower-storage reduction, one launch)
+        if (cur != n && use_reg(cur)) return launch_tridiag_reg(cur, Hp, nk, D, E, st, ms, n, done);
         const int nsteps = next ? cur - next : (1 << 30);
         int gg = g, cc = cs;
         if (gg == 0) {  // defaults, from the size only
@@ -970,7 +978,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         }
         cudaError_t err = cudaErrorInvalidValue;
 #define TBK_CASE(G_, CS_) \
-    if (gg == G_ && cc == CS_) err = launch_g<G_, CS_>(cur, Hp, nk, D, E, st, ms, n, done, nsteps)
+    if (gg == G_ && cc == CS_) err = launch_g<G_, CS_>(cur, Hp, nk, D, E, st, tune, ms, n, done, nsteps)
         TBK_CASE(8, 1);
         TBK_CASE(16, 1);
         TBK_CASE(32, 1);

@@ -443,7 +443,7 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
 }
 
 template <int THREADS, int MAXC, int MINB, int LPR>
-cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
+cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
     const size_t smem = panel_smem_doubles(n, THREADS / 32, MAXC) * 8;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB, LPR>,
@@ -451,8 +451,7 @@ cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cud
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    int pfd = 1;  // measured (C4, ms per 1184 matrices): off 167, 1 trip 154, 2 trips 156, 4 trips 167, 8 trips 175
-    if (const char* e = getenv("TBK_PANEL_PFD")) pfd = atoi(e);  // tuning hook
+    int pfd = tune.panel_pfd;  // measured (C4, ms per 1184 matrices): off 167, 1 trip 154, 2 trips 156, 4 trips 167, 8 trips 175
     if (pfd < 0 || pfd > 8) pfd = 1;
     tridiag_panel_kernel<THREADS, MAXC, MINB, LPR><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd);
     return cudaGetLastError();
@@ -465,32 +464,30 @@ bool tridiag_panel_fits(int n) {  // (the 16-warp configuration has the largest 
     return n >= 2 && n <= 640 && panel_smem_doubles(n, 16, n <= 512 ? 16 : 20) * 8 <= 227 * 1024;
 }
 
-cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st) {
-    int t = 0, lpr = 0;
-    if (const char* e = getenv("TBK_PANEL_T")) t = atoi(e);      // tuning hooks: threads per matrix,
-    if (const char* e = getenv("TBK_PANEL_LPR")) lpr = atoi(e);  // lanes per row of the Hermitian product
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
+    const int t = tune.panel_t, lpr = tune.panel_lpr;  // tuning hooks: threads per matrix, lanes per row of the product
     // template arguments: threads, column chunks (n <= chunks * lanes per row), min CTAs per SM, lanes per row.
     // Measured on B200, tridiagonalisation ms per 1000 matrices:
     //   N = 128: 16 lanes/row 3.11 (256 thr, 4 CTAs/SM), 32 lanes/row 3.32, 128 thr 3.69, shared-memory kernel 3.65
     //   N = 200: 16 lanes/row 9.39, 32 lanes/row 10.47 (512 thr: 12.6);  N = 256: 17.6 / 19.2 (512 thr: 20.8)
     if (n <= 128) {
         if (lpr == 32) {
-            if (t == 128) return launch_panel_t<128, 4, 8, 32>(n, Hp, nk, D, E, st);
-            if (t == 512) return launch_panel_t<512, 4, 2, 32>(n, Hp, nk, D, E, st);
-            return launch_panel_t<256, 4, 4, 32>(n, Hp, nk, D, E, st);
+            if (t == 128) return launch_panel_t<128, 4, 8, 32>(n, Hp, nk, D, E, st, tune);
+            if (t == 512) return launch_panel_t<512, 4, 2, 32>(n, Hp, nk, D, E, st, tune);
+            return launch_panel_t<256, 4, 4, 32>(n, Hp, nk, D, E, st, tune);
         }
-        if (t == 128) return launch_panel_t<128, 8, 8, 16>(n, Hp, nk, D, E, st);
-        return launch_panel_t<256, 8, 4, 16>(n, Hp, nk, D, E, st);
+        if (t == 128) return launch_panel_t<128, 8, 8, 16>(n, Hp, nk, D, E, st, tune);
+        return launch_panel_t<256, 8, 4, 16>(n, Hp, nk, D, E, st, tune);
     }
     if (n <= 256) {
         if (lpr == 32) {
-            if (t == 512) return launch_panel_t<512, 8, 1, 32>(n, Hp, nk, D, E, st);
-            return launch_panel_t<256, 8, 2, 32>(n, Hp, nk, D, E, st);
+            if (t == 512) return launch_panel_t<512, 8, 1, 32>(n, Hp, nk, D, E, st, tune);
+            return launch_panel_t<256, 8, 2, 32>(n, Hp, nk, D, E, st, tune);
         }
-        return launch_panel_t<256, 16, 2, 16>(n, Hp, nk, D, E, st);
+        return launch_panel_t<256, 16, 2, 16>(n, Hp, nk, D, E, st, tune);
     }
-    if (n <= 512) return launch_panel_t<512, 16, 1, 32>(n, Hp, nk, D, E, st);
-    return launch_panel_t<512, 20, 1, 32>(n, Hp, nk, D, E, st);
+    if (n <= 512) return launch_panel_t<512, 16, 1, 32>(n, Hp, nk, D, E, st, tune);
+    return launch_panel_t<512, 20, 1, 32>(n, Hp, nk, D, E, st, tune);
 }
 
 }  // namespace tbk

@@ -1,0 +1,399 @@
+// eig_tridiag_reg.cu -- register-resident Hermitian -> tridiagonal reduction, one warp per matrix, 21 <= N <= 48.
+//
+// Same role as eig_tridiag.cu (first half of the replacement for the per-k scipy.linalg.eigvalsh loop of
+// Model.eigenval, reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr JOBZ='N', UPLO='L') for the mid-size
+// matrices of the Wannier-model workloads (C3: N = 36).  The shared-memory kernel spends ten instructions per useful
+// DFMA there (triangle selects, address arithmetic, two LDS per four DFMA, 20 of 32 lanes active; ncu r01l: 35.8 k
+// warp instructions and 12.4 k shared-memory wavefronts per 36 x 36 matrix, 18 matrices resident per SM).  Here
+//   * lane c holds the FULL row c of the Hermitian matrix (both triangles, NMAX complex numbers = 4 NMAX registers);
+//     the Hermitian matrix-vector product is a plain row . v (no transposed part, no selects) and the rank-2 update
+//     A -= v w^H + w v^H touches only the lane's own registers;
+//   * v and w are broadcast from shared memory (one LDS.128 per column, all lanes read the same address);
+//   * every register index is a compile-time constant: the column loops are fully unrolled in blocks of four with a
+//     warp-uniform early exit at the size of the trailing block, and the pivot column is picked by a switch.
+// The reduction runs on the index-reversed matrix B[i][j] = A[N-1-i][N-1-j] and eliminates the LAST column of the
+// active leading block each step -- which is exactly the lower-storage reduction of LAPACK zhetd2 / hetrd_serial
+// (tbk_math.cuh) on A (same reflectors, same tridiagonal matrix up to the summation order): the active block stays
+// anchored at index 0, so its rows are lanes 0 .. p-1 and its columns registers 0 .. p-1 for every step p.
+// Matrices with N > 32 keep rows 32 .. N-1 implicitly: their entries left of column 32 are the conjugates of
+// columns 32 .. N-1 of the lane rows (updated there anyway); only the (N-32)^2 corner block lives in shared memory.
+// Those rows are eliminated first (N - 32 "corner" steps with a few extra warp reductions), after which the loop is
+// the lean 32-lane form.
+// Shared memory per matrix is only the load staging (N^2 doubles) + v, w + corner: residency is bounded by registers
+// (9-10 warps per SM at NMAX = 36) and the kernel is FP64-pipe / issue bound instead of shared-memory bound.
+// Bits depend on N only (fixed reduction orders), never on the batch.
+#include "tbk_kernels.h"
+#include "tbk_math.cuh"
+
+namespace tbk {
+
+namespace {
+
+__device__ __forceinline__ int itri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ int itrs(int i) { return (i * (i - 1)) >> 1; }
+
+__device__ __forceinline__ double warp_sum(double a) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    return a;
+}
+
+template <int B, int NMAX>
+__device__ __forceinline__ void pick(const double (&ar)[NMAX], const double (&ai)[NMAX], double& xr, double& xi) {
+    if constexpr (B < NMAX) {
+        xr = ar[B];
+        xi = ai[B];
+    }
+}
+
+// x = column p of the lane's row (p is warp-uniform; a switch keeps the register indices static)
+template <int NMAX>
+__device__ __forceinline__ void get_col(const double (&ar)[NMAX], const double (&ai)[NMAX], int p, double& xr, double& xi) {
+    xr = 0.0;
+    xi = 0.0;
+    switch (p) {
+#define TBK_PICK(B) \
+    case B:         \
+        pick<B, NMAX>(ar, ai, xr, xi); \
+        break;
+        TBK_PICK(0) TBK_PICK(1) TBK_PICK(2) TBK_PICK(3) TBK_PICK(4) TBK_PICK(5) TBK_PICK(6) TBK_PICK(7)
+        TBK_PICK(8) TBK_PICK(9) TBK_PICK(10) TBK_PICK(11) TBK_PICK(12) TBK_PICK(13) TBK_PICK(14) TBK_PICK(15)
+        TBK_PICK(16) TBK_PICK(17) TBK_PICK(18) TBK_PICK(19) TBK_PICK(20) TBK_PICK(21) TBK_PICK(22) TBK_PICK(23)
+        TBK_PICK(24) TBK_PICK(25) TBK_PICK(26) TBK_PICK(27) TBK_PICK(28) TBK_PICK(29) TBK_PICK(30) TBK_PICK(31)
+#undef TBK_PICK
+        default: break;
+    }
+}
+
+// q = (row of this lane) . v over the columns b < m (block granular: V is zero from m up to the next multiple of 4)
+template <int NMAX>
+__device__ __forceinline__ void row_dot(const double (&ar)[NMAX], const double (&ai)[NMAX], const double2* __restrict__ V,
+                                        int m, double& qr, double& qi) {
+    double sr[4] = {0.0, 0.0, 0.0, 0.0}, si[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int b0 = 0; b0 < NMAX; b0 += 4) {
+        if (b0 >= m) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = V[b0 + j];
+            sr[j] = fma(ar[b0 + j], v.x, sr[j]);
+            si[j] = fma(ar[b0 + j], v.y, si[j]);
+            sr[j] = fma(-ai[b0 + j], v.y, sr[j]);
+            si[j] = fma(ai[b0 + j], v.x, si[j]);
+        }
+    }
+    qr = (sr[0] + sr[1]) + (sr[2] + sr[3]);
+    qi = (si[0] + si[1]) + (si[2] + si[3]);
+}
+
+// row -= v_c conj(w_b) + w_c conj(v_b) over the columns b < m (block granular; V, W zero beyond m)
+template <int NMAX>
+__device__ __forceinline__ void row_update(double (&ar)[NMAX], double (&ai)[NMAX], const double2* __restrict__ V,
+                                           const double2* __restrict__ W, int m, double vr, double vi, double wr, double wi) {
+#pragma unroll
+    for (int b0 = 0; b0 < NMAX; b0 += 4) {
+        if (b0 >= m) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 vb = V[b0 + j], wb = W[b0 + j];
+            ar[b0 + j] = fma(-vr, wb.x, fma(-vi, wb.y, fma(-wr, vb.x, fma(-wi, vb.y, ar[b0 + j]))));
+            ai[b0 + j] = fma(-vi, wb.x, fma(vr, wb.y, fma(-wi, vb.x, fma(wr, vb.y, ai[b0 + j]))));
+        }
+    }
+}
+
+template <int NREG>
+constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers are per SM sub-partition: 16 K each)
+    return NREG <= 20 ? 16 : 12;  // <= 128 / <= 168 registers per thread
+}
+
+// NREG: columns (and rows) held in registers, a multiple of 4 up to 32.  XMAX: capacity for the rows / columns beyond 32
+// (N <= 32 + XMAX); 0 for N <= 32.
+template <int NREG, int XMAX>
+__global__ void __launch_bounds__(32, reg_min_blocks<NREG>())
+tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
+                   double* __restrict__ E, int ldo, int off) {
+    static_assert(NREG % 4 == 0 && NREG <= 32, "NREG must be a multiple of 4, at most 32");
+    static_assert(XMAX == 0 || NREG == 32, "extra rows only behind a full warp of register rows");
+    constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;  // entries of v / w (every lane writes its own)
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x;
+    const long kk = blockIdx.x;
+    if (kk >= nk) return;
+    const int ntri = itri(N);
+    const int nn = N * N;
+    double* S = smem;                                                    // load staging: the packed matrix
+    double2* V = reinterpret_cast<double2*>(S + ((nn + 1) & ~1));        // [NV]
+    double2* W = V + NV;                                                 // [NV]
+    double2* C = W + NV;                                                 // [XMAX][XMAX] corner block B[32+r][32+s]
+    double2* XC = C + XMAX * XMAX;                                       // [XMAX][32]   XC[s][c] = B[c][32+s]
+
+    {   // asynchronous copy of the packed matrix (every element in flight at once, no register staging)
+        const double* src = Hp + kk * mstride;
+        const unsigned sS = (unsigned)__cvta_generic_to_shared(S);
+        if ((nn & 1) == 0 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {
+            for (int e = lane; e < nn / 2; e += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sS + 16u * e), "l"(src + 2 * e) : "memory");
+        } else {
+            for (int e = lane; e < nn; e += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sS + 8u * e), "l"(src + e) : "memory");
+        }
+        for (int i = lane; i < 2 * NV; i += 32) V[i] = make_double2(0.0, 0.0);  // V and W are contiguous
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncwarp();
+
+    // ---- registers: row `lane` of the index-reversed matrix B[c][b] = A[N-1-c][N-1-b], columns b < NREG ----
+    double ar[NREG], ai[NREG];
+    {
+        const int I = N - 1 - lane;  // row of A held by this lane (lane < N)
+        const bool row_ok = lane < N;
+        const double* Si = S + ntri;
+        const int Ic = row_ok ? I : 0;
+        const int triI = itri(Ic), trsI = itrs(Ic);
+#pragma unroll
+        for (int b = 0; b < NREG; ++b) {
+            // b >= lane (J <= I): stored entry (I, J); else the conjugate of the stored entry (J, I).  Branch-free:
+            // select the two packed offsets, load, fix the sign, zero what lies outside the matrix / on the diagonal.
+            const int J = b < N ? N - 1 - b : 0;
+            const bool own = b >= lane;
+            const int ire = own ? triI + J : itri(J) + Ic;
+            int iim = own ? trsI + J : itrs(J) + Ic;
+            const bool diag = b == lane;
+            iim = diag ? 0 : iim;
+            const double re = S[ire];
+            const double im = Si[iim];
+            const bool ok = row_ok && b < N;
+            ar[b] = ok ? re : 0.0;
+            ai[b] = (ok && !diag) ? (own ? im : -im) : 0.0;
+        }
+        if constexpr (XMAX > 0) {
+            const int X = N - 32;  // rows / columns 32 .. N-1 of B = rows / columns X-1 .. 0 of A
+            for (int s = 0; s < X; ++s) {  // B[lane][32+s] = A[I][X-1-s], I >= X > X-1-s: stored
+                const int J = X - 1 - s;
+                XC[s * 32 + lane] = make_double2(S[itri(I) + J], Si[itrs(I) + J]);
+            }
+            for (int e = lane; e < X * X; e += 32) {
+                const int r = e / X, s = e - r * X;
+                const int Ir = X - 1 - r, Js = X - 1 - s;
+                double re, im = 0.0;
+                if (Js <= Ir) {
+                    re = S[itri(Ir) + Js];
+                    if (Js < Ir) im = Si[itrs(Ir) + Js];
+                } else {
+                    re = S[itri(Js) + Ir];
+                    im = -Si[itrs(Js) + Ir];
+                }
+                C[r * XMAX + s] = make_double2(re, im);
+            }
+        }
+    }
+    __syncwarp();
+
+    double d1 = 0.0, e1 = 0.0;  // d[lane], e[lane] of the reversed problem
+    double d2 = 0.0, e2 = 0.0;  // d[32 + lane], e[32 + lane]
+    int p = N - 1;
+
+    if constexpr (XMAX > 0) {
+        // ---- corner steps: pivot columns N-1 .. 32.  Rows 32 .. p-1 are the "second slot" of lanes 0 .. p-33; their
+        // entries left of column 32 are conj(XC), the rest is the corner block C ----
+        for (; p >= 32; --p) {
+            const int xc = p - 32;  // active second-slot rows = active extra columns; pivot column of XC and C
+            const double2 x1 = XC[xc * 32 + lane];
+            const double xr = x1.x, xi = x1.y;
+            double x2r = 0.0, x2i = 0.0;
+            if (lane < xc) {
+                const double2 z = C[lane * XMAX + xc];
+                x2r = z.x;
+                x2i = z.y;
+            }
+            if (lane == xc) d2 = C[xc * XMAX + xc].x;
+            double alr, ali, xn;
+            if (xc >= 1) {  // alpha sits in the second slot of lane xc - 1 (row p - 1)
+                alr = __shfl_sync(0xffffffffu, x2r, xc - 1);
+                ali = __shfl_sync(0xffffffffu, x2i, xc - 1);
+                xn = fma(xr, xr, xi * xi);
+                if (lane < xc - 1) xn += fma(x2r, x2r, x2i * x2i);
+            } else {        // p == 32: alpha is row 31
+                alr = __shfl_sync(0xffffffffu, xr, 31);
+                ali = __shfl_sync(0xffffffffu, xi, 31);
+                xn = lane < 31 ? fma(xr, xr, xi * xi) : 0.0;
+            }
+            xn = warp_sum(xn);
+            double beta, tr, ti, sr, si;
+            householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
+            if (xc >= 1) {
+                if (lane == xc - 1) e2 = beta;
+            } else if (lane == 31) {
+                e1 = beta;
+            }
+            if (tr == 0.0 && ti == 0.0) continue;
+            double vr = xr * sr - xi * si, vi = xr * si + xi * sr;
+            double v2r = 0.0, v2i = 0.0;
+            if (xc >= 1) {
+                if (lane < xc - 1) {
+                    v2r = x2r * sr - x2i * si;
+                    v2i = x2r * si + x2i * sr;
+                } else if (lane == xc - 1) {
+                    v2r = 1.0;
+                }
+            } else if (lane == 31) {
+                vr = 1.0;
+                vi = 0.0;
+            }
+            V[lane] = make_double2(vr, vi);
+            if (lane < XMAX) V[32 + lane] = make_double2(v2r, v2i);
+            __syncwarp();
+            // q = B v.  Lane rows: register columns 0 .. 31, then the extra columns 32 .. p-1 from XC
+            double qr, qi;
+            row_dot<NREG>(ar, ai, V, 32, qr, qi);
+            for (int s = 0; s < xc; ++s) {
+                const double2 z = XC[s * 32 + lane], v = V[32 + s];
+                qr = fma(z.x, v.x, fma(-z.y, v.y, qr));
+                qi = fma(z.x, v.y, fma(z.y, v.x, qi));
+            }
+            // second-slot rows: sum_{b<32} conj(B[b][32+r]) v_b (one warp reduction per row) + corner part
+            double q2r = 0.0, q2i = 0.0;
+            for (int r = 0; r < xc; ++r) {
+                const double2 z = XC[r * 32 + lane];
+                double tr_ = fma(z.x, vr, z.y * vi);
+                double ti_ = fma(z.x, vi, -z.y * vr);
+                tr_ = warp_sum(tr_);
+                ti_ = warp_sum(ti_);
+                if (lane == r) {
+                    q2r = tr_;
+                    q2i = ti_;
+                }
+            }
+            if (lane < xc) {
+                for (int s = 0; s < xc; ++s) {
+                    const double2 z = C[lane * XMAX + s], v = V[32 + s];
+                    q2r = fma(z.x, v.x, fma(-z.y, v.y, q2r));
+                    q2i = fma(z.x, v.y, fma(z.y, v.x, q2i));
+                }
+            }
+            const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+            const double p2r = tr * q2r - ti * q2i, p2i = tr * q2i + ti * q2r;
+            double dr = pr * vr + pi * vi + (p2r * v2r + p2i * v2i);
+            double di = pr * vi - pi * vr + (p2r * v2i - p2i * v2r);
+            dr = warp_sum(dr);
+            di = warp_sum(di);
+            const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
+            const double wr = pr + cr * vr - ci * vi, wi = pi + cr * vi + ci * vr;
+            const double w2r = p2r + cr * v2r - ci * v2i, w2i = p2i + cr * v2i + ci * v2r;
+            W[lane] = make_double2(wr, wi);
+            if (lane < XMAX) W[32 + lane] = make_double2(w2r, w2i);
+            __syncwarp();
+            row_update<NREG>(ar, ai, V, W, 32, vr, vi, wr, wi);
+            for (int s = 0; s < xc; ++s) {
+                const double2 vb = V[32 + s], wb = W[32 + s];
+                double2 z = XC[s * 32 + lane];
+                z.x = fma(-vr, wb.x, fma(-vi, wb.y, fma(-wr, vb.x, fma(-wi, vb.y, z.x))));
+                z.y = fma(-vi, wb.x, fma(vr, wb.y, fma(-wi, vb.x, fma(wr, vb.y, z.y))));
+                XC[s * 32 + lane] = z;
+            }
+            for (int e = lane; e < xc * xc; e += 32) {
+                const int r = e / xc, s = e - r * xc;
+                const double2 va = V[32 + r], wa = W[32 + r], vb = V[32 + s], wb = W[32 + s];
+                double2 z = C[r * XMAX + s];
+                z.x = fma(-va.x, wb.x, fma(-va.y, wb.y, fma(-wa.x, vb.x, fma(-wa.y, vb.y, z.x))));
+                z.y = fma(-va.y, wb.x, fma(va.x, wb.y, fma(-wa.y, vb.x, fma(wa.x, vb.y, z.y))));
+                C[r * XMAX + s] = z;
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- lean steps: pivot columns min(N-1, 31) .. 1; active rows = lanes 0 .. p-1, active columns = registers 0 .. p-1 ----
+    for (; p >= 1; --p) {
+        double xr, xi;
+        get_col<NREG>(ar, ai, p, xr, xi);
+        if (lane == p) d1 = xr;
+        const double alr = __shfl_sync(0xffffffffu, xr, p - 1);
+        const double ali = __shfl_sync(0xffffffffu, xi, p - 1);
+        double xn = lane < p - 1 ? fma(xr, xr, xi * xi) : 0.0;
+        xn = warp_sum(xn);
+        double beta, tr, ti, sr, si;
+        householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
+        if (lane == p - 1) e1 = beta;
+        if (tr == 0.0 && ti == 0.0) continue;
+        double vr = 0.0, vi = 0.0;
+        if (lane < p - 1) {
+            vr = xr * sr - xi * si;
+            vi = xr * si + xi * sr;
+        } else if (lane == p - 1) {
+            vr = 1.0;
+        }
+        V[lane] = make_double2(vr, vi);  // zero from p on: the block-granular loops read up to the next multiple of 4
+        __syncwarp();
+        double qr, qi;
+        row_dot<NREG>(ar, ai, V, p, qr, qi);
+        const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+        double dr = pr * vr + pi * vi;  // lanes >= p: v = 0
+        double di = pr * vi - pi * vr;
+        dr = warp_sum(dr);
+        di = warp_sum(di);
+        const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
+        double wr = 0.0, wi = 0.0;
+        if (lane < p) {
+            wr = pr + cr * vr - ci * vi;
+            wi = pi + cr * vi + ci * vr;
+        }
+        W[lane] = make_double2(wr, wi);
+        __syncwarp();
+        row_update<NREG>(ar, ai, V, W, p, vr, vi, wr, wi);
+        __syncwarp();
+    }
+    {
+        double xr, xi;
+        get_col<NREG>(ar, ai, 0, xr, xi);
+        if (lane == 0) d1 = xr;
+    }
+
+    // ---- store, undoing the index reversal: d_A[i] = d_B[N-1-i], e_A[i] = e_B[N-2-i] ----
+    double* Dk = D + kk * (long)ldo + off;
+    double* Ek = E + kk * (long)ldo + off;
+    if (lane < N) Dk[N - 1 - lane] = d1;
+    if (lane <= N - 2) Ek[N - 2 - lane] = e1;
+    if constexpr (XMAX > 0) {
+        if (32 + lane < N) Dk[N - 1 - 32 - lane] = d2;
+        if (32 + lane <= N - 2) Ek[N - 2 - 32 - lane] = e2;
+    }
+    if (lane == 0) Ek[N - 1] = 0.0;
+}
+
+template <int NREG, int XMAX>
+cudaError_t launch_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
+                       int off) {
+    constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;
+    const size_t smem = (size_t)(((n * n + 1) & ~1)) * 8 + (size_t)(2 * NV + XMAX * XMAX + XMAX * 32) * 16;
+    cudaError_t err =
+        cudaFuncSetAttribute(tridiag_reg_kernel<NREG, XMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (nk <= 0) return cudaSuccess;
+    if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_reg_kernel<NREG, XMAX><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool tridiag_reg_fits(int n) { return n >= 2 && n <= kTridiagRegMaxN; }
+
+cudaError_t launch_tridiag_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
+                               int ldo, int off) {
+    if (mstride == 0) mstride = (long)n * n;
+    if (ldo == 0) ldo = n;
+    if (n <= 12) return launch_reg<12, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 16) return launch_reg<16, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 20) return launch_reg<20, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 24) return launch_reg<24, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 28) return launch_reg<28, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 32) return launch_reg<32, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 36) return launch_reg<32, 4>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 40) return launch_reg<32, 8>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (n <= 48) return launch_reg<32, 16>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tbk

@@ -408,8 +408,7 @@ cudaError_t launch_basis_ndk(const ModelDev& md, const double* k, long nk, doubl
 template <int N, int D>
 cudaError_t launch_basis_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
     if (D <= 2) {
-        if (const char* e = getenv("TBK_BASIS_KP"))  // tuning hook: k-points per thread and trip
-            if (atoi(e) == 2) return launch_basis_ndk<N, D, 2>(md, k, nk, Hp, eig, st);
+        if (md.tune.basis_kp == 2) return launch_basis_ndk<N, D, 2>(md, k, nk, Hp, eig, st);  // tuning hook
         return launch_basis_ndk<N, D, 4>(md, k, nk, Hp, eig, st);
     }
     return launch_basis_ndk<N, D, 2>(md, k, nk, Hp, eig, st);

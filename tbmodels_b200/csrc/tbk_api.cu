@@ -89,7 +89,39 @@ void pack_hermitian_rows_host(int n, int nterms, const double* mats, double* W) 
     }
 }
 
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
 }  // namespace
+
+namespace tbk {
+// Environment hooks, read once per handle: tbk_model_create / tbk_kdotp_create.
+Tuning read_tuning() {
+    Tuning t;
+    const long ws = env_int("TBK_WORKSPACE_MB", 0), hc = env_int("TBK_HOST_CHUNK_MB", 0);
+    if (ws > 0) t.workspace_mb = ws;
+    if (hc > 0) t.host_chunk_mb = hc;
+    t.no_mesh_factor = getenv("TBK_NO_MESH_FACTOR") ? 1 : 0;
+    t.basis_kp = env_int("TBK_BASIS_KP", 0);
+    t.tridiag_g = env_int("TBK_TRIDIAG_G", 0);
+    t.tridiag_cs = env_int("TBK_TRIDIAG_CS", 1);
+    t.tridiag_mpb = env_int("TBK_TRIDIAG_MPB", 0);
+    t.tridiag_stages = env_int("TBK_TRIDIAG_STAGES", t.tridiag_stages);
+    t.tridiag_panel_min = env_int("TBK_TRIDIAG_PANEL_MIN", 0);
+    t.tridiag_nopanel = getenv("TBK_TRIDIAG_NOPANEL") ? 1 : 0;
+    t.tridiag_oldbig = getenv("TBK_TRIDIAG_OLDBIG") ? 1 : 0;
+    t.tridiag_reg_min = env_int("TBK_TRIDIAG_REG_MIN", t.tridiag_reg_min);
+    t.tridiag_reg_max = env_int("TBK_TRIDIAG_REG_MAX", t.tridiag_reg_max);
+    if (t.tridiag_reg_max > kTridiagRegMaxN) t.tridiag_reg_max = kTridiagRegMaxN;
+    t.panel_t = env_int("TBK_PANEL_T", 0);
+    t.panel_lpr = env_int("TBK_PANEL_LPR", 0);
+    t.panel_pfd = env_int("TBK_PANEL_PFD", 1);
+    t.ql_bisect_min = env_int("TBK_QL_BISECT_MIN", 0);
+    return t;
+}
+}  // namespace tbk
 
 struct tbk_model {
     int device = 0;
@@ -193,11 +225,7 @@ int upload_gemm_weights(tbk_model* m, const std::vector<double>& W, int n_rows) 
 }
 
 long pick_chunk(const tbk_model* m) {
-    size_t budget_mb = 2048;
-    if (const char* s = getenv("TBK_WORKSPACE_MB")) {
-        const long v = atol(s);
-        if (v > 0) budget_mb = (size_t)v;
-    }
+    const size_t budget_mb = (size_t)m->md.tune.workspace_mb;
     const size_t per_k = ((size_t)m->md.n * m->md.n + m->md.n + (m->md.small_ok ? 0 : (size_t)m->md.kchunks * kGemmKC)) * 8;
     long chunk = (long)((budget_mb << 20) / per_k);
     if (chunk < 1) chunk = 1;
@@ -205,7 +233,7 @@ long pick_chunk(const tbk_model* m) {
     if (chunk >= 1024) chunk &= ~127L;  // whole GEMM row tiles
     if (!m->md.small_ok) {
         // whole waves of the thread-per-matrix QL kernel (its threads all run equally long: a partial wave idles SMs)
-        const long wave = ql_wave_matrices(m->md.n);
+        const long wave = ql_wave_matrices(m->md.n, m->md.tune);
         if (wave > 0 && chunk > wave) chunk -= chunk % wave;
     }
     return chunk;
@@ -247,8 +275,8 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
         double* D = out + c0 * md.n;
         LAUNCH(5, st, launch_hk_phase(md, k + c0 * md.dim, cn, m->wsQ, st));
         LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
-        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
-        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
+        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st, md.tune));
+        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st, md.tune));
     }
     return TBK_OK;
 }
@@ -268,7 +296,7 @@ int grow(double** p, size_t* have, size_t want) {
 bool mesh_factorised(const tbk_model* m, const int64_t* dims) {
     const ModelDev& md = m->md;
     if (md.small_ok || md.kind != 0 || md.nclass <= 0 || md.dim < 2) return false;
-    if (getenv("TBK_NO_MESH_FACTOR")) return false;  // test hook: explicit k-points through the ordinary path
+    if (md.tune.no_mesh_factor) return false;  // test hook: explicit k-points through the ordinary path
     const long nz = (long)dims[md.dim - 1];
     if (2L * md.nclass > nz || 2 * md.nclass > 256) return false;
     if (mesh_lines_smem_bytes(2 * md.nclass) > 200 * 1024) return false;
@@ -309,8 +337,8 @@ int run_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, lo
         LAUNCH(0, st, launch_hk_gemm(md, ln * K2, m->wsQ, m->wsAB, st));
         // stage B: expand every line along the last mesh dimension
         LAUNCH(6, st, launch_mesh_lines(md, m->wsAB, m->wsQz, nz, ln, m->wsH, st));
-        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st));
-        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st));
+        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st, md.tune));
+        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st, md.tune));
     }
     return TBK_OK;
 }
@@ -372,11 +400,7 @@ int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int 
     if (nk <= 0) return TBK_OK;
     const size_t out_per_k = convention ? (size_t)2 * md.n * md.n : (size_t)md.n;
     const size_t bytes_per_k = ((size_t)md.dim + out_per_k) * 8;
-    size_t target_mb = 64;
-    if (const char* s = getenv("TBK_HOST_CHUNK_MB")) {
-        const long v = atol(s);
-        if (v > 0) target_mb = (size_t)v;
-    }
+    const size_t target_mb = (size_t)md.tune.host_chunk_mb;
     long hchunk = (long)((target_mb << 20) / bytes_per_k);
     if (hchunk < 1) hchunk = 1;
     if (hchunk >= 1024) hchunk &= ~127L;
@@ -447,6 +471,7 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
     if (!m) return fail(TBK_E_INVALID, "out of host memory");
     m->device = device;
     ModelDev& md = m->md;
+    md.tune = read_tuning();
     md.n = n_orb;
     md.dim = dim;
     md.nR = n_R;
@@ -582,6 +607,7 @@ int tbk_kdotp_create(int dim, int n_orb, int n_terms, const int32_t* powers, con
     if (!m) return fail(TBK_E_INVALID, "out of host memory");
     m->device = device;
     ModelDev& md = m->md;
+    md.tune = read_tuning();
     md.n = n_orb;
     md.dim = dim;
     md.nR = n_terms;

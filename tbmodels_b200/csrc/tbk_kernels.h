@@ -10,6 +10,30 @@ constexpr int kSmallMaxN = 8;     // thread-per-k fused kernel handles N <= 8 (i
 constexpr int kGemmBM = 128;      // k-points per CTA tile of the H(k) GEMM
 constexpr int kGemmKC = 16;       // K (= 2 * R-vectors) per pipeline stage
 constexpr int kGemmStages = 5;
+constexpr int kTridiagRegMaxN = 48;  // register-resident warp-per-matrix tridiagonalisation (eig_tridiag_reg.cu)
+
+// Tuning / test hooks, read from the environment ONCE per handle at tbk_model_create (never on the launch path).
+// Defaults are the measured best; none of them depends on the batch.
+struct Tuning {
+    long workspace_mb = 2048;   // TBK_WORKSPACE_MB: scratch budget that sizes the k-point chunk of the GEMM path
+    long host_chunk_mb = 64;    // TBK_HOST_CHUNK_MB: chunk of the H2D | kernels | D2H pipeline of the _host entry points
+    int no_mesh_factor = 0;     // TBK_NO_MESH_FACTOR: tbk_eigenval_mesh generates explicit k-points instead
+    int basis_kp = 0;           // TBK_BASIS_KP: k-points per thread of the trigonometric-product kernel (0 = default)
+    int tridiag_g = 0;          // TBK_TRIDIAG_G: shared-memory kernel: threads per matrix (1 = tensor-core variant)
+    int tridiag_cs = 1;         // TBK_TRIDIAG_CS: column slices
+    int tridiag_mpb = 0;        // TBK_TRIDIAG_MPB: matrices per CTA (0 = maximise residency)
+    int tridiag_stages = 67;    // TBK_TRIDIAG_STAGES: staged reduction, size ratio between launches in percent (0 = off)
+    int tridiag_panel_min = 0;  // TBK_TRIDIAG_PANEL_MIN: blocked kernel from this N on (0 = default 120)
+    int tridiag_nopanel = 0;    // TBK_TRIDIAG_NOPANEL
+    int tridiag_oldbig = 0;     // TBK_TRIDIAG_OLDBIG
+    int tridiag_reg_min = 21;   // TBK_TRIDIAG_REG_MIN / _MAX: sizes served by the register-resident kernel
+    int tridiag_reg_max = 40;   //   (TBK_TRIDIAG_REG_MAX=0 disables it)
+    int panel_t = 0;            // TBK_PANEL_T: blocked kernel: threads per matrix
+    int panel_lpr = 0;          // TBK_PANEL_LPR: lanes per row
+    int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
+    int ql_bisect_min = 0;      // TBK_QL_BISECT_MIN: bisection instead of QL from this N on (0 = default)
+};
+Tuning read_tuning();
 
 // Device-resident packed model (see DESIGN.md "Data layout in HBM").
 struct ModelDev {
@@ -39,6 +63,7 @@ struct ModelDev {
     // prod_d k_d^{p_d} instead of [cos | sin] phases; Pw holds the integer powers [kchunks * 16][dim]
     int kind = 0;
     const int* Pw = nullptr;
+    Tuning tune;  // environment hooks, captured when the handle was created
 };
 
 // H(k) build on the FP64 tensor cores: Hp[k][0..n*n) (packed Hermitian, see tbk_math.cuh).
@@ -63,14 +88,19 @@ cudaError_t launch_mesh_kpoints(int dim, const int64_t* dims, const double* shif
                                 cudaStream_t st);
 size_t mesh_lines_smem_bytes(int K2);
 // Batched Hermitian -> tridiagonal reduction (Hp is destroyed). D, E: [nk][n].
-cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
+cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
+// Register-resident warp-per-matrix variant (eig_tridiag_reg.cu), n <= kTridiagRegMaxN.  The matrix of problem k is the
+// packed n x n block at Hp + k * mstride; results go to D / E [k * ldo + off + i] (mstride = 0 -> n * n, ldo = 0 -> n).
+bool tridiag_reg_fits(int n);
+cudaError_t launch_tridiag_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
+                               int ldo, int off);
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
 bool tridiag_panel_fits(int n);
-cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st);
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
 // Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
-cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st);
+cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, const Tuning& tune);
 // Matrices per full wave of the QL kernel on the current device (chunks are sized in whole waves); 0 if n/a.
-long ql_wave_matrices(int n);
+long ql_wave_matrices(int n, const Tuning& tune);
 
 // FP64 peak micro-benchmarks (bench.py roofline denominators). Return achieved TFLOP/s, or < 0 on error.
 double measure_fp64_peak(int kind /*0 = DMMA, 1 = DFMA*/, int iters);
