@@ -47,7 +47,7 @@ WORKLOADS = {
 
 
 def build_model(workload: str):
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     if workload == "c1":
         return wl.load_packed(os.path.join(ROOT, "tests", "golden", "silicon.npz"))
@@ -64,7 +64,7 @@ def build_model(workload: str):
 
 def host_kpoints(workload: str, n_k: int, dim: int, seed: int = 0) -> np.ndarray:
     if workload == "c1":
-        from tbmodels_b200 import workloads as wl
+        from oracle import workloads as wl
 
         return wl.kgrid(20, 3)[:n_k]
     return np.random.default_rng(seed).random((n_k, dim))

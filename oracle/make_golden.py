@@ -104,7 +104,7 @@ def find_scattered(raw: bytes, expected: np.ndarray, tol=1e-9):
 def main():
     warnings.simplefilter("ignore")
     tb = import_reference()
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     os.makedirs(GOLD, exist_ok=True)
     rng = np.random.default_rng(20240917)

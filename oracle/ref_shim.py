@@ -4,9 +4,8 @@ This module is part of the parity oracle: only ``tests/``, ``oracle/make_golden.
 ``cpu_baseline`` leg of ``bench.py`` may use anything under ``oracle/``.  The product package
 ``tbmodels_b200`` never imports it.
 
-``/root/reference`` exists only in the build container (never on the GPU box), so everything that
-goes through this shim is either a ``-m "not gpu"`` test that skips when the tree is absent, or the
-golden-vector generator whose outputs are committed under ``tests/golden/``.
+``/root/reference`` exists only in the build container; on the GPU box the shim falls back to the byte-identical copy
+of the package that ``oracle/build_ref.py`` places under ``oracle/_ref/`` (git-ignored, shipped like ``libtbk.so``).
 
 The reference (v1.4.4) does not import on this image as-is; the hot path itself needs only numpy and
 scipy.  The shims:
@@ -27,10 +26,23 @@ import warnings
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("TBK_REFERENCE_ROOT", "/root/reference")
+_REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_src() -> str | None:
+    """Directory to put on ``sys.path``: the reference tree itself, else the verified copy under ``oracle/_ref``."""
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "tbmodels")):
+        return os.path.join(REFERENCE_ROOT, "src")
+    if os.path.isdir(os.path.join(_REF_COPY, "tbmodels")):
+        from . import build_ref
+
+        if build_ref.verify():
+            return _REF_COPY
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "tbmodels"))
+    return reference_src() is not None
 
 
 def _install_stubs() -> None:
@@ -93,10 +105,10 @@ def import_reference():
     """Return the reference ``tbmodels`` module (unmodified sources, shimmed imports)."""
     if "tbmodels" in sys.modules:
         return sys.modules["tbmodels"]
-    if not reference_available():
-        raise ImportError(f"reference tree not found at {REFERENCE_ROOT}")
+    src = reference_src()
+    if src is None:
+        raise ImportError(f"reference package found neither at {REFERENCE_ROOT} nor (verified) under {_REF_COPY}")
     _install_stubs()
-    src = os.path.join(REFERENCE_ROOT, "src")
     if src not in sys.path:
         sys.path.insert(0, src)
     with warnings.catch_warnings():

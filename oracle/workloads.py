@@ -1,9 +1,11 @@
-"""Benchmark / parity workloads of BASELINE.json, generated directly in packed (half-set) form.
+"""TEST / BENCH INPUT GENERATORS -- the workloads of BASELINE.json, generated directly in packed (half-set) form.
 
-The reference package is not available on the GPU box, so the models of SURVEY.md section 8 (d2) are
-rebuilt here with numpy following the reference's own construction rules; ``tests/test_workloads.py``
-checks each generator against the unmodified reference (in the build container) and against committed
-golden digests (everywhere).
+Not part of the product: ``tbmodels_b200`` never imports this module.  Model construction is OUT OF SCOPE for the
+device path and stays the reference's Python; these generators restate the reference's
+construction rules with numpy only so that ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` can build their
+synthetic input models without importing ``tbmodels``.  ``oracle/make_golden.py`` asserts array equality of every
+generator with the unmodified reference, and ``tests/test_host_side.py`` re-checks that live when the reference is
+importable (``/root/reference`` or ``oracle/_ref``).
 
 Reference rules restated:
 * ``Model.add_hop`` (src/tbmodels/_tb_model.py:1196-1215): R = 0 stores overlap/2 at (i, j) and its conjugate
@@ -21,7 +23,7 @@ import itertools
 
 import numpy as np
 
-from ._pack import PackedModel, pack_arrays
+from tbmodels_b200._pack import PackedModel, pack_arrays
 
 
 class HopBuilder:

@@ -12,7 +12,6 @@ Public surface
     KdotpModel                               ``tbmodels.kdotp.KdotpModel`` duck-type (k.p models, same kernels)
     install / uninstall                      switch ``tbmodels.Model`` itself over to the GPU path
     sharded                                  one-process-per-GPU k-point sharding (torch.distributed)
-    workloads                                the benchmark / parity model generators of BASELINE.json
     io                                       HDF5 model / k-point / eigenvalue files of the `tbmodels eigenvals` CLI
                                              (no h5py needed); `python -m tbmodels_b200 eigenvals` is that command
 """

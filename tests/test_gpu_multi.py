@@ -23,7 +23,7 @@ def _worker(rank, world, port, n_k, out_dir):
     import torch
     import torch.distributed as dist
 
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
     from tbmodels_b200.sharded import ShardedEvaluator, broadcast_model
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -52,7 +52,7 @@ def test_two_gpu_nccl_sharding(tmp_path, n_k):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import tbmodels_b200 as tbk
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path)), nprocs=2, join=True)
     d0 = np.load(tmp_path / "r0.npz")

@@ -66,7 +66,7 @@ def test_silicon_c1(tbk):
 
 def test_silicon_c1_full_grid_vs_oracle(tbk):
     """Config C1 at full size: 20x20x20 mesh, both conventions and eigenvalues, against the oracle."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = packed_from(load_golden("silicon.npz"))
@@ -91,7 +91,7 @@ def test_reference_cli_known_answer(tbk):
 
 def test_reference_regression_goldens(tbk):
     """The reference's own goldens for test_simple_hamilton / test_simple_eigenval (np.allclose there)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("ref_regression.npz")
     for ti, (t1, t2) in enumerate(d["t_values"]):
@@ -137,7 +137,7 @@ def test_edge_cases(tbk):
 
 @pytest.mark.parametrize("tag", ["c3", "c5s", "n3", "n5", "n7", "n12", "n17", "n33", "n50", "n70"])
 def test_synthetic_golden(tbk, tag):
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("synthetic.npz")
     n_orb, n_half = (int(x) for x in d[f"{tag}_shape"])
@@ -148,7 +148,7 @@ def test_synthetic_golden(tbk, tag):
 @pytest.mark.parametrize("tag,size", [("s222", (2, 2, 2)), ("s444", (4, 4, 4))])
 def test_supercell_c4(tbk, tag, size):
     """Config C4 (N = 512) and its N = 64 little brother, against reference eigenvalues."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("supercell.npz")
     p = wl.supercell(packed_from(load_golden("silicon.npz")), size)
@@ -180,7 +180,7 @@ def test_general_path_on_small_models(tbk, monkeypatch):
 def test_batch_invariance_bit_exact(tbk):
     """reference tests/test_hamilton.py:21-32, test_eigenval.py:17-20 (assert_allclose rtol 1e-7, atol 0):
     a k-point's result must not depend on where it sits in the batch."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     rng = np.random.default_rng(3)
     for p in (packed_from(load_golden("silicon.npz")), wl.synthetic(36, 40), wl.synthetic(12, 10), wl.haldane()):
@@ -210,7 +210,7 @@ def test_invalid_convention_raises_before_device(tbk):
 def test_device_pointer_api_matches_host_api(tbk):
     import torch
 
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     rng = np.random.default_rng(11)
     for p in (wl.haldane(), packed_from(load_golden("silicon.npz")), wl.synthetic(36, 30)):
@@ -280,7 +280,7 @@ def test_haldane_c2_large_properties(tbk):
     """C2 at 2e7 k-points (device resident): size-independent properties + oracle on a subsample."""
     import torch
 
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.haldane()
@@ -306,7 +306,7 @@ def test_c3_properties_and_subsample(tbk):
     """C3 model (N = 36, 251 stored R) on a 64^3 slab of the 256^3 mesh: trace identity, ordering, oracle subsample."""
     import torch
 
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(36, 250, seed=1234)
@@ -327,7 +327,7 @@ def test_c3_properties_and_subsample(tbk):
 
 def test_c5_small_sweep(tbk):
     """C5 shape (N = 128) with 200 stored R, 512 k-points against the oracle."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(128, 200, seed=1234)
@@ -339,7 +339,7 @@ def test_c5_small_sweep(tbk):
 
 def test_host_pipeline_chunking(tbk, monkeypatch):
     """Small host chunks force many pipeline iterations; pinned and pageable buffers give identical results."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     p = wl.haldane()
     k = np.random.default_rng(4).random((300_001, 2))
@@ -359,7 +359,7 @@ def test_host_pipeline_chunking(tbk, monkeypatch):
 @pytest.mark.parametrize("g", ["1", "32", "64"])
 def test_tridiag_variants_agree(tbk, monkeypatch, g):
     """Every thread-group size of the packed kernel and the tensor-core variant give reference eigenvalues."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     monkeypatch.setenv("TBK_TRIDIAG_G", g)
     d = load_golden("synthetic.npz")
@@ -372,7 +372,7 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
 @pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 48, 49, 64, 65, 96, 97, 119, 120, 121, 128, 129, 164, 165, 200, 257, 300, 513, 600, 601])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
     """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(n_orb, 4, seed=n_orb)
@@ -384,7 +384,7 @@ def test_size_boundaries_vs_oracle(tbk, n_orb):
 def test_trig_product_kernel_matches_general_small_kernel(tbk, monkeypatch):
     """Nearest-cell N <= 2 models run on the trigonometric-product kernel; the generic fused kernel (TBK_NO_BASIS=1)
     and the oracle must give the same H(k) and eigenvalues, for every (N, dim) instantiation and ragged batch sizes."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     rng = np.random.default_rng(7)
@@ -415,7 +415,7 @@ def test_trig_product_kernel_matches_general_small_kernel(tbk, monkeypatch):
 def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
     """The blocked (panel + tensor-core her2k) reduction forced onto small and ragged sizes: partial last panels,
     sizes that are not multiples of the 8 x 8 blocks, every thread-count instantiation."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     monkeypatch.setenv("TBK_TRIDIAG_PANEL_MIN", "2")
@@ -431,7 +431,7 @@ def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
 def test_staged_tridiag_ratios(tbk, monkeypatch, ratio):
     """Staged shared-memory reduction (trailing block relaunched at a smaller size): every stage boundary the default
     and two other ratios produce, against the oracle; "0" is the single-launch kernel."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     monkeypatch.setenv("TBK_TRIDIAG_STAGES", ratio)
@@ -444,7 +444,7 @@ def test_staged_tridiag_ratios(tbk, monkeypatch, ratio):
 @pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
 def test_unblocked_large_kernels_still_agree(tbk, monkeypatch, n_orb):
     """The shared-memory / row-sweep kernels the blocked one replaced stay reachable (sizes 601..640, tuning hook)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     monkeypatch.setenv("TBK_TRIDIAG_NOPANEL", "1")
@@ -488,7 +488,7 @@ def test_reference_wannier_goldens(tbk, tag):
 
 
 def test_reference_simple_model_goldens(tbk):
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("ref_simple_model.npz")
     r = load_golden("ref_regression.npz")
@@ -501,7 +501,7 @@ def test_reference_simple_model_goldens(tbk):
 
 def test_oversize_matrix_fallback(tbk):
     """N = 650 is past the row-sweep kernel's limit (640): exercises the thread-per-row fallback and bisection."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(650, 2, seed=3)
@@ -541,7 +541,7 @@ def _mesh_points(dims, shift=None):
 def test_eigenval_mesh_matches_explicit_kpoints(tbk, case):
     """tbk_eigenval_mesh: factorised over the last mesh dimension where the model allows it, explicit
     device-generated k-points otherwise; either way the oracle's eigenvalues on the explicit mesh points."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     shift = None
@@ -584,7 +584,7 @@ def test_eigenval_mesh_matches_explicit_kpoints(tbk, case):
 
 def test_eigenval_mesh_small_workspace_chunks_lines(tbk, monkeypatch):
     """Several workspace chunks of whole lines give the bits of one chunk (the line is the unit of the factorisation)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     p = wl.synthetic(36, 40, seed=21)
     dims = (7, 9, 48)
@@ -601,7 +601,7 @@ def test_eigenval_mesh_small_workspace_chunks_lines(tbk, monkeypatch):
 
 
 def test_eigenval_mesh_argument_errors(tbk):
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     ev = tbk.Evaluator(wl.synthetic(12, 5, seed=3))
     try:
@@ -659,7 +659,7 @@ def test_eigenval_mesh_edge_shapes(tbk):
     """Mesh entry point corner cases: unit dimensions, a single class of lattice vectors (planar model in 3-D), the empty
     model, line lengths around the 64-point step of the line kernel, large and negative shifts."""
     from tbmodels_b200 import pack_arrays
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     orc = _oracle()
     rng = np.random.default_rng(77)

@@ -163,7 +163,7 @@ def test_kmodel_pickles_without_device_state():
 
 
 def test_workload_generators_golden():
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("haldane.npz")
     h = wl.haldane()

@@ -41,7 +41,7 @@ def test_reference_cli_known_answer():
 
 def test_reference_regression_goldens():
     """96 + 48 goldens of tests/regression_data/test_hamilton|test_eigenval (np.allclose in the reference)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("ref_regression.npz")
     n = 0
@@ -83,7 +83,7 @@ def test_edge_cases():
 
 
 def test_synthetic_golden():
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("synthetic.npz")
     for tag in ("c3", "n3", "n5", "n7", "n12", "n17", "n33"):
@@ -155,7 +155,7 @@ def test_reference_wannier_goldens():
 
 def test_reference_simple_model_goldens():
     """tests/regression_data/test_simple_model/* (reference tests/test_simple_model.py:12-20)."""
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     d = load_golden("ref_simple_model.npz")
     r = load_golden("ref_regression.npz")
@@ -170,7 +170,7 @@ def test_mesh_factorisation_algebra_matches_the_fourier_sum():
     """The identity behind tbk_eigenval_mesh (class sums over the leading mesh coordinates, then one phase per class
     along the last one), restated in numpy, against the pinned restatement of Model.hamilton on the explicit points."""
     from oracle import tb_oracle as orc
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     for p, dims, shift in (
         (wl.synthetic(5, 40, seed=1), (3, 4, 6), None),

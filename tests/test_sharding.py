@@ -41,7 +41,7 @@ def _worker(rank, world, port, n_k, result_dir):
     import torch.distributed as dist
 
     from oracle import tb_oracle as orc
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
     from tbmodels_b200.sharded import ShardedEvaluator, broadcast_model
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -80,7 +80,7 @@ def test_two_rank_gloo_sharding(tmp_path, n_k):
     import torch.multiprocessing as mp
 
     from oracle import tb_oracle as orc
-    from tbmodels_b200 import workloads as wl
+    from oracle import workloads as wl
 
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_k, str(tmp_path)), nprocs=world, join=True)

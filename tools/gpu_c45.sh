@@ -19,7 +19,7 @@ echo "== hamilton path timing"
 timeout 600 python - <<'PY'
 import torch, time, numpy as np
 import tbmodels_b200 as tbk
-from tbmodels_b200 import workloads as wl
+from oracle import workloads as wl
 for name,p,nk in (("haldane",wl.haldane(),20_000_000),("c3",wl.synthetic(36,250),131072)):
     ev=tbk.Evaluator(p,device=0); ev.profile(True)
     k=torch.rand((nk,p.dim),dtype=torch.float64,device="cuda")

@@ -11,7 +11,7 @@ os.environ["TBK_TRIDIAG_REG_MAX"] = "48"
 os.environ["TBK_FORCE_GEMM"] = "1"
 import tbmodels_b200 as tbk  # noqa: E402
 from oracle import tb_oracle as orc  # noqa: E402
-from tbmodels_b200 import workloads as wl  # noqa: E402
+from oracle import workloads as wl  # noqa: E402
 
 rng = np.random.default_rng(0)
 worst = 0.0

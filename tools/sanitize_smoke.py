@@ -6,7 +6,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tbmodels_b200 as tbk  # noqa: E402
-from tbmodels_b200 import workloads as wl  # noqa: E402
+from oracle import workloads as wl  # noqa: E402
 
 rng = np.random.default_rng(0)
 cases = [

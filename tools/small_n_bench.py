@@ -7,7 +7,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tbmodels_b200 as tbk  # noqa: E402
-from tbmodels_b200 import workloads as wl  # noqa: E402
+from oracle import workloads as wl  # noqa: E402
 
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cases = [("silicon N=8 95R", wl.load_packed(os.path.join(root, "tests", "golden", "silicon.npz")), 2_000_000)]
