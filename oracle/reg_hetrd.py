@@ -3,8 +3,7 @@
 
 Nothing like it exists in the reference (it calls LAPACK through scipy, src/tbmodels/_tb_model.py:1149).  This file
 restates the device ALGORITHM lane by lane -- index reversal, full rows per lane, the "second slot" rows 32 .. N-1
-that exist only as conj(XC) plus the corner block C, block-granular column loops over zero-padded v / w, and the
-single fused reduction per step (product with the UNSCALED column, v^H A v from three sums) -- so that
+that exist only as conj(XC) plus the corner block C, block-granular column loops over zero-padded v / w -- so that
 its algebra is pinned against LAPACK on the CPU (tests/test_oracle_golden.py) before the kernel runs on a GPU.
 Arrays indexed [lane] stand for per-lane registers; V, W, XC, C stand for the kernel's shared-memory arrays.
 """
@@ -85,43 +84,20 @@ def reg_tridiagonalise(S: np.ndarray, N: int):
     def blocks(m):  # columns the block-granular loops touch
         return min(nreg, -(-m // 4) * 4)
 
-    def scalars(alpha, s1, s2, s3, adiag):
-        """(beta, tau, scale, coef): reflector + the real coefficient of v in w (one fused reduction: s1, s2, s3)."""
-        beta, tau, scale = reflector(complex(alpha), float(s1))
-        g = abs(scale) ** 2 * s2 + 2.0 * (np.conj(scale) * s3).real + adiag
-        return beta, tau, scale, -0.5 * abs(tau) ** 2 * g
-
     p = N - 1
     while p >= 32:  # ---- corner steps ----
         xc = p - 32
         x1 = XC[xc].copy()
         x2 = np.zeros(LANES, dtype=complex)
-        a2 = np.zeros(LANES, dtype=complex)
         x2[:xc] = C[:xc, xc]
         d2[xc] = C[xc, xc].real
         if xc >= 1:
-            a1 = XC[xc - 1].copy()
-            a2[:xc] = C[:xc, xc - 1]
-            a2[xc - 1] = a2[xc - 1].real
-            alpha, adiag = x2[xc - 1], a2[xc - 1].real
-            x2[xc - 1] = 0.0
+            alpha = x2[xc - 1]
+            xn = np.sum(np.abs(x1) ** 2) + np.sum(np.abs(x2[: xc - 1]) ** 2)
         else:
-            a1 = a[:, 31].copy()
-            alpha, adiag = x1[31], a1[31].real
-            x1[31] = 0.0
-            a1[31] = a1[31].real
-        V[:32] = x1
-        V[32 : 32 + xmax] = x2[:xmax]
-        y1 = a[:, : blocks(32)] @ V[: blocks(32)]
-        for s in range(xc):
-            y1 = y1 + XC[s] * V[32 + s]
-        y2 = np.zeros(LANES, dtype=complex)
-        for r in range(xc):
-            y2[r] = np.sum(np.conj(XC[r]) * x1) + np.sum(C[r, :xc] * V[32 : 32 + xc])
-        s1 = np.sum(np.abs(x1) ** 2) + np.sum(np.abs(x2) ** 2)
-        s2 = np.sum((np.conj(x1) * y1).real) + np.sum((np.conj(x2) * y2).real)
-        s3 = np.sum(np.conj(x1) * a1) + np.sum(np.conj(x2) * a2)
-        beta, tau, scale, coef = scalars(alpha, s1, s2, s3, adiag)
+            alpha = x1[31]
+            xn = np.sum(np.abs(x1[:31]) ** 2)
+        beta, tau, scale = reflector(complex(alpha), float(xn))
         if xc >= 1:
             e2[xc - 1] = beta
         else:
@@ -129,17 +105,28 @@ def reg_tridiagonalise(S: np.ndarray, N: int):
         if tau == 0:
             p -= 1
             continue
-        v1, v2 = x1 * scale, x2 * scale
+        v1 = x1 * scale
+        v2 = np.zeros(LANES, dtype=complex)
         if xc >= 1:
+            v2[: xc - 1] = x2[: xc - 1] * scale
             v2[xc - 1] = 1.0
         else:
             v1[31] = 1.0
-        w1 = tau * (scale * y1 + a1) + coef * v1
-        w2 = np.zeros(LANES, dtype=complex)
-        w2[:xc] = tau * (scale * y2[:xc] + a2[:xc]) + coef * v2[:xc]
         V[:32] = v1
-        W[:32] = w1
         V[32 : 32 + xmax] = v2[:xmax]
+        q1 = a[:, : blocks(32)] @ V[: blocks(32)]
+        for s in range(xc):
+            q1 = q1 + XC[s] * V[32 + s]
+        q2 = np.zeros(LANES, dtype=complex)
+        for r in range(xc):
+            q2[r] = np.sum(np.conj(XC[r]) * v1)
+        for r in range(xc):
+            q2[r] += np.sum(C[r, :xc] * V[32 : 32 + xc])
+        p1, p2 = tau * q1, tau * q2
+        dot = np.sum(np.conj(p1) * v1) + np.sum(np.conj(p2) * v2)
+        coef = -0.5 * tau * dot
+        w1, w2 = p1 + coef * v1, p2 + coef * v2
+        W[:32] = w1
         W[32 : 32 + xmax] = w2[:xmax]
         nb = blocks(32)
         a[:, :nb] -= np.outer(v1, np.conj(W[:nb])) + np.outer(w1, np.conj(V[:nb]))
@@ -152,29 +139,26 @@ def reg_tridiagonalise(S: np.ndarray, N: int):
 
     while p >= 1:  # ---- lean steps ----
         x = a[:, p].copy()
-        ac = a[:, p - 1].copy()
         d1[p] = x[p].real
-        alpha, adiag = x[p - 1], ac[p - 1].real
-        x[p - 1 :] = 0.0
-        ac[p - 1] = ac[p - 1].real
-        V[:32] = x
-        nb = blocks(p - 1)
-        y = a[:, :nb] @ V[:nb]
-        s1 = np.sum(np.abs(x) ** 2)
-        s2 = np.sum((np.conj(x) * y).real)
-        s3 = np.sum(np.conj(x) * ac)
-        beta, tau, scale, coef = scalars(alpha, s1, s2, s3, adiag)
+        alpha = x[p - 1]
+        xn = np.sum(np.abs(x[: p - 1]) ** 2)
+        beta, tau, scale = reflector(complex(alpha), float(xn))
         e1[p - 1] = beta
         if tau == 0:
             p -= 1
             continue
-        v = x * scale
+        v = np.zeros(LANES, dtype=complex)
+        v[: p - 1] = x[: p - 1] * scale
         v[p - 1] = 1.0
-        w = np.zeros(LANES, dtype=complex)
-        w[:p] = tau * (scale * y[:p] + ac[:p]) + coef * v[:p]
         V[:32] = v
-        W[:32] = w
         nb = blocks(p)
+        q = a[:, :nb] @ V[:nb]
+        pv = tau * q
+        dot = np.sum(np.conj(pv) * v)
+        coef = -0.5 * tau * dot
+        w = np.zeros(LANES, dtype=complex)
+        w[:p] = pv[:p] + coef * v[:p]
+        W[:32] = w
         a[:, :nb] -= np.outer(v, np.conj(W[:nb])) + np.outer(w, np.conj(V[:nb]))
         p -= 1
     d1[0] = a[0, 0].real

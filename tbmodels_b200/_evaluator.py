@@ -66,7 +66,13 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
 
 
 class Evaluator:
-    """GPU-resident copy of one packed model plus the launch plumbing."""
+    """GPU-resident copy of one packed model plus the launch plumbing.
+
+    The handle owns ONE set of device scratch.  The ``*_device`` methods enqueue on torch's current stream and return
+    without synchronising; libtbk orders every call behind the previous one on the device (an event recorded on the
+    stream of each call, waited on by the next), so mixing ``*_device`` calls on different torch streams with the
+    host-buffer methods (which run on private streams) is safe -- they serialise, they do not race.  Deferred errors of
+    the asynchronous calls (QL non-convergence) surface at :meth:`check`."""
 
     def __init__(self, packed: PackedModel, device=None):
         self._lib = _capi.load()

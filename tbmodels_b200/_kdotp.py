@@ -8,6 +8,7 @@ same DMMA GEMM with a monomial generator in place of the phase generator, then t
 from __future__ import annotations
 
 import hashlib
+import weakref
 
 import numpy as np
 
@@ -72,5 +73,17 @@ def kdotp_evaluator_for(model, holder=None, cache: dict = None, device=None) -> 
         if holder is not None:
             holder._cache = entry
         else:
-            cache[id(model)] = entry
+            key = id(model)
+            if key not in cache:  # release the device copy when the model object goes away (as evaluator_for does)
+                try:
+                    weakref.finalize(model, _drop_cached, cache, key)
+                except TypeError:  # no weakref support: the entry lives until uninstall()
+                    pass
+            cache[key] = entry
     return entry[1]
+
+
+def _drop_cached(cache: dict, key) -> None:
+    entry = cache.pop(key, None)
+    if entry is not None:
+        entry[1].close()

@@ -38,19 +38,6 @@ __device__ __forceinline__ double warp_sum(double a) {
     return a;
 }
 
-// four sums at once: the shuffles of one butterfly stage are independent, so their latencies overlap
-__device__ __forceinline__ void warp_sum4(double& a, double& b, double& c, double& d) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double ta = __shfl_xor_sync(0xffffffffu, a, off), tb = __shfl_xor_sync(0xffffffffu, b, off);
-        const double tc = __shfl_xor_sync(0xffffffffu, c, off), td = __shfl_xor_sync(0xffffffffu, d, off);
-        a += ta;
-        b += tb;
-        c += tc;
-        d += td;
-    }
-}
-
 template <int B, int NMAX>
 __device__ __forceinline__ void pick(const double (&ar)[NMAX], const double (&ai)[NMAX], double& xr, double& xi) {
     if constexpr (B < NMAX) {
@@ -119,15 +106,15 @@ __device__ __forceinline__ void row_update(double (&ar)[NMAX], double (&ai)[NMAX
     }
 }
 
-template <int NREG>
+template <int NREG, int OCC>
 constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers are per SM sub-partition: 16 K each)
-    return NREG <= 20 ? 16 : 12;  // <= 128 / <= 168 registers per thread
+    return OCC ? OCC : (NREG <= 20 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
 }
 
 // NREG: columns (and rows) held in registers, a multiple of 4 up to 32.  XMAX: capacity for the rows / columns beyond 32
 // (N <= 32 + XMAX); 0 for N <= 32.
-template <int NREG, int XMAX, int BW>
-__global__ void __launch_bounds__(32, reg_min_blocks<NREG>())
+template <int NREG, int XMAX, int BW, int OCC>
+__global__ void __launch_bounds__(32, reg_min_blocks<NREG, OCC>())
 tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
                    double* __restrict__ E, int ldo, int off) {
     static_assert(NREG % 4 == 0 && NREG <= 32, "NREG must be a multiple of 4, at most 32");
@@ -211,117 +198,91 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
 
     int p = N - 1;
 
-    // One step eliminates pivot column p of the active leading block [0, p).  With x = column p above the diagonal,
-    // alpha = x[p-1], xt = x with the alpha entry zeroed and a = column p-1 of the block, the reflector
-    // v = scale xt + e_{p-1} gives  A v = scale (A xt) + a,  so the product y = A xt starts from the UNSCALED column,
-    // before the norm is known, and the three sums the step needs
-    //     s1 = xt^H xt (norm^2),  s2 = xt^H y (real),  s3 = xt^H a
-    // go through ONE fused warp reduction (the textbook order needs two dependent ones: norm, then p^H v):
-    //     v^H A v = |scale|^2 s2 + 2 Re(conj(scale) s3) + a[p-1],   w = tau A v - (|tau|^2 / 2)(v^H A v) v.
     if constexpr (XMAX > 0) {
         // ---- corner steps: pivot columns N-1 .. 32.  Rows 32 .. p-1 are the "second slot" of lanes 0 .. p-33; their
         // entries left of column 32 are conj(XC), the rest is the corner block C ----
         for (; p >= 32; --p) {
             const int xc = p - 32;  // active second-slot rows = active extra columns; pivot column of XC and C
             const double2 x1 = XC[xc * 32 + lane];
-            double xr = x1.x, xi = x1.y;          // x, rows 0 .. 31
-            double x2r = 0.0, x2i = 0.0;          // x, rows 32 + lane (lane < xc)
-            double a1r, a1i, a2r = 0.0, a2i = 0.0;  // a = column p - 1
-            double alr, ali, adiag;
+            const double xr = x1.x, xi = x1.y;
+            double x2r = 0.0, x2i = 0.0;
+            if (lane < xc) {
+                const double2 z = C[lane * XMAX + xc];
+                x2r = z.x;
+                x2i = z.y;
+            }
             if (lane == xc) DS[p] = C[xc * XMAX + xc].x;
+            double alr, ali, xn;
             if (xc >= 1) {  // alpha sits in the second slot of lane xc - 1 (row p - 1)
-                if (lane < xc) {
-                    const double2 z = C[lane * XMAX + xc], za = C[lane * XMAX + xc - 1];
-                    x2r = z.x;
-                    x2i = z.y;
-                    a2r = za.x;
-                    a2i = lane == xc - 1 ? 0.0 : za.y;
-                }
-                const double2 za1 = XC[(xc - 1) * 32 + lane];
-                a1r = za1.x;
-                a1i = za1.y;
                 alr = __shfl_sync(0xffffffffu, x2r, xc - 1);
                 ali = __shfl_sync(0xffffffffu, x2i, xc - 1);
-                adiag = __shfl_sync(0xffffffffu, a2r, xc - 1);
-                if (lane == xc - 1) x2r = x2i = 0.0;  // xt
-            } else {        // p == 32: alpha is row 31, a is register column 31
-                get_col<NREG>(ar, ai, 31, a1r, a1i);
+                xn = fma(xr, xr, xi * xi);
+                if (lane < xc - 1) xn += fma(x2r, x2r, x2i * x2i);
+            } else {        // p == 32: alpha is row 31
                 alr = __shfl_sync(0xffffffffu, xr, 31);
                 ali = __shfl_sync(0xffffffffu, xi, 31);
-                adiag = __shfl_sync(0xffffffffu, a1r, 31);
-                if (lane == 31) {
-                    xr = xi = 0.0;
-                    a1i = 0.0;
-                }
+                xn = lane < 31 ? fma(xr, xr, xi * xi) : 0.0;
             }
-            V[lane] = make_double2(xr, xi);
-            if (lane < XMAX) V[32 + lane] = make_double2(x2r, x2i);
+            xn = warp_sum(xn);
+            double beta, tr, ti, sr, si;
+            householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
+            if (lane == 0) ES[p - 1] = beta;
+            if (tr == 0.0 && ti == 0.0) continue;
+            double vr = xr * sr - xi * si, vi = xr * si + xi * sr;
+            double v2r = 0.0, v2i = 0.0;
+            if (xc >= 1) {
+                if (lane < xc - 1) {
+                    v2r = x2r * sr - x2i * si;
+                    v2i = x2r * si + x2i * sr;
+                } else if (lane == xc - 1) {
+                    v2r = 1.0;
+                }
+            } else if (lane == 31) {
+                vr = 1.0;
+                vi = 0.0;
+            }
+            V[lane] = make_double2(vr, vi);
+            if (lane < XMAX) V[32 + lane] = make_double2(v2r, v2i);
             __syncwarp();
-            // y = B xt.  Lane rows: register columns 0 .. 31, then the extra columns 32 .. p-1 from XC
-            double yr, yi;
-            row_dot<NREG, BW>(ar, ai, V, 32, yr, yi);
+            // q = B v.  Lane rows: register columns 0 .. 31, then the extra columns 32 .. p-1 from XC
+            double qr, qi;
+            row_dot<NREG, BW>(ar, ai, V, 32, qr, qi);
             for (int s = 0; s < xc; ++s) {
                 const double2 z = XC[s * 32 + lane], v = V[32 + s];
-                yr = fma(z.x, v.x, fma(-z.y, v.y, yr));
-                yi = fma(z.x, v.y, fma(z.y, v.x, yi));
+                qr = fma(z.x, v.x, fma(-z.y, v.y, qr));
+                qi = fma(z.x, v.y, fma(z.y, v.x, qi));
             }
-            // second-slot rows: sum_{b<32} conj(B[b][32+r]) xt_b (one warp reduction per row) + corner part
-            double y2r = 0.0, y2i = 0.0;
+            // second-slot rows: sum_{b<32} conj(B[b][32+r]) v_b (one warp reduction per row) + corner part
+            double q2r = 0.0, q2i = 0.0;
             for (int r = 0; r < xc; ++r) {
                 const double2 z = XC[r * 32 + lane];
-                double tr_ = fma(z.x, xr, z.y * xi);
-                double ti_ = fma(z.x, xi, -z.y * xr);
+                double tr_ = fma(z.x, vr, z.y * vi);
+                double ti_ = fma(z.x, vi, -z.y * vr);
                 tr_ = warp_sum(tr_);
                 ti_ = warp_sum(ti_);
                 if (lane == r) {
-                    y2r = tr_;
-                    y2i = ti_;
+                    q2r = tr_;
+                    q2i = ti_;
                 }
             }
             if (lane < xc) {
                 for (int s = 0; s < xc; ++s) {
                     const double2 z = C[lane * XMAX + s], v = V[32 + s];
-                    y2r = fma(z.x, v.x, fma(-z.y, v.y, y2r));
-                    y2i = fma(z.x, v.y, fma(z.y, v.x, y2i));
+                    q2r = fma(z.x, v.x, fma(-z.y, v.y, q2r));
+                    q2i = fma(z.x, v.y, fma(z.y, v.x, q2i));
                 }
             }
-            double s1 = fma(xr, xr, xi * xi) + fma(x2r, x2r, x2i * x2i);
-            double s2 = fma(xr, yr, xi * yi) + fma(x2r, y2r, x2i * y2i);
-            double s3r = fma(xr, a1r, xi * a1i) + fma(x2r, a2r, x2i * a2i);
-            double s3i = fma(xr, a1i, -xi * a1r) + fma(x2r, a2i, -x2i * a2r);
-            warp_sum4(s1, s2, s3r, s3i);
-            double beta, tr, ti, sr, si;
-            householder_gen(alr, ali, s1, beta, tr, ti, sr, si);
-            if (lane == 0) ES[p - 1] = beta;
-            if (tr == 0.0 && ti == 0.0) {
-                __syncwarp();
-                continue;
-            }
-            const double g = fma(fma(sr, sr, si * si), s2, fma(2.0, fma(sr, s3r, si * s3i), adiag));
-            const double coef = -0.5 * fma(tr, tr, ti * ti) * g;
-            double vr = xr * sr - xi * si, vi = xr * si + xi * sr;
-            double v2r = x2r * sr - x2i * si, v2i = x2r * si + x2i * sr;  // zero where xt is zero
-            if (xc >= 1) {
-                if (lane == xc - 1) v2r = 1.0;
-            } else if (lane == 31) {
-                vr = 1.0;
-            }
-            // A v = scale y + a;  w = tau A v + coef v
-            const double avr = fma(sr, yr, fma(-si, yi, a1r)), avi = fma(sr, yi, fma(si, yr, a1i));
-            const double wr = fma(tr, avr, fma(-ti, avi, coef * vr)), wi = fma(tr, avi, fma(ti, avr, coef * vi));
-            double w2r = 0.0, w2i = 0.0;
-            if (lane < xc) {
-                const double av2r = fma(sr, y2r, fma(-si, y2i, a2r)), av2i = fma(sr, y2i, fma(si, y2r, a2i));
-                w2r = fma(tr, av2r, fma(-ti, av2i, coef * v2r));
-                w2i = fma(tr, av2i, fma(ti, av2r, coef * v2i));
-            }
-            __syncwarp();  // every lane is done reading xt from V
-            V[lane] = make_double2(vr, vi);
+            const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+            const double p2r = tr * q2r - ti * q2i, p2i = tr * q2i + ti * q2r;
+            double dr = pr * vr + pi * vi + (p2r * v2r + p2i * v2i);
+            double di = pr * vi - pi * vr + (p2r * v2i - p2i * v2r);
+            dr = warp_sum(dr);
+            di = warp_sum(di);
+            const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
+            const double wr = pr + cr * vr - ci * vi, wi = pi + cr * vi + ci * vr;
+            const double w2r = p2r + cr * v2r - ci * v2i, w2i = p2i + cr * v2i + ci * v2r;
             W[lane] = make_double2(wr, wi);
-            if (lane < XMAX) {
-                V[32 + lane] = make_double2(v2r, v2i);
-                W[32 + lane] = make_double2(w2r, w2i);
-            }
+            if (lane < XMAX) W[32 + lane] = make_double2(w2r, w2i);
             __syncwarp();
             row_update<NREG, BW>(ar, ai, V, W, 32, vr, vi, wr, wi);
             for (int s = 0; s < xc; ++s) {
@@ -345,45 +306,39 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
 
     // ---- lean steps: pivot columns min(N-1, 31) .. 1; active rows = lanes 0 .. p-1, active columns = registers 0 .. p-1 ----
     for (; p >= 1; --p) {
-        double xr, xi, acr, aci;
-        get_col<NREG>(ar, ai, p, xr, xi);        // x: rows < p; the diagonal entry in lane p
-        get_col<NREG>(ar, ai, p - 1, acr, aci);  // a = column p - 1
+        double xr, xi;
+        get_col<NREG>(ar, ai, p, xr, xi);
         if (lane == p) DS[p] = xr;
         const double alr = __shfl_sync(0xffffffffu, xr, p - 1);
         const double ali = __shfl_sync(0xffffffffu, xi, p - 1);
-        const double adiag = __shfl_sync(0xffffffffu, acr, p - 1);
-        if (lane >= p - 1) {  // xt: alpha entry and everything outside the block zeroed
-            xr = xi = 0.0;
-            aci = lane == p - 1 ? 0.0 : aci;
-        }
-        V[lane] = make_double2(xr, xi);  // zero from p-1 on: the block-granular loops read up to the next multiple of 4
-        __syncwarp();
-        double yr, yi;
-        row_dot<NREG, BW>(ar, ai, V, p - 1, yr, yi);
-        double s1 = fma(xr, xr, xi * xi);
-        double s2 = fma(xr, yr, xi * yi);
-        double s3r = fma(xr, acr, xi * aci);
-        double s3i = fma(xr, aci, -xi * acr);
-        warp_sum4(s1, s2, s3r, s3i);
+        double xn = lane < p - 1 ? fma(xr, xr, xi * xi) : 0.0;
+        xn = warp_sum(xn);
         double beta, tr, ti, sr, si;
-        householder_gen(alr, ali, s1, beta, tr, ti, sr, si);
+        householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
         if (lane == 0) ES[p - 1] = beta;
-        if (tr == 0.0 && ti == 0.0) {
-            __syncwarp();
-            continue;
+        if (tr == 0.0 && ti == 0.0) continue;
+        double vr = 0.0, vi = 0.0;
+        if (lane < p - 1) {
+            vr = xr * sr - xi * si;
+            vi = xr * si + xi * sr;
+        } else if (lane == p - 1) {
+            vr = 1.0;
         }
-        const double g = fma(fma(sr, sr, si * si), s2, fma(2.0, fma(sr, s3r, si * s3i), adiag));
-        const double coef = -0.5 * fma(tr, tr, ti * ti) * g;
-        double vr = xr * sr - xi * si, vi = xr * si + xi * sr;  // zero where xt is zero
-        if (lane == p - 1) vr = 1.0;
+        V[lane] = make_double2(vr, vi);  // zero from p on: the block-granular loops read up to the next multiple of 4
+        __syncwarp();
+        double qr, qi;
+        row_dot<NREG, BW>(ar, ai, V, p, qr, qi);
+        const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+        double dr = pr * vr + pi * vi;  // lanes >= p: v = 0
+        double di = pr * vi - pi * vr;
+        dr = warp_sum(dr);
+        di = warp_sum(di);
+        const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
         double wr = 0.0, wi = 0.0;
-        if (lane < p) {  // A v = scale y + a;  w = tau A v + coef v
-            const double avr = fma(sr, yr, fma(-si, yi, acr)), avi = fma(sr, yi, fma(si, yr, aci));
-            wr = fma(tr, avr, fma(-ti, avi, coef * vr));
-            wi = fma(tr, avi, fma(ti, avr, coef * vi));
+        if (lane < p) {
+            wr = pr + cr * vr - ci * vi;
+            wi = pi + cr * vi + ci * vr;
         }
-        __syncwarp();  // every lane is done reading xt from V
-        V[lane] = make_double2(vr, vi);
         W[lane] = make_double2(wr, wi);
         __syncwarp();
         row_update<NREG, BW>(ar, ai, V, W, p, vr, vi, wr, wi);
@@ -406,25 +361,26 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
     if (lane == 0) Ek[N - 1] = 0.0;
 }
 
-template <int NREG, int XMAX, int BW>
+template <int NREG, int XMAX, int BW, int OCC>
 cudaError_t launch_reg_bw(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
                           int off) {
     constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;
     const size_t smem = (size_t)(((n * n + 1) & ~1)) * 8 + (size_t)(3 * NV + XMAX * XMAX + XMAX * 32) * 16;
     cudaError_t err =
-        cudaFuncSetAttribute(tridiag_reg_kernel<NREG, XMAX, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tridiag_reg_kernel<NREG, XMAX, BW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_reg_kernel<NREG, XMAX, BW><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off);
+    tridiag_reg_kernel<NREG, XMAX, BW, OCC><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off);
     return cudaGetLastError();
 }
 
 template <int NREG, int XMAX>
 cudaError_t launch_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
                        int off, int bw) {
-    if (bw == 8) return launch_reg_bw<NREG, XMAX, 8>(n, Hp, nk, D, E, st, mstride, ldo, off);
-    return launch_reg_bw<NREG, XMAX, 4>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    // bw: tuning hook.  8 = the 255-register build (8 resident warps per SM instead of 12), NREG = 32 only
+    if (bw == 8 && NREG == 32) return launch_reg_bw<NREG, XMAX, 4, (NREG == 32 ? 8 : 0)>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    return launch_reg_bw<NREG, XMAX, 4, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
 }
 
 }  // namespace

@@ -102,7 +102,13 @@ cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp,
         long blocks = nk;
         const long cap = (long)sms * 16;
         if (blocks > cap) blocks = cap;
-        const size_t smem = (size_t)md.n * sizeof(double2);
+        // the per-orbital phase table is only used by convention 1; large N needs the opt-in limit (> 48 KB from N = 3073)
+        const size_t smem = convention == 1 ? (size_t)md.n * sizeof(double2) : 0;
+        if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+        if (smem > 48 * 1024) {
+            cudaError_t err = cudaFuncSetAttribute(expand_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+        }
         expand_block_kernel<<<(unsigned)blocks, 256, smem, st>>>(Hp, k, md.pos, md.n, md.dim, nk, convention,
                                                                  reinterpret_cast<double2*>(out));
     }

@@ -51,7 +51,7 @@ template <int N, int D>  // D = 0: run-time dimension (<= kMaxDim)
 __global__ void __launch_bounds__(TPB)
 hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restrict__ Rd, const int* __restrict__ Ri,
                 const double* __restrict__ W, int dim_rt, int nR, int use_z, double* __restrict__ Hp,
-                double* __restrict__ eig) {
+                double* __restrict__ eig, int* __restrict__ fail_count) {
     constexpr int NN = N * N;
     const int dim = D ? D : dim_rt;
     extern __shared__ __align__(16) double sm[];
@@ -183,7 +183,8 @@ hk_small_kernel(const double* __restrict__ kpts, long nk, const double* __restri
                     double* dd = wv + 4L * N * TPB;
                     double* ee = dd + (long)N * TPB;
                     hetrd_serial(N, A, TPB, dd, ee, TPB, wv);
-                    tridiag_ql(N, dd, ee, TPB);
+                    const int fails = tridiag_ql(N, dd, ee, TPB);
+                    if (fails && fail_count) atomicAdd(fail_count, fails);  // reported by tbk_model_check / the _host calls
                     double* o = eig + idx * N;
 #pragma unroll
                     for (int i = 0; i < N; ++i) o[i] = dd[(long)i * TPB];
@@ -425,7 +426,8 @@ cudaError_t launch_basis_n(const ModelDev& md, const double* k, long nk, double*
 }
 
 template <int N, int D>
-cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, int* fail_count,
+                      cudaStream_t st) {
     const size_t smem = hk_small_smem_bytes(N, md.dim, md.nR, TPB);
     cudaError_t err =
         cudaFuncSetAttribute(hk_small_kernel<N, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -440,17 +442,18 @@ cudaError_t launch_nd(const ModelDev& md, const double* k, long nk, double* Hp, 
     if (blocks > cap) blocks = cap;
     if (blocks <= 0) return cudaSuccess;
     hk_small_kernel<N, D><<<(unsigned)blocks, TPB, smem, st>>>(k, nk, md.Rd, md.Ri, md.W, md.dim, md.nR, md.use_z, Hp,
-                                                               eig);
+                                                               eig, fail_count);
     return cudaGetLastError();
 }
 
 template <int N>
-cudaError_t launch_n(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+cudaError_t launch_n(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, int* fail_count,
+                     cudaStream_t st) {
     switch (md.dim) {
-        case 1: return launch_nd<N, 1>(md, k, nk, Hp, eig, st);
-        case 2: return launch_nd<N, 2>(md, k, nk, Hp, eig, st);
-        case 3: return launch_nd<N, 3>(md, k, nk, Hp, eig, st);
-        default: return launch_nd<N, 0>(md, k, nk, Hp, eig, st);
+        case 1: return launch_nd<N, 1>(md, k, nk, Hp, eig, fail_count, st);
+        case 2: return launch_nd<N, 2>(md, k, nk, Hp, eig, fail_count, st);
+        case 3: return launch_nd<N, 3>(md, k, nk, Hp, eig, fail_count, st);
+        default: return launch_nd<N, 0>(md, k, nk, Hp, eig, fail_count, st);
     }
 }
 
@@ -464,20 +467,21 @@ size_t hk_small_smem_bytes(int n, int dim, int nR, int threads) {
     return doubles * 8;
 }
 
-cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st) {
+cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, int* fail_count,
+                            cudaStream_t st) {
     if (md.basis_ok) {
         if (md.n == 1) return launch_basis_n<1>(md, k, nk, Hp, eig, st);
         if (md.n == 2) return launch_basis_n<2>(md, k, nk, Hp, eig, st);
     }
     switch (md.n) {
-        case 1: return launch_n<1>(md, k, nk, Hp, eig, st);
-        case 2: return launch_n<2>(md, k, nk, Hp, eig, st);
-        case 3: return launch_n<3>(md, k, nk, Hp, eig, st);
-        case 4: return launch_n<4>(md, k, nk, Hp, eig, st);
-        case 5: return launch_n<5>(md, k, nk, Hp, eig, st);
-        case 6: return launch_n<6>(md, k, nk, Hp, eig, st);
-        case 7: return launch_n<7>(md, k, nk, Hp, eig, st);
-        case 8: return launch_n<8>(md, k, nk, Hp, eig, st);
+        case 1: return launch_n<1>(md, k, nk, Hp, eig, fail_count, st);
+        case 2: return launch_n<2>(md, k, nk, Hp, eig, fail_count, st);
+        case 3: return launch_n<3>(md, k, nk, Hp, eig, fail_count, st);
+        case 4: return launch_n<4>(md, k, nk, Hp, eig, fail_count, st);
+        case 5: return launch_n<5>(md, k, nk, Hp, eig, fail_count, st);
+        case 6: return launch_n<6>(md, k, nk, Hp, eig, fail_count, st);
+        case 7: return launch_n<7>(md, k, nk, Hp, eig, fail_count, st);
+        case 8: return launch_n<8>(md, k, nk, Hp, eig, fail_count, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -155,6 +155,12 @@ struct tbk_model {
     double* ho[2] = {nullptr, nullptr};
     size_t hk_bytes = 0, ho_bytes = 0;
     int64_t launches = 0;
+    // The handle has ONE scratch set (wsH / wsE / wsQ / ...).  Every entry point records ev_busy on the stream it used
+    // when its launches are queued and makes its stream wait on the previous record first, so calls on different
+    // streams (a device-pointer call on a torch stream followed by a _host call on s_comp, two torch streams, ...)
+    // are ordered on the device instead of racing on the scratch.
+    cudaEvent_t ev_busy = nullptr;
+    bool busy_recorded = false;
     // optional per-kernel-class CUDA-event timing (tbk_profile / tbk_profile_read)
     bool prof_on = false;
     struct ProfRec {
@@ -267,7 +273,7 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (md.small_ok) {
-        LAUNCH(1, st, launch_hk_small(md, k, nk, nullptr, out, st));
+        LAUNCH(1, st, launch_hk_small(md, k, nk, nullptr, out, m->dFail, st));
         return TBK_OK;
     }
     if (int rc = ensure_workspace(m, nk)) return rc;
@@ -352,13 +358,26 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
     for (long c0 = 0; c0 < nk; c0 += m->chunk) {
         const long cn = std::min(m->chunk, nk - c0);
         const double* kc = k + c0 * md.dim;
-        if (md.small_ok) LAUNCH(1, st, launch_hk_small(md, kc, cn, m->wsH, nullptr, st));
+        if (md.small_ok) LAUNCH(1, st, launch_hk_small(md, kc, cn, m->wsH, nullptr, nullptr, st));
         else {
             LAUNCH(5, st, launch_hk_phase(md, kc, cn, m->wsQ, st));
             LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
         }
         LAUNCH(2, st, launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
     }
+    return TBK_OK;
+}
+
+// Order this call's use of the handle's scratch behind the previous call's (possibly on another stream).
+int scratch_acquire(tbk_model* m, cudaStream_t st) {
+    if (!m->ev_busy) CU(cudaEventCreateWithFlags(&m->ev_busy, cudaEventDisableTiming));
+    if (m->busy_recorded) CU(cudaStreamWaitEvent(st, m->ev_busy, 0));
+    return TBK_OK;
+}
+
+int scratch_release(tbk_model* m, cudaStream_t st) {
+    CU(cudaEventRecord(m->ev_busy, st));
+    m->busy_recorded = true;
     return TBK_OK;
 }
 
@@ -407,6 +426,7 @@ int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int 
     if (hchunk >= 1024) hchunk &= ~127L;
     if (hchunk > nk) hchunk = nk;
     if (int rc = ensure_pipeline(m, (size_t)hchunk * md.dim * 8, (size_t)hchunk * out_per_k * 8)) return rc;
+    if (int rc = scratch_acquire(m, m->s_comp)) return rc;
 
     int it = 0;
     for (long c0 = 0; c0 < nk; c0 += hchunk, ++it) {
@@ -428,6 +448,7 @@ int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int 
                            cudaMemcpyDeviceToHost, m->s_out));
         CU(cudaEventRecord(m->ev_out[b], m->s_out));
     }
+    if (int rc = scratch_release(m, m->s_comp)) return rc;
     CU(cudaStreamSynchronize(m->s_in));
     CU(cudaStreamSynchronize(m->s_comp));
     CU(cudaStreamSynchronize(m->s_out));
@@ -669,6 +690,7 @@ int tbk_model_destroy(tbk_model* m) {
         if (m->ev_comp[b]) cudaEventDestroy(m->ev_comp[b]);
         if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
     }
+    if (m->ev_busy) cudaEventDestroy(m->ev_busy);
     if (m->s_in) cudaStreamDestroy(m->s_in);
     if (m->s_comp) cudaStreamDestroy(m->s_comp);
     if (m->s_out) cudaStreamDestroy(m->s_out);
@@ -692,7 +714,9 @@ int tbk_hamilton(tbk_model* m, const double* k_dev, int64_t n_k, int convention,
     if (n_k < 0 || (n_k > 0 && (!k_dev || !out_dev))) return fail(TBK_E_INVALID, "tbk_hamilton: bad buffers");
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
-    return run_hamilton(m, k_dev, (long)n_k, convention, out_dev, (cudaStream_t)stream);
+    if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
+    if (int rc = run_hamilton(m, k_dev, (long)n_k, convention, out_dev, (cudaStream_t)stream)) return rc;
+    return scratch_release(m, (cudaStream_t)stream);
 }
 
 int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* stream) {
@@ -700,7 +724,9 @@ int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev
     if (n_k < 0 || (n_k > 0 && (!k_dev || !out_dev))) return fail(TBK_E_INVALID, "tbk_eigenval: bad buffers");
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
-    return run_eigenval(m, k_dev, (long)n_k, out_dev, (cudaStream_t)stream);
+    if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
+    if (int rc = run_eigenval(m, k_dev, (long)n_k, out_dev, (cudaStream_t)stream)) return rc;
+    return scratch_release(m, (cudaStream_t)stream);
 }
 
 int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
@@ -718,7 +744,9 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
     if (n_lines > 0 && !out_dev) return fail(TBK_E_INVALID, "tbk_eigenval_mesh: bad buffers");
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
-    return run_eigenval_mesh(m, dims, shift, (long)first_line, (long)n_lines, out_dev, (cudaStream_t)stream);
+    if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
+    if (int rc = run_eigenval_mesh(m, dims, shift, (long)first_line, (long)n_lines, out_dev, (cudaStream_t)stream)) return rc;
+    return scratch_release(m, (cudaStream_t)stream);
 }
 
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims) {

@@ -74,7 +74,9 @@ cudaError_t launch_hk_phase(const ModelDev& md, const double* k, long nk, double
 cudaError_t launch_hk_gemm(const ModelDev& md, long nk, const double* Qt, double* Hp, cudaStream_t st);
 size_t hk_gemm_q_doubles(const ModelDev& md, long nk);
 // Fused thread-per-k-point path for N <= 8: writes packed H (if Hp) and/or ascending eigenvalues (if eig).
-cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, cudaStream_t st);
+// fail_count (may be null): incremented by the number of eigenvalues whose QL iteration did not converge.
+cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, int* fail_count,
+                            cudaStream_t st);
 size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);
 // packed H -> full complex128 [nk][n][n]; convention 1 applies the orbital-position phases.
 cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention,

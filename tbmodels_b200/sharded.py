@@ -88,10 +88,22 @@ class ShardedEvaluator:
     def bounds(self, n_k: int):
         return shard_bounds(n_k, self.world_size, self.rank)
 
-    def eigenval_local(self, k_all):
-        """Evaluate this rank's contiguous shard of the replicated ``k_all`` -> ``(lo, hi, eig[lo:hi])``."""
+    def _check(self):
+        """Surface deferred device errors (QL non-convergence) of the asynchronous device-pointer calls."""
+        check = getattr(self.local, "check", None)
+        if check is not None:
+            check()
+
+    def eigenval_local(self, k_all, check=True):
+        """Evaluate this rank's contiguous shard of the replicated ``k_all`` -> ``(lo, hi, eig[lo:hi])``.
+
+        ``check=True`` synchronises and raises on a deferred device error; pass ``False`` to stay asynchronous (and call
+        ``self.local.check()`` yourself)."""
         lo, hi = self.bounds(k_all.shape[0])
-        return lo, hi, self.local.eigenval_device(k_all[lo:hi].contiguous())
+        eig = self.local.eigenval_device(k_all[lo:hi].contiguous())
+        if check:
+            self._check()
+        return lo, hi, eig
 
     def eigenval_mesh_local(self, dims, shift=None):
         """This rank's contiguous range of LINES (runs along the last dimension) of the regular mesh ``dims``
@@ -100,6 +112,7 @@ class ShardedEvaluator:
         n_lines = int(np.prod(dims[:-1])) if len(dims) > 1 else 1
         lo, hi = self.bounds(n_lines)
         eig = self.local.eigenval_mesh_device(dims, shift, first_line=lo, n_lines=hi - lo)
+        self._check()
         return lo * dims[-1], hi * dims[-1], eig
 
     def hamilton_local(self, k_all, convention=2):

@@ -337,6 +337,34 @@ def test_c5_small_sweep(tbk):
     assert np.all(np.diff(got, axis=1) >= 0)
 
 
+def test_c5_benchmarked_model_full_size(tbk):
+    """The model bench.py times as C5 -- synthetic N = 128 with 1001 stored R (126 K-stages of the GEMM, a 270 MB tiled
+    weight tensor that no longer fits L2) -- at 64 k-points: ``hamilton`` in both conventions and ``eigenval`` against
+    the oracle on all 64 points and against the golden written by the unmodified reference (oracle/make_golden_c5.py)."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    d = load_golden("c5_full.npz")
+    n_orb, n_half, seed = (int(x) for x in d["shape"])
+    p = wl.synthetic(n_orb, n_half, seed=seed)
+    assert p.n_R == 1001 and p.size == 128
+    k = d["k"]
+    ev = tbk.Evaluator(p)
+    assert ev.path == "gemm+tridiag-ql"
+    eig = ev.eigenval_array(k)
+    assert_eig_close(eig, d["eig"], "C5 vs reference golden")
+    assert_eig_close(eig, orc.eigenval_array(p.R, p.hop, p.pos, k), "C5 vs oracle")
+    for conv, key in ((1, "H1"), (2, "H2")):
+        h = ev.hamilton(k, convention=conv)
+        assert_h_close(h[:2], d[key], p, f"C5 hamilton conv {conv} vs reference golden")
+        assert_h_close(h, orc.hamilton(p.R, p.hop, p.pos, k, conv), p, f"C5 hamilton conv {conv} vs oracle")
+    # the mesh entry point on the same model: a small k-grid whose lines are long enough to be factorised
+    dims = (2, 2, 48)
+    km = wl.kgrid_points(dims)
+    assert_eig_close(ev.eigenval_mesh(dims), orc.eigenval_array(p.R, p.hop, p.pos, km), "C5 mesh vs oracle")
+    ev.close()
+
+
 def test_host_pipeline_chunking(tbk, monkeypatch):
     """Small host chunks force many pipeline iterations; pinned and pageable buffers give identical results."""
     from oracle import workloads as wl

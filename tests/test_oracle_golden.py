@@ -96,6 +96,19 @@ def test_synthetic_golden():
         assert_eig_close(np.array(orc.eigenval(p.R, p.hop, p.pos, k)), d[f"{tag}_eig"], tag)
 
 
+def test_c5_benchmarked_model_golden():
+    """Oracle vs the reference-written golden of the benchmarked C5 model (N = 128, 1001 stored R), 8 of the 64 points."""
+    from oracle import workloads as wl
+
+    d = load_golden("c5_full.npz")
+    n_orb, n_half, seed = (int(x) for x in d["shape"])
+    p = wl.synthetic(n_orb, n_half, seed=seed)
+    assert p.n_R == 1001
+    assert_eig_close(orc.eigenval_array(p.R, p.hop, p.pos, d["k"][:8]), d["eig"][:8], "c5 full")
+    np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, d["k"][:2], 1), d["H1"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(orc.hamilton(p.R, p.hop, p.pos, d["k"][:2], 2), d["H2"], rtol=0, atol=1e-12)
+
+
 def test_invalid_convention():
     d = load_golden("haldane.npz")
     p = packed_from(d)
