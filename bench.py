@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- k-points/s of Model.eigenval (H(k) build + eigenvalues, fp64) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch of synthetic k-points (per GPU: the workload's batch;
-weak scaling, no data-path collective -- every k-point is independent).  Default workload is
-BASELINE.json configs[1] (C2: 2-band Haldane model, 1e8 k-points per GPU).  Rank 0 prints ONE JSON line.
+Default workload: BASELINE.json configs[2] (C3: synthetic 36-orbital Wannier model, 251 stored R-vectors, the
+256^3 k-grid), the configuration the north_star target is quoted on.  One "step" = one pass of the hot path over the
+WHOLE k-set of the configuration: the k-points are cut into contiguous shards, one per GPU (strong scaling: total work
+is fixed as N grows), every rank evaluates its shard with the CUDA kernels and -- for N > 1 -- the eigenvalue shards
+are gathered with NCCL (all_gather_into_tensor over NVLink) so that every rank holds the full [N_k, N] result.  The
+gather is INSIDE the timed region.  Rank 0 prints ONE JSON line.
 
-  value        device-resident throughput (k already in HBM, eigenvalues left in HBM), CUDA events, max over ranks
-  e2e          same metric through the host-buffer C-ABI entry point (tbk_eigenval_host): pinned host k in,
-               pinned host eigenvalues out, H2D/D2H inside the timed region
-  roofline     dominant kernel: algorithmic bytes (or flops) per launch / CUDA-event duration of that kernel
-  cpu_baseline the oracle (numpy/scipy restatement of the reference path) timed on this box's host cores
-  extra        a short C3 run (N = 36, 251 stored R): FP64 tensor-core (DMMA) roofline of the H(k) GEMM
+  value        device-resident throughput: k [N_k, D] already in HBM -> gathered eigenvalues in HBM; CUDA events on the
+               launching stream, max over ranks
+  e2e          same metric through the host-buffer C-ABI entry point (tbk_eigenval_host): pinned host k in, pinned host
+               eigenvalues out, H2D / D2H inside the timed region (each rank its shard)
+  roofline     dominant kernel: algorithmic flops (or bytes) per launch / CUDA-event duration of that kernel
+  kernels      the same for every kernel class of the step
+  cpu_baseline the UNMODIFIED reference (oracle/_ref, imported through oracle/ref_shim.py) -- or the numpy/scipy oracle
+               port when the reference copy is absent -- timed on this box's host cores on a bounded sample
+  extra        N = 1: the other BASELINE configs (C2 at 1e8 k-points, C1, C5 with its N_k sweep, C4 at 12 500 k-points),
+               each with value / e2e / roofline / cpu_baseline, and C3 as a k-grid through eigenval_mesh;
+               N > 1: the C5 strong-scaling sweep and C3 through eigenval_mesh, gathers included
 
-``--impl reference`` times the reference's CPU implementation of the same path (the oracle port; the reference
-itself cannot travel to the GPU box) on all host cores with the same metric / unit / config.
+``--impl reference`` times the reference's own ``Model.eigenval`` on all host cores (process pool over k-chunks,
+BLAS threads = 1 each: the parallel mode the reference documents) with the same metric / unit / config.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import platform
 import subprocess
 import sys
 import tempfile
@@ -36,13 +45,19 @@ if ROOT not in sys.path:
 METRIC = "kpoints_per_s_eigenval_fp64"
 UNIT = "k-points/s"
 
+# name: description, total k-points of the configuration, mesh dims (None = seeded random k-points),
+#       default steps / warm-up, k-points of the single-process CPU sample
 WORKLOADS = {
-    # name: (description, default k-points per GPU, default steps, default warmup, cpu sample k-points)
-    "c1": ("silicon sp3 Wannier90 model N=8 95 stored R, 20^3 k-grid", 8000, 50, 5, 8000),
-    "c2": ("2-band Haldane model N=2 D=2 4 stored R, 1e8 random k-points per GPU", 10**8, 50, 5, 300_000),
-    "c3": ("synthetic N=36 251 stored R (seed 1234), 2^21 k-points per GPU (= 256^3 mesh over 8 GPUs)", 2**21, 5, 3, 6000),
-    "c4": ("silicon 4x4x4 supercell N=512 14 stored R, 12500 random k-points per GPU (= 1e5 over 8 GPUs)", 12500, 2, 3, 100),
-    "c5": ("synthetic N=128 1001 stored R (seed 1234), 2^14 k-points per GPU", 2**14, 3, 3, 100),
+    "c1": dict(desc="silicon sp3 Wannier90 model N=8 95 stored R, 20^3 k-grid (8000 k-points)", total=8000,
+               dims=(20, 20, 20), steps=50, warmup=5, cpu_sample=8000),
+    "c2": dict(desc="2-band Haldane model N=2 D=2 4 stored R, 1e8 random k-points", total=10**8, dims=None,
+               steps=20, warmup=5, cpu_sample=200_000),
+    "c3": dict(desc="synthetic N=36 251 stored R (seed 1234), 256^3 k-grid (16 777 216 explicit k-points)",
+               total=2**24, dims=(256, 256, 256), steps=3, warmup=3, cpu_sample=6000),
+    "c4": dict(desc="silicon 4x4x4 supercell N=512 14 stored R, 1e5 random k-points", total=10**5, dims=None,
+               steps=2, warmup=3, cpu_sample=60),
+    "c5": dict(desc="synthetic N=128 1001 stored R (seed 1234), 2^17 k-points of a 32x64x64 k-grid", total=2**17,
+               dims=(32, 64, 64), steps=3, warmup=3, cpu_sample=100),
 }
 
 
@@ -62,35 +77,144 @@ def build_model(workload: str):
     raise SystemExit(f"unknown workload {workload}")
 
 
-def host_kpoints(workload: str, n_k: int, dim: int, seed: int = 0) -> np.ndarray:
-    if workload == "c1":
-        from oracle import workloads as wl
+def mesh_dims_for(total: int, dims):
+    """Mesh whose point count is ``total``: the configured one, or (for an --nk override / the C5 sweep) the
+    power-of-two box (2^a, 2^b, 2^c), a <= b <= c as equal as possible.  None = seeded random k-points."""
+    if dims is None:
+        return None
+    if int(np.prod(dims)) == total:
+        return tuple(dims)
+    if total < 8 or total & (total - 1) or len(dims) != 3:
+        return None
+    e = total.bit_length() - 1
+    c = -(-e // 3)
+    b = -(-(e - c) // 2)
+    return (1 << (e - c - b), 1 << b, 1 << c)
 
-        return wl.kgrid(20, 3)[:n_k]
-    return np.random.default_rng(seed).random((n_k, dim))
+
+def host_kpoints(workload: str, n_k: int, dim: int, seed: int = 0) -> np.ndarray:
+    """A bounded CPU sample of the workload's k-set (mesh workloads: a seeded random subset of the mesh points)."""
+    cfg = WORKLOADS[workload]
+    rng = np.random.default_rng(seed)
+    if cfg["dims"] is None:
+        return rng.random((n_k, dim))
+    dims = np.array(cfg["dims"], dtype=np.int64)
+    total = int(np.prod(dims))
+    if n_k >= total:
+        idx = np.arange(total)
+    else:
+        idx = np.sort(rng.choice(total, size=n_k, replace=False))
+    return np.stack(np.unravel_index(idx, dims), axis=1).astype(np.float64) / dims
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference
-def _ref_chunk(args):
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    R, hop, pos, k = args
+_REF_STATE = {}
+
+
+def _ref_init(R, hop, pos, want_reference: bool):
+    """Pool initialiser: BLAS threads = 1 (also set in the environment before the pool was spawned, so the BLAS
+    library of this fresh interpreter never created a thread pool), then the evaluation callable."""
+    try:
+        import threadpoolctl
+
+        _REF_STATE["limits"] = threadpoolctl.threadpool_limits(1)
+    except Exception:  # noqa: BLE001
+        pass
+    _REF_STATE["fn"], _REF_STATE["kind"] = _make_ref_callable(R, hop, pos, want_reference)
+
+
+def _make_ref_callable(R, hop, pos, want_reference: bool = True):
+    """``fn(k[n,D]) -> None`` running Model.eigenval of the UNMODIFIED reference (kind "reference") when the package is
+    importable (/root/reference or the verified copy under oracle/_ref), else the oracle port (kind "port")."""
+    import warnings
+
+    from oracle import ref_shim
+
+    if want_reference and ref_shim.reference_available():
+        tb = ref_shim.import_reference()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = tb.Model(hop={tuple(int(x) for x in r): np.array(h) for r, h in zip(R, hop)}, pos=np.array(pos),
+                             size=pos.shape[0], dim=pos.shape[1], contains_cc=False)
+
+        def fn(k, chunk=2048):  # chunked only to bound the two [n_k, N, N] temporaries of the reference
+            for s in range(0, k.shape[0], chunk):
+                model.eigenval(k[s : s + chunk])
+
+        return fn, "reference"
     from oracle import tb_oracle as orc
 
+    return (lambda k: orc.eigenval_array(R, hop, pos, k, chunk=2048)), "port"
+
+
+def _ref_chunk(k):
     t0 = time.perf_counter()
-    orc.eigenval_array(R, hop, pos, k, chunk=2048)
+    _REF_STATE["fn"](k)
     return time.perf_counter() - t0
 
 
-def cpu_reference_rate(packed, k: np.ndarray, procs: int, pool=None) -> float:
-    """k-points/s of the oracle port on ``procs`` host processes (contiguous k-chunks, BLAS threads = 1)."""
-    if procs <= 1:
-        t0 = time.perf_counter()
-        _ref_chunk((packed.R, packed.hop, packed.pos, k))
-        return k.shape[0] / (time.perf_counter() - t0)
-    parts = np.array_split(k, procs)
+def _ref_info(_):
+    try:
+        import threadpoolctl
+
+        tp = [{k: d.get(k) for k in ("user_api", "internal_api", "version", "num_threads", "threading_layer")}
+              for d in threadpoolctl.threadpool_info()]
+    except Exception:  # noqa: BLE001
+        tp = None
+    return {"kind": _REF_STATE["kind"], "threadpool_info": tp}
+
+
+def host_record() -> dict:
+    """CPU model, library versions and BLAS thread pools of THIS process."""
+    import scipy
+
+    rec = {"python": platform.python_version(), "numpy": np.__version__, "scipy": scipy.__version__,
+           "host_cores": os.cpu_count()}
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    rec["cpu_model"] = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    try:
+        import threadpoolctl
+
+        rec["threadpool_info"] = [{k: d.get(k) for k in ("user_api", "internal_api", "version", "num_threads", "threading_layer")}
+                                  for d in threadpoolctl.threadpool_info()]
+    except Exception:  # noqa: BLE001
+        rec["threadpool_info"] = None
+    return rec
+
+
+def cpu_baseline_single(workload: str, packed, budget_s: float = 8.0) -> dict:
+    """The reference, single process as shipped (BLAS threads = library default), on a bounded sample."""
+    fn, kind = _make_ref_callable(packed.R, packed.hop, packed.pos)
+    cfg = WORKLOADS[workload]
+    ks = host_kpoints(workload, min(cfg["cpu_sample"], cfg["total"]), packed.dim, seed=1)
+    n_cal = max(4, min(ks.shape[0] // 20, 256))
     t0 = time.perf_counter()
-    pool.map(_ref_chunk, [(packed.R, packed.hop, packed.pos, p) for p in parts])
-    return k.shape[0] / (time.perf_counter() - t0)
+    fn(ks[:n_cal])
+    rate = n_cal / (time.perf_counter() - t0)
+    n = int(min(ks.shape[0], max(n_cal, rate * budget_s)))
+    ts = []
+    for _ in range(3 if n * 3 / rate < 2 * budget_s else 1):
+        t0 = time.perf_counter()
+        fn(ks[:n])
+        ts.append(time.perf_counter() - t0)
+    rec = host_record()
+    blas_threads = max([d.get("num_threads") or 1 for d in (rec.get("threadpool_info") or [])] or [1])
+    return {
+        "value": n / float(np.median(ts)),
+        "unit": UNIT,
+        "cores": int(blas_threads),
+        "kind": kind,
+        "sample": f"{n} k-points of the same workload (seeded subset), Model.eigenval of the "
+                  f"{'unmodified reference (oracle/_ref via oracle/ref_shim.py)' if kind == 'reference' else 'numpy/scipy oracle port'}"
+                  f", single process as the reference ships, BLAS threads = library default ({blas_threads}), median of {len(ts)}",
+        "host": rec,
+    }
 
 
 def run_reference_arm(args) -> None:
@@ -99,30 +223,39 @@ def run_reference_arm(args) -> None:
         return
     import multiprocessing as mp
 
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"  # before the workers are spawned: their BLAS reads it when numpy is first imported there
     packed = build_model(args.workload)
-    desc, nk_default, steps_d, warm_d, sample = WORKLOADS[args.workload]
+    cfg = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     steps = args.steps if args.steps is not None else 3
     warmup = args.warmup if args.warmup is not None else 1
     ctx = mp.get_context("spawn")
-    with ctx.Pool(procs) as pool:
+    with ctx.Pool(procs, initializer=_ref_init, initargs=(packed.R, packed.hop, packed.pos, True)) as pool:
+        info = pool.map(_ref_info, range(procs))[0]
+
+        def rate_of(k):
+            parts = [p for p in np.array_split(k, procs) if p.shape[0]]
+            t0 = time.perf_counter()
+            pool.map(_ref_chunk, parts, chunksize=1)
+            return k.shape[0] / (time.perf_counter() - t0)
+
         # calibrate on a small sample, then size each step so the whole run stays within ~2 minutes
-        cal = host_kpoints(args.workload, max(procs * 8, min(sample, 2000) * procs // 8), packed.dim, seed=2)
-        cpu_reference_rate(packed, cal[: procs * 4], procs, pool)  # spin the workers up
-        rate = cpu_reference_rate(packed, cal, procs, pool)
-        step_s = min(12.0, max(1.0, 110.0 / max(steps + warmup, 1)))
-        sample_k = int(max(procs * 8, rate * step_s))
-        if args.workload == "c1":
-            sample_k = min(sample_k, 8000)
+        cal = host_kpoints(args.workload, min(cfg["total"], max(procs * 4, min(cfg["cpu_sample"], 2000) * procs // 8)), packed.dim, seed=2)
+        rate_of(cal[: procs * 2])  # spin the workers up
+        rate = rate_of(cal)
+        step_s = min(12.0, max(1.0, 100.0 / max(steps + warmup, 1)))
+        sample_k = int(min(cfg["total"], max(procs * 4, rate * step_s)))
         k = host_kpoints(args.workload, sample_k, packed.dim, seed=1)
         for _ in range(warmup):
-            cpu_reference_rate(packed, k, procs, pool)
+            rate_of(k)
         t0 = time.perf_counter()
         for _ in range(steps):
-            cpu_reference_rate(packed, k, procs, pool)
+            rate_of(k)
         dt = time.perf_counter() - t0
     value = steps * k.shape[0] / dt
+    kind = info["kind"]
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -133,18 +266,21 @@ def run_reference_arm(args) -> None:
         "warmup": warmup,
         "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "n_orb": packed.size, "n_R_stored": packed.n_R, "dim": packed.dim},
+        "config": {"workload": f"{args.workload}: {cfg['desc']}"},
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
             "cores": procs,
-            "kind": "port",
-            "sample": f"{k.shape[0]} k-points of the same workload per step, numpy/scipy oracle port of "
-            f"Model.eigenval in {procs} processes (OPENBLAS_NUM_THREADS=1 each), host has {cores} cores",
+            "kind": kind,
+            "sample": f"{k.shape[0]} k-points of the same workload per step (seeded subset), Model.eigenval of the "
+                      f"{'unmodified reference (oracle/_ref via oracle/ref_shim.py)' if kind == 'reference' else 'numpy/scipy oracle port'}"
+                      f" in {procs} processes over contiguous k-chunks, BLAS threads = 1 each (set before the workers import "
+                      f"numpy), host has {cores} cores",
+            "host": {**host_record(), "worker_threadpool_info": info["threadpool_info"]},
         },
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -231,23 +367,19 @@ def measured_hbm_peak():
     try:
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    except Exception:
+    except Exception:  # noqa: BLE001
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-# DRAM bytes per k-point of the dominant kernels, from the ncu --set full captures summarised in
-# profiles/r01g_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch / its k-points).
-NCU_TRAFFIC_PER_K = {
-    ("c2", "hk_small"): (320.040704e6 + 279.324160e6) / 2.0e7,   # hk_basis_kernel<2,2,4>, 2e7 k-points per launch (r01m2_ncu_hk_basis_final.txt)
-    ("c3", "hk_gemm"): (0.472531e9 + 1.130096e9) / 113664.0,     # hk_gemm_kernel<9>, 113664 k-points per launch
-    # staged tridiag_smem_kernel<32,1>: stage 36 -> 24 (1.179 + 0.509 GB) + stage 24 -> 16 (0.524 + 0.209 GB) captured;
-    # the last stage (16 x 16 blocks, ~2.3 KB per matrix) estimated from its algorithmic bytes
-    ("c3", "tridiag"): (1.178607e9 + 0.506849e9 + 0.523854e9 + 0.208934e9) / 113664.0 + 2.3e3,
-    ("c5", "hk_gemm"): (7.805435e9 + 0.530372e9) / 4096.0,       # hk_gemm_kernel<8>
-    ("c5", "tridiag"): (0.834399e9 + 1.809944e9) / 4096.0,       # tridiag_panel_kernel<256,8,4,16> (matrices stay in L2)
-    ("c4", "tridiag"): (104.832851e9 + 11.813608e9) / 296.0,     # tridiag_panel_kernel<512,16,1,32>
-}
-NCU_TRAFFIC_SOURCE = "profiles/r01l_ncu_summary.txt (ncu --set full, per launch, scaled per k-point)"
+def ncu_traffic_table() -> dict:
+    """DRAM bytes per k-point of the dominant kernels (dram__bytes_read.sum + dram__bytes_write.sum of one launch of
+    an ``ncu --set full`` capture / the k-points of that launch): profiles/ncu_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep files of the round."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def flops_per_k(packed):
@@ -255,11 +387,57 @@ def flops_per_k(packed):
     return {"F_H": 8.0 * nR * n * n + 2.0 * n * n, "F_eig": (16.0 / 3.0) * n**3, "bytes": 8.0 * packed.dim + 8.0 * n}
 
 
-def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None, step=None):
+def kernel_rooflines(workload, prof, steps, n_local, fl, peaks, path):
+    """One roofline record per kernel class of the step (CUDA events around every launch, same timed region)."""
+    hbm_peak, hbm_src = measured_hbm_peak()
+    traffic = ncu_traffic_table()
+    total_ms = sum(v[0] for v in prof.values()) or 1e-12
+    out = {}
+    for cls, (ms, cnt) in prof.items():
+        if not cnt:
+            continue
+        per_launch_s = ms * 1e-3 / cnt
+        k_per_launch = n_local * steps / cnt
+        rec = {"kernel_ms_per_launch": per_launch_s * 1e3, "launches_per_step": cnt / steps,
+               "kernel_share_of_step": ms / total_ms, "kpoints_per_launch": k_per_launch}
+        if cls in ("hk_small", "expand"):
+            a = fl["bytes"] * k_per_launch / per_launch_s / 1e9
+            rec.update(kernel="hk_basis (profile class hk_small)" if path == "fused-product" else cls, bound="hbm", achieved=a,
+                       peak=hbm_peak, unit="GB/s", frac=a / hbm_peak, peak_source=hbm_src,
+                       algorithmic_bytes_per_kpoint=fl["bytes"],
+                       note="fp64 sincospi/FMA work per k-point is co-limiting; see DESIGN.md")
+        elif cls == "hk_gemm":
+            a = fl["F_H"] * k_per_launch / per_launch_s / 1e12
+            rec.update(kernel=cls, bound="tensor", achieved=a, peak=peaks["dmma"], unit="TFLOP/s", frac=a / peaks["dmma"],
+                       peak_source="tbk_measure_fp64_peak: mma.sync.m8n8k4.f64 register loop on this GPU in this run",
+                       algorithmic_flops_per_kpoint=fl["F_H"], executed_flops_per_kpoint=fl["F_H"] / 2.0,
+                       frac_executed=a / 2.0 / peaks["dmma"],
+                       note="achieved/frac count the ALGORITHMIC flops of the reference formulation (8 n_R N^2 per k-point); the "
+                            "Hermitian split executes half of them, so frac_executed (= ncu tensor-pipe utilisation) is the "
+                            "hardware utilisation and frac may legitimately reach 2.0")
+        elif cls in ("tridiag", "ql"):
+            # the eigensolver's algorithmic work, (16/3) N^3 flops per matrix, is charged to the tridiagonalisation;
+            # the QL / bisection stage is O(N^2) latency-bound work with no meaningful flop roofline
+            a = (fl["F_eig"] if cls == "tridiag" else 0.0) * k_per_launch / per_launch_s / 1e12
+            rec.update(kernel=cls, bound="tensor", achieved=a, peak=peaks["dfma"], unit="TFLOP/s", frac=a / peaks["dfma"],
+                       peak_source="tbk_measure_fp64_peak: DFMA register loop (the eigensolver runs on the FP64 FMA pipe, "
+                                   "which shares its datapath with DMMA on B200)",
+                       algorithmic_flops_per_kpoint=fl["F_eig"] if cls == "tridiag" else 0.0)
+        else:
+            rec.update(kernel=cls, bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
+        tpk = traffic.get(f"{workload}:{cls}")
+        rec["traffic"] = tpk["bytes_per_kpoint"] * k_per_launch if tpk else None
+        if tpk:
+            rec["traffic_source"] = tpk.get("source")
+        out[cls] = rec
+    return out
+
+
+def time_device_steps(ev, step, steps, warmup, dist, dev, sampler=None):
     import torch
 
     for _ in range(warmup):
-        (step or (lambda: ev.eigenval_device(k_dev, out=out_dev)))()
+        step()
     ev.check()
     ev.profile_read()  # drop warm-up records
     if dist is not None:
@@ -272,7 +450,7 @@ def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None, ste
     l0 = ev.launch_count
     e0.record()
     for _ in range(steps):
-        (step or (lambda: ev.eigenval_device(k_dev, out=out_dev)))()
+        step()
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -284,10 +462,179 @@ def time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler=None, ste
     prof = ev.profile_read()
     ev.check()
     if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=k_dev.device)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms, launches, prof
+
+
+def shard_k_device(workload, dims, total, lo, hi, dim, dev, seed_rank):
+    """Explicit k-points [lo, hi) of the workload's k-set, generated on the device (mesh points in C order, or the
+    rank's seeded random shard)."""
+    import torch
+
+    if dims is not None:
+        idx = torch.arange(lo, hi, device=dev, dtype=torch.int64)
+        cols = []
+        stride = 1
+        for d in reversed(range(len(dims))):
+            cols.append(((idx // stride) % dims[d]).double() / dims[d])
+            stride *= dims[d]
+        return torch.stack(list(reversed(cols)), dim=1).contiguous()
+    g = torch.Generator(device=dev).manual_seed(1234 + seed_rank)
+    return torch.rand((hi - lo, dim), dtype=torch.float64, device=dev, generator=g)
+
+
+def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=None, e2e_cap=None, use_mesh=False):
+    """Strong-scaling measurement of one workload: shard, evaluate, gather (world > 1), all inside the timed region."""
+    import torch
+
+    import tbmodels_b200 as tbk
+    from tbmodels_b200.sharded import shard_bounds
+
+    dist, dev, rank, world = ctx["dist"], ctx["dev"], ctx["rank"], ctx["world"]
+    cfg = WORKLOADS[workload]
+    dims = mesh_dims_for(total, cfg["dims"])
+    ev = tbk.Evaluator(packed, device=dev.index)
+    ev.profile(True)
+    fl = flops_per_k(packed)
+    if total % world:
+        raise SystemExit(f"{workload}: {total} k-points do not split evenly over {world} ranks")
+    lo, hi = shard_bounds(total, world, rank)
+    n_local = hi - lo
+    k_dev = shard_k_device(workload, dims, total, lo, hi, packed.dim, dev, rank)
+    out_dev = torch.empty((n_local, packed.size), dtype=torch.float64, device=dev)
+    gathered = torch.empty((total, packed.size), dtype=torch.float64, device=dev) if world > 1 else None
+    mesh_cfg = None
+    if use_mesh:
+        if dims is None:
+            raise SystemExit("--mesh needs a k-grid workload (c1, c3, c5)")
+        n_last = dims[-1]
+        if lo % n_last or hi % n_last:
+            raise SystemExit("--mesh: shard is not a whole number of mesh lines")
+        mesh_cfg = {"dims": list(dims), "lines_per_gpu": n_local // n_last, "factorised": bool(ev.mesh_factorised(dims))}
+        compute = lambda: ev.eigenval_mesh_device(dims, first_line=lo // n_last, n_lines=n_local // n_last, out=out_dev)  # noqa: E731
+    else:
+        compute = lambda: ev.eigenval_device(k_dev, out=out_dev)  # noqa: E731
+
+    def step():
+        compute()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+
+    ms, launches, prof = time_device_steps(ev, step, steps, warmup, dist, dev, sampler)
+    value = total * steps / (ms * 1e-3)
+
+    # gather time alone (same buffers), for the record
+    gather_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gathered, out_dev)
+        g1.record()
+        torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+
+    # ---- parity inside the bench: sorted + finite; the NCCL-gathered rows of EVERY rank's shard against a single-rank
+    # evaluation of the same k-points on this GPU (bit-exact: a k-point's bits do not depend on batch or shard) ----
+    chk = out_dev[:: max(1, n_local // 1000)]
+    assert bool(torch.isfinite(chk).all()) and bool((chk[:, 1:] >= chk[:, :-1]).all()), "bench output failed sanity check"
+    gather_checked = 0
+    if world > 1:
+        assert torch.equal(gathered[lo:hi], out_dev), "all-gather misplaced this rank's own shard"
+        m = min(256, n_local)
+        for r in range(world):
+            rlo, rhi = shard_bounds(total, world, r)
+            if dims is not None:
+                kr = shard_k_device(workload, dims, total, rlo, rlo + m, packed.dim, dev, r)
+            else:
+                kr = shard_k_device(workload, dims, total, rlo, rhi, packed.dim, dev, r)[:m].contiguous()
+            want = ev.eigenval_device(kr)
+            got = gathered[rlo : rlo + m]
+            if use_mesh:
+                scale = float(want.abs().max())
+                assert float((got - want).abs().max()) <= 1e-10 * scale, f"gathered shard of rank {r} differs from a local evaluation"
+            else:
+                assert torch.equal(got, want), f"gathered shard of rank {r} differs from a local evaluation (not bit-equal)"
+            gather_checked += m
+        ev.check()
+        ev.profile_read()
+
+    kern = kernel_rooflines(workload, prof, steps, n_local, fl, peaks, ev.path) if peaks else {}
+    dom = max(kern, key=lambda c: kern[c]["kernel_share_of_step"]) if kern else None
+    if dom in ("hk_phase", "mesh_lines") and "hk_gemm" in kern:
+        dom = "hk_gemm"
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside) ----
+    e2e_n = min(n_local, e2e_cap) if e2e_cap else n_local
+    k_host = tbk.pinned_empty((e2e_n, packed.dim))
+    k_host[:] = k_dev[:e2e_n].cpu().numpy()
+    out_host = tbk.pinned_empty((e2e_n, packed.size))
+    per_step_s = ms * 1e-3 / steps
+    e2e_steps = int(max(1, min(steps, 10, 20.0 / max(per_step_s, 1e-3))))
+    for _ in range(2 if per_step_s < 1.0 else 1):
+        ev.eigenval_array(k_host, out=out_host)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ev.eigenval_array(k_host, out=out_host)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    ref_rows = out_dev[:64].cpu().numpy()
+    if use_mesh:  # explicit k-points (e2e arm) vs the mesh entry point: same values to rounding, not the same bits
+        assert np.abs(out_host[:64] - ref_rows).max() <= 1e-10 * float(np.abs(ref_rows).max()), "mesh and explicit paths disagree"
+    else:
+        assert np.array_equal(out_host[:64], ref_rows), "host and device entry points disagree"
+    e2e = {
+        "value": world * e2e_n * e2e_steps / e2e_s,
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(e2e_n * packed.dim * 8),
+        "d2h_bytes_per_step": int(e2e_n * packed.size * 8),
+        "steps": e2e_steps,
+        "kpoints_per_gpu_per_step": e2e_n,
+        "api": "Evaluator.eigenval_array -> tbk_eigenval_host (pinned host buffers, chunked 3-stream pipeline); "
+               "every rank evaluates its shard into its own host buffer",
+    }
+    ev.profile_read()
+    res = {
+        "value": value,
+        "unit": UNIT,
+        "ms_per_step": ms / steps,
+        "steps": steps,
+        "warmup": warmup,
+        "kpoints_total": total,
+        "kpoints_per_gpu": n_local,
+        "path": ev.path,
+        "gpu_launches": int(launches),
+        "e2e": e2e,
+        "roofline": kern.get(dom),
+        "kernels": kern,
+        "kernel_ms_per_step": {c: v[0] / steps for c, v in prof.items() if v[1]},
+        "allgather_ms": gather_ms,
+        "gather_rows_checked": gather_checked,
+        "fl": fl,
+        "mesh": mesh_cfg,
+    }
+    ev.close()
+    del k_dev, out_dev, gathered, k_host, out_host
+    torch.cuda.empty_cache()
+    return res
+
+
+def l2_note(res, packed):
+    b = res["kpoints_per_gpu"] * res["fl"]["bytes"]
+    scratch = res["kpoints_per_gpu"] * 8.0 * packed.size**2 if res["path"].startswith("gemm") else 0
+    if b > 2 * 126e6 or scratch > 2 * 126e6:
+        return "not flushed: inputs + outputs + H(k) scratch per step exceed the 126 MB L2 many times"
+    return "not flushed: batch smaller than L2 (latency-bound parity config)"
 
 
 def run_gpu_arm(args) -> None:
@@ -310,250 +657,102 @@ def run_gpu_arm(args) -> None:
         dist = dist_mod
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; reporting n_gpus={world}", file=sys.stderr)
-
-    desc, nk_default, steps_d, warm_d, cpu_sample = WORKLOADS[args.workload]
-    n_k = args.nk or nk_default
-    steps = args.steps if args.steps is not None else steps_d
-    warmup = max(args.warmup if args.warmup is not None else warm_d, 3)
-    packed = build_model(args.workload)
-    ev = tbk.Evaluator(packed, device=local_rank)
-    ev.profile(True)
-    fl = flops_per_k(packed)
     dev = torch.device("cuda", local_rank)
+    ctx = {"dist": dist, "dev": dev, "rank": rank, "world": world}
+
+    cfg = WORKLOADS[args.workload]
+    total = args.nk or cfg["total"]
+    steps = args.steps if args.steps is not None else cfg["steps"]
+    warmup = max(args.warmup if args.warmup is not None else cfg["warmup"], 3)
+    packed = build_model(args.workload)
+    peaks = tbk.fp64_peaks() if not args.no_peaks else {"dmma": float("nan"), "dfma": float("nan")}
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.mark("run_start")
+    main = measure(args.workload, packed, total, steps, warmup, ctx, sampler, peaks, args.e2e_nk, use_mesh=args.mesh)
 
-    # ---- device-resident batch (synthetic k-points generated on the device, seeded per rank) ----
-    if args.workload == "c1":
-        k_dev = torch.from_numpy(host_kpoints("c1", n_k, 3)).to(dev)
-    else:
-        g = torch.Generator(device=dev).manual_seed(1234 + rank)
-        k_dev = torch.rand((n_k, packed.dim), dtype=torch.float64, device=dev, generator=g)
-    out_dev = torch.empty((n_k, packed.size), dtype=torch.float64, device=dev)
-    step = None
-    mesh_cfg = None
-    if args.mesh:
-        # the workload's k-grid through the mesh entry point: this rank's lines of the (world * L, n, n) mesh
-        if packed.dim != 3:
-            raise SystemExit("--mesh: only the 3-D k-grid workloads (c3, c5)")
-        n_last = 256 if n_k % (256 * 256) == 0 else 64
-        lines = n_k // n_last
-        if lines * n_last != n_k or lines % n_last != 0:
-            raise SystemExit(f"--mesh: n_k = {n_k} is not a whole number of {n_last} x {n_last} mesh planes")
-        planes = lines // n_last
-        dims = (world * planes, n_last, n_last)
-        mesh_cfg = {"dims": list(dims), "lines_per_gpu": lines, "factorised": bool(ev.mesh_factorised(dims))}
-        step = lambda: ev.eigenval_mesh_device(dims, first_line=rank * lines, n_lines=lines, out=out_dev)  # noqa: E731
-        # the same mesh points as an explicit array, for the end-to-end (host buffer) arm and the cross-check
-        idx = torch.arange(rank * n_k, (rank + 1) * n_k, device=dev, dtype=torch.int64)
-        k_dev = torch.stack([(idx // (n_last * n_last)).double() / dims[0], ((idx // n_last) % n_last).double() / n_last,
-                             (idx % n_last).double() / n_last], dim=1).contiguous()
-    ms, launches, prof = time_device_steps(ev, k_dev, out_dev, steps, warmup, dist, sampler, step)
-    value = world * n_k * steps / (ms * 1e-3)
+    def brief(res, workload, pk, with_cpu=True):
+        rec = {k: res[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "kpoints_total", "kpoints_per_gpu", "path",
+                                   "gpu_launches", "e2e", "roofline", "kernel_ms_per_step", "allgather_ms")}
+        rec["workload"] = f"{workload}: {WORKLOADS[workload]['desc']}"
+        if res.get("mesh"):
+            rec["mesh"] = res["mesh"]
+        if with_cpu and rank == 0 and world == 1 and not args.no_cpu:
+            rec["cpu_baseline"] = cpu_baseline_single(workload, pk, budget_s=4.0)
+        return rec
 
-    # spot parity inside the bench itself (tiny): sorted output, finite
-    chk = out_dev[:: max(1, n_k // 1000)]
-    assert bool(torch.isfinite(chk).all()) and bool((chk[:, 1:] >= chk[:, :-1]).all()), "bench output failed sanity check"
-
-    # ---- roofline of the dominant kernel (CUDA events around each launch, same timed region) ----
-    dom = max(prof, key=lambda c: prof[c][0])
-    dom_ms, dom_n = prof[dom]
-    total_prof_ms = sum(v[0] for v in prof.values())
-    per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
-    k_per_launch = n_k * steps / max(dom_n, 1)
-    hbm_peak, hbm_src = measured_hbm_peak()
-    peaks = tbk.fp64_peaks() if not args.no_peaks else {"dmma": float("nan"), "dfma": float("nan")}
-    if dom == "hk_phase":  # never dominant in practice; attribute it to the GEMM it feeds
-        dom = "hk_gemm"
-        dom_ms, dom_n = prof[dom]
-        per_launch_s = dom_ms * 1e-3 / max(dom_n, 1)
-        k_per_launch = n_k * steps / max(dom_n, 1)
-    if dom == "hk_small" or dom == "expand":
-        achieved = fl["bytes"] * k_per_launch / per_launch_s / 1e9
-        roofline = {
-            "kernel": "hk_basis (profile class hk_small)" if ev.path == "fused-product" else dom,
-            "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
-            "algorithmic_bytes_per_kpoint": fl["bytes"],
-            "note": "fp64 sincospi/FMA work per k-point is co-limiting; see DESIGN.md",
-        }
-    elif dom == "hk_gemm":
-        achieved = fl["F_H"] * k_per_launch / per_launch_s / 1e12
-        roofline = {
-            "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["dmma"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["dmma"], "traffic": None,
-            "peak_source": "tbk_measure_fp64_peak: mma.sync.m8n8k4.f64 register loop on this GPU in this run",
-            "algorithmic_flops_per_kpoint": fl["F_H"],
-            "executed_flops_per_kpoint": fl["F_H"] / 2.0,
-            "frac_executed": achieved / 2.0 / peaks["dmma"],
-            "note": "achieved/frac use the ALGORITHMIC flops of the reference formulation (8 n_R N^2 per k-point); the "
-            "Hermitian split executes half of them, so frac_executed (= ncu tensor-pipe utilisation, 89 %) is the "
-            "hardware utilisation and frac may legitimately reach 2.0",
-        }
-    else:
-        achieved = fl["F_eig"] * k_per_launch / per_launch_s / 1e12
-        roofline = {
-            "kernel": dom, "bound": "tensor", "achieved": achieved, "peak": peaks["dfma"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["dfma"], "traffic": None,
-            "peak_source": "tbk_measure_fp64_peak: DFMA register loop (the eigensolver runs on the FP64 FMA pipe)",
-            "algorithmic_flops_per_kpoint": fl["F_eig"],
-        }
-    tpk = NCU_TRAFFIC_PER_K.get((args.workload, dom))
-    if tpk is not None:
-        roofline["traffic"] = tpk * k_per_launch
-        roofline["traffic_source"] = NCU_TRAFFIC_SOURCE
-    roofline["kernel_share_of_step"] = dom_ms / max(total_prof_ms, 1e-12)
-    roofline["kernel_ms_per_launch"] = per_launch_s * 1e3
-
-    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory, copies inside) ----
-    e2e_nk = min(n_k, args.e2e_nk) if args.e2e_nk else n_k
-    k_host = tbk.pinned_empty((e2e_nk, packed.dim))
-    k_host[:] = k_dev[:e2e_nk].cpu().numpy()
-    out_host = tbk.pinned_empty((e2e_nk, packed.size))
-    e2e_steps = max(1, min(steps, 10))
-    for _ in range(2):
-        ev.eigenval_array(k_host, out=out_host)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ev.eigenval_array(k_host, out=out_host)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    if args.mesh:  # explicit k-points (e2e arm) vs the mesh entry point: same values to rounding, not the same bits
-        scale = float(np.abs(out_host[:64]).max())
-        assert np.abs(out_host[:64] - out_dev[:64].cpu().numpy()).max() <= 1e-10 * scale, "mesh and explicit paths disagree"
-    else:
-        assert np.array_equal(out_host[:64], out_dev[:64].cpu().numpy()), "host and device entry points disagree"
-    e2e = {
-        "value": world * e2e_nk * e2e_steps / e2e_s,
-        "unit": UNIT,
-        "h2d_bytes_per_step": int(e2e_nk * packed.dim * 8),
-        "d2h_bytes_per_step": int(e2e_nk * packed.size * 8),
-        "steps": e2e_steps,
-        "kpoints_per_gpu_per_step": e2e_nk,
-        "api": "Evaluator.eigenval_array -> tbk_eigenval_host (pinned host buffers, chunked 3-stream pipeline)",
-    }
-    ev.profile_read()
-
-    # ---- optional: NCCL all-gather of the eigenvalue shards (the API's exchange step, outside `value`) ----
     extra = {}
-    if dist is not None and packed.size * n_k * 8 * world <= 8 << 30:
-        gathered = torch.empty((world * n_k, packed.size), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered, out_dev)
-        torch.cuda.synchronize()
-        g0 = torch.cuda.Event(enable_timing=True)
-        g1 = torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.all_gather_into_tensor(gathered, out_dev)
-        g1.record()
-        torch.cuda.synchronize()
-        extra["allgather_ms"] = g0.elapsed_time(g1)
-        del gathered
-
-    # ---- extra: short C3 run for the FP64 tensor-core roofline of the H(k) GEMM ----
-    if args.workload == "c2" and not args.no_extra:
-        del k_dev, out_dev
-        torch.cuda.empty_cache()
-        p3 = build_model("c3")
-        ev3 = tbk.Evaluator(p3, device=local_rank)
-        ev3.profile(True)
-        nk3 = 2**19
-        g = torch.Generator(device=dev).manual_seed(99 + rank)
-        k3 = torch.rand((nk3, 3), dtype=torch.float64, device=dev, generator=g)
-        o3 = torch.empty((nk3, 36), dtype=torch.float64, device=dev)
-        ms3, l3, prof3 = time_device_steps(ev3, k3, o3, 3, 3, dist, None)
-        f3 = flops_per_k(p3)
-        gemm_s = prof3["hk_gemm"][0] * 1e-3
-        tf = f3["F_H"] * nk3 * 3 / gemm_s / 1e12
-        extra["c3"] = {
-            "workload": "c3: " + WORKLOADS["c3"][0].split(",")[0] + f", {nk3} k-points per GPU per step",
-            "value": world * nk3 * 3 / (ms3 * 1e-3),
-            "unit": UNIT,
-            "ms_per_step": ms3 / 3,
-            "kernel_ms": {c: v[0] / 3 for c, v in prof3.items() if v[1]},
-            "roofline": {
-                "kernel": "hk_gemm", "bound": "tensor", "achieved": tf, "peak": peaks["dmma"], "unit": "TFLOP/s",
-                "frac": tf / peaks["dmma"], "traffic": None,
-                "algorithmic_flops_per_kpoint": f3["F_H"],
-                "executed_flops_per_kpoint": f3["F_H"] / 2.0,
-                "frac_executed": tf / 2.0 / peaks["dmma"],
-                "note": "frac counts the algorithmic flops of the reference formulation; the Hermitian split executes "
-                "half of them (frac_executed = hardware tensor-pipe utilisation, 89 % in ncu)",
-                "peak_source": "tbk_measure_fp64_peak (DMMA register loop, this GPU, this run)",
-            },
-        }
-        # the same model on its k-grid (this rank's 8 planes of a 256 x 256-per-plane mesh) through the mesh entry point
-        dims3 = (world * 8, 256, 256)
-        lines3 = 8 * 256
-        step3 = lambda: ev3.eigenval_mesh_device(dims3, first_line=rank * lines3, n_lines=lines3, out=o3)  # noqa: E731
-        ms3m, l3m, prof3m = time_device_steps(ev3, k3, o3, 3, 3, dist, None, step3)
-        extra["c3_kgrid"] = {
-            "workload": f"c3 model on a {dims3} k-grid via eigenval_mesh (factorised over the last dimension), "
-                        f"{nk3} k-points per GPU per step",
-            "value": world * nk3 * 3 / (ms3m * 1e-3),
-            "unit": UNIT,
-            "ms_per_step": ms3m / 3,
-            "kernel_ms": {c: v[0] / 3 for c, v in prof3m.items() if v[1]},
-        }
-        launches_extra = l3 + l3m
-        ev3.close()
+    if not args.no_extra and args.workload == "c3" and not args.mesh and args.nk is None:
+        # C3 as a k-grid through the mesh entry point (no k array; Fourier sum factorised over the last dimension)
+        r = measure("c3", packed, total, steps, 3, ctx, None, peaks, args.e2e_nk, use_mesh=True)
+        extra["c3_kgrid"] = brief(r, "c3", packed, with_cpu=False)
+        extra["c3_kgrid"]["workload"] += " via eigenval_mesh"
+        # C5: N_k sweep of the strong-scaling configuration (explicit k-points of 2^m-point meshes)
+        p5 = build_model("c5")
+        sweep = {}
+        for e in (14, 16, 18, 20):
+            if (1 << e) % world:
+                continue
+            r = measure("c5", p5, 1 << e, 3 if e <= 16 else 1, 3 if e <= 16 else 1, ctx, None, peaks, 1 << 14)
+            sweep[f"2^{e}"] = {k: r[k] for k in ("value", "ms_per_step", "kpoints_per_gpu", "kernel_ms_per_step", "allgather_ms", "steps", "warmup")}
+            if e == 14 or (e == 16 and "c5" not in extra):
+                extra["c5"] = brief(r, "c5", p5, with_cpu=(e == 14))
+        extra["c5_sweep"] = {"workload": "c5: " + WORKLOADS["c5"]["desc"].split(",")[0] + ", N_k = 2^14 .. 2^20 (total, strong scaling)",
+                             "unit": UNIT, "points": sweep}
+        del p5
+        if world == 1:
+            for name, tot, st, wu in (("c2", 10**8, 20, 5), ("c1", 8000, 50, 5), ("c4", 12500, 2, 1)):
+                pk = build_model(name)
+                r = measure(name, pk, tot, st, wu, ctx, None, peaks, None)
+                extra[name] = brief(r, name, pk)
+                if name == "c4":
+                    extra[name]["workload"] += " -- 12 500 of them per step (one GPU's share of the 8-GPU configuration)"
+                del pk
     sampler.mark("run_end")
     clocks = sampler.stop()
 
-    # ---- CPU baseline: the oracle port on this box's host cores (rank 0, N = 1 only) ----
+    # ---- CPU baseline: the reference on this box's host cores (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        ks = host_kpoints(args.workload, min(cpu_sample, n_k), packed.dim, seed=1)
-        rate = cpu_reference_rate(packed, ks, 1)
-        cpu = {
-            "value": rate,
-            "unit": UNIT,
-            "cores": 1,
-            "kind": "port",
-            "sample": f"{ks.shape[0]} k-points of the same workload, numpy/scipy oracle port of Model.eigenval, "
-            f"single process as the reference ships (host has {os.cpu_count()} cores)",
-        }
+        cpu = cpu_baseline_single(args.workload, packed, budget_s=10.0)
 
     if rank == 0:
         line = {
             "metric": METRIC,
-            "value": value,
+            "value": main["value"],
             "unit": UNIT,
             "n_gpus": world,
             "steps": steps,
             "warmup": warmup,
-            "ms_per_step": ms / steps,
+            "ms_per_step": main["ms_per_step"],
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": f"{args.workload}: {desc}",
-                "kpoints_per_gpu": n_k,
+                "workload": f"{args.workload}: {cfg['desc']}",
+                "kpoints_total": main["kpoints_total"],
+                "kpoints_per_gpu": main["kpoints_per_gpu"],
                 "n_orb": packed.size,
                 "n_R_stored": packed.n_R,
                 "dim": packed.dim,
-                "path": ev.path,
-                "parallelism": f"k-shards x{world}, no data-path collective",
-                "l2": "inputs+outputs per step exceed the 126 MB L2" if n_k * fl["bytes"] > 2 * 126e6 else "L2 not flushed: batch smaller than L2 (latency-bound parity config)",
-                **({"mesh": mesh_cfg} if mesh_cfg else {}),
+                "path": main["path"],
+                "parallelism": f"contiguous k-shards x{world}" + (", NCCL all_gather_into_tensor of the eigenvalue shards inside the timed region" if world > 1 else ""),
+                "l2": l2_note(main, packed),
+                **({"mesh": main["mesh"]} if main.get("mesh") else {}),
             },
             "clocks": clocks,
-            "e2e": e2e,
-            "gpu_launches": int(launches),
-            "roofline": roofline,
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
+            "roofline": main["roofline"],
+            "kernels": main["kernels"],
             "cpu_baseline": cpu,
             "fp64_peak_tflops": peaks,
-            "kernel_ms_per_step": {c: v[0] / steps for c, v in prof.items() if v[1]},
+            "kernel_ms_per_step": main["kernel_ms_per_step"],
+            "allgather_ms": main["allgather_ms"],
+            "gather_rows_checked_bit_exact": main["gather_rows_checked"],
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -568,13 +767,13 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
-    ap.add_argument("--nk", type=int, default=None, help="k-points per GPU per step (default: the workload's)")
-    ap.add_argument("--e2e-nk", type=int, default=None, help="cap the k-points per e2e step")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    ap.add_argument("--nk", type=int, default=None, help="TOTAL k-points per step over all GPUs (default: the configuration's)")
+    ap.add_argument("--e2e-nk", type=int, default=None, help="cap the k-points per GPU of an e2e step")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
-    ap.add_argument("--mesh", action="store_true", help="c3 / c5: evaluate the workload's k-grid through eigenval_mesh")
+    ap.add_argument("--mesh", action="store_true", help="c1 / c3 / c5: evaluate the workload's k-grid through eigenval_mesh")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -6,6 +6,7 @@ fill-value messages and by the round trip through the reader.
 """
 import glob
 import os
+import pathlib
 import struct
 
 import numpy as np
@@ -80,7 +81,7 @@ def test_writer_round_trip(tmp_path):
 
 
 def _messages(path, *names):
-    data = open(path, "rb").read()
+    data = pathlib.Path(path).read_bytes()
     r = _h5lite._Reader(data)
     addr = r.root_header
     for n in names:
@@ -98,7 +99,7 @@ def test_writer_emits_the_messages_h5py_emits(tmp_path):
     for names in (("pos",), ("uc",), ("size",), ("sparse",), ("type_tag",), ("hop", "0", "mat"), ("hop", "0", "R")):
         assert _messages(mine, *names) == _messages(ref_model, *names), names
     # superblock: same version, offset / length sizes and group B-tree parameters
-    a, b = open(mine, "rb").read(24), open(ref_model, "rb").read(24)
+    a, b = pathlib.Path(mine).read_bytes()[:24], pathlib.Path(ref_model).read_bytes()[:24]
     assert a == b
     assert _tree_equal(tree, _h5lite.load(mine))
 
@@ -215,7 +216,7 @@ def test_writer_large_groups_use_multi_level_btrees(tmp_path, n_links):
     back = _h5lite.load(path)
     assert set(back["hop"]) == set(tree["hop"])
     assert all(np.array_equal(back["hop"][k]["R"], tree["hop"][k]["R"]) for k in tree["hop"])
-    data = open(path, "rb").read()
+    data = pathlib.Path(path).read_bytes()
     r = _h5lite._Reader(data)
     hop = r.links(r.messages(r.root_header))["hop"]
     bt = next(struct.unpack_from("<Q", data, b)[0] for t, b, _ in r.messages(hop) if t == 0x0011)
@@ -272,7 +273,7 @@ def test_loader_reads_csr_hoppings(tmp_path):
 
 
 def test_truncated_and_corrupt_files_raise_h5error(tmp_path):
-    data = open(os.path.join(CLI, "kpoints.hdf5"), "rb").read()
+    data = pathlib.Path(os.path.join(CLI, "kpoints.hdf5")).read_bytes()
     for cut in (100, 700, 2100, len(data) - 3000):
         f = tmp_path / f"cut{cut}.hdf5"
         f.write_bytes(data[:cut])

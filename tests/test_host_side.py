@@ -35,7 +35,8 @@ def test_library_exports_every_declared_symbol():
     from tbmodels_b200 import _capi
 
     lib = _lib()
-    header = open(os.path.join(ROOT, "include", "tbk.h")).read()
+    with open(os.path.join(ROOT, "include", "tbk.h")) as fh:
+        header = fh.read()
     declared = set(re.findall(r"\b(tbk_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_capi.SYMBOLS)
     for name in declared:
