@@ -84,6 +84,20 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
                       double* out_dev, void* stream);
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims);
 
+/* Model.construct_kdotp (reference src/tbmodels/_tb_model.py:942-982), batched over expansion points: the Taylor
+ * coefficients C_p = (2 pi i)^|p| / p! * sum_R [R^p e^{2 pi i k.R} T_R + (-R)^p e^{-2 pi i k.R} T_R^H] of H around k
+ * (convention 2), the same Fourier sum as tbk_hamilton with R^p weights.
+ *   k_dev   [n_k][dim]                       f64    device: expansion points
+ *   powers  [n_terms][dim]                   int32  HOST: the power tuples p (keys of KdotpModel.taylor_coefficients),
+ *                                                   each component in [0, 64]
+ *   out_dev [n_k][n_terms][n_orb][n_orb]     c128   device: exactly Hermitian matrices
+ * Not defined for handles made by tbk_kdotp_create (TBK_E_INVALID). */
+int tbk_kdotp_coefficients(tbk_model* m, const double* k_dev, int64_t n_k, const int32_t* powers, int n_terms,
+                           double* out_dev, void* stream);
+/* Same with HOST buffers for k and out (synchronous on return). */
+int tbk_kdotp_coefficients_host(tbk_model* m, const double* k_host, int64_t n_k, const int32_t* powers, int n_terms,
+                                double* out_host);
+
 /* Same two operations with HOST buffers (copies inside, synchronous on return). */
 int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host);
 int tbk_eigenval_host(tbk_model* m, const double* k_host, int64_t n_k, double* out_host);

@@ -95,6 +95,36 @@ def eigenval_array(R, hop, pos, k, chunk=4096):
     return out
 
 
+def construct_kdotp(R, hop, pos, k, order):
+    """Restates ``Model.construct_kdotp`` (reference src/tbmodels/_tb_model.py:942-982) on the packed arrays: the
+    ``taylor_coefficients`` dict ``{power tuple: matrix}`` of the k.p expansion of the convention-2 Hamiltonian at ``k``,
+    every operation in the reference's order (``pos`` is not used: convention 2)."""
+    import itertools
+
+    from scipy.special import factorial
+
+    if order < 0:
+        raise ValueError("The order for the k.p model must be positive.")
+    R = np.asarray(R)
+    hop = np.asarray(hop)
+    size = hop.shape[1] if hop.ndim == 3 and hop.shape[0] else np.asarray(pos).shape[0]
+    dim = R.shape[1] if R.ndim == 2 and R.shape[0] else np.asarray(pos).shape[1]
+    taylor_coefficients = dict()
+    for k_powers in itertools.product(range(order + 1), repeat=dim):
+        curr_order = sum(k_powers)
+        if curr_order > order:
+            continue
+        taylor_coefficients[k_powers] = ((2j * np.pi) ** curr_order / np.prod(factorial(k_powers, exact=True))) * sum(
+            (
+                np.prod(np.array(Rv) ** np.array(k_powers)) * np.exp(2j * np.pi * np.dot(k, Rv)) * mat
+                + np.prod((-np.array(Rv)) ** np.array(k_powers)) * np.exp(-2j * np.pi * np.dot(k, Rv)) * mat.T.conj()
+                for Rv, mat in zip(R, hop)
+            ),
+            np.zeros((size, size), dtype=complex),
+        )
+    return taylor_coefficients
+
+
 def kdotp_hamilton(taylor_coefficients, k):
     """Restates ``KdotpModel.hamilton`` (reference src/tbmodels/kdotp.py:51-82): sum over the Taylor terms of
     ``prod(k**powers) * C`` in dict order."""

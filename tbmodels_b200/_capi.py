@@ -24,6 +24,8 @@ SYMBOLS = (
     "tbk_eigenval",
     "tbk_eigenval_mesh",
     "tbk_mesh_factorised",
+    "tbk_kdotp_coefficients",
+    "tbk_kdotp_coefficients_host",
     "tbk_hamilton_host",
     "tbk_eigenval_host",
     "tbk_model_check",
@@ -87,6 +89,10 @@ def load() -> C.CDLL:
     lib.tbk_eigenval_mesh.restype = C.c_int
     lib.tbk_mesh_factorised.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.tbk_mesh_factorised.restype = C.c_int
+    lib.tbk_kdotp_coefficients.argtypes = [vp, vp, C.c_int64, vp, C.c_int, vp, vp]
+    lib.tbk_kdotp_coefficients.restype = C.c_int
+    lib.tbk_kdotp_coefficients_host.argtypes = [vp, vp, C.c_int64, vp, C.c_int, vp]
+    lib.tbk_kdotp_coefficients_host.restype = C.c_int
     lib.tbk_hamilton_host.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
     lib.tbk_hamilton_host.restype = C.c_int
     lib.tbk_eigenval_host.argtypes = [vp, vp, C.c_int64, vp]

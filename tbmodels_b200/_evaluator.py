@@ -51,6 +51,14 @@ def _normalise_k(k, dim: int):
     return np.ascontiguousarray(k_array, dtype=np.float64), single_point
 
 
+def kdotp_powers(dim: int, order: int) -> np.ndarray:
+    """Power tuples of a k.p expansion up to ``order`` in the reference's order (:963-966)."""
+    import itertools
+
+    keys = [p for p in itertools.product(range(order + 1), repeat=dim) if sum(p) <= order]
+    return np.array(keys, dtype=np.int32).reshape(len(keys), dim)
+
+
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     """Uninitialised page-locked numpy array (fast path of the host entry points); freed with the array."""
     lib = _capi.load()
@@ -260,6 +268,57 @@ class Evaluator:
         if single_point:
             return res[0]
         return list(res)
+
+    # ------------------------------------------------------------------ k.p expansion (Model.construct_kdotp)
+    def kdotp_coefficients(self, k, order: int):
+        """Taylor coefficients of ``Model.construct_kdotp(k, order)`` (reference src/tbmodels/_tb_model.py:942-982).
+
+        Returns ``(powers, coeff)``: the power tuples in the reference's dict order
+        (``itertools.product(range(order + 1), repeat=dim)`` filtered by ``sum <= order``) as int32 ``[n_terms, dim]`` and
+        the matrices as complex128 ``[n_terms, N, N]`` -- or ``[n_k, n_terms, N, N]`` when ``k`` is a list of expansion
+        points (a batched extension; the reference takes a single point)."""
+        if order < 0:
+            raise ValueError("The order for the k.p model must be positive.")
+        k_array, single_point = _normalise_k(k, self.dim)
+        powers = np.ascontiguousarray(kdotp_powers(self.dim, int(order)))
+        n_k, n_terms = k_array.shape[0], powers.shape[0]
+        out = np.empty((n_k, n_terms, self.size, self.size), dtype=np.complex128)
+        _capi.check(
+            self._lib.tbk_kdotp_coefficients_host(
+                self._handle, k_array.ctypes.data_as(C.c_void_p), n_k, powers.ctypes.data_as(C.c_void_p), n_terms,
+                out.ctypes.data_as(C.c_void_p),
+            )
+        )
+        return powers, (out[0] if single_point else out)
+
+    def construct_kdotp(self, k, order: int) -> dict:
+        """``{power tuple: matrix}`` -- the ``taylor_coefficients`` argument of ``KdotpModel`` -- for ONE expansion point."""
+        k_array, single_point = _normalise_k(k, self.dim)
+        if not single_point:
+            raise ValueError("construct_kdotp expands around a single k-point")
+        powers, coeff = self.kdotp_coefficients(k_array[0], order)
+        return {tuple(int(x) for x in p): coeff[i] for i, p in enumerate(powers)}
+
+    def kdotp_coefficients_device(self, k_dev, order: int, out=None):
+        """Device-buffer form: ``[n_k, dim]`` float64 CUDA tensor -> ``(powers, [n_k, n_terms, N, N] complex128 tensor)``."""
+        import torch
+
+        if order < 0:
+            raise ValueError("The order for the k.p model must be positive.")
+        k_dev = self._check_k_dev(k_dev)
+        powers = np.ascontiguousarray(kdotp_powers(self.dim, int(order)))
+        shape = (k_dev.shape[0], powers.shape[0], self.size, self.size)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.complex128, device=k_dev.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.complex128 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous complex128 tensor [n_k, n_terms, N, N]")
+        _capi.check(
+            self._lib.tbk_kdotp_coefficients(
+                self._handle, C.c_void_p(k_dev.data_ptr()), shape[0], powers.ctypes.data_as(C.c_void_p), shape[1],
+                C.c_void_p(out.data_ptr()), self._stream(),
+            )
+        )
+        return powers, out
 
     # ------------------------------------------------------------------ device buffers (torch tensors as allocators)
     def _stream(self):

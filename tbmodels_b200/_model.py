@@ -72,3 +72,9 @@ class KModel:
     def eigenval(self, k):
         """Same contract as ``tbmodels.Model.eigenval`` (reference :1134-1150)."""
         return self.evaluator().eigenval(k)
+
+    def construct_kdotp(self, k, order: int):
+        """Same contract as ``tbmodels.Model.construct_kdotp`` (reference :942-982); returns a :class:`KdotpModel`."""
+        from ._kdotp import KdotpModel
+
+        return KdotpModel(self.evaluator().construct_kdotp(k, order), device=self._device)

@@ -64,6 +64,20 @@ def _eigenval(self, k):
     return evaluator_for(self).eigenval(k)
 
 
+def _construct_kdotp(self, k, order):
+    """GPU version of ``Model.construct_kdotp`` (reference :942-982): same result type -- the ``KdotpModel`` class of
+    the package the model class comes from (``tbmodels.kdotp.KdotpModel``), else this package's duck-type."""
+    import sys
+
+    if order < 0:
+        raise ValueError("The order for the k.p model must be positive.")
+    coeff = evaluator_for(self).construct_kdotp(k, order)
+    kdotp_cls = getattr(sys.modules.get(type(self).__module__), "KdotpModel", None)
+    if kdotp_cls is None:
+        from ._kdotp import KdotpModel as kdotp_cls
+    return kdotp_cls(taylor_coefficients=coeff)
+
+
 def _kdotp_hamilton(self, k):
     from ._kdotp import kdotp_evaluator_for
 
@@ -109,11 +123,15 @@ def install(model_cls=None, device=None):
             pass
     _device = device
     if model_cls not in _originals:
-        _originals[model_cls] = (model_cls.__dict__.get("hamilton"), model_cls.__dict__.get("eigenval"))
+        _originals[model_cls] = (model_cls.__dict__.get("hamilton"), model_cls.__dict__.get("eigenval"),
+                                 model_cls.__dict__.get("construct_kdotp"))
     _hamilton.__doc__ = getattr(_originals[model_cls][0], "__doc__", None)
     _eigenval.__doc__ = getattr(_originals[model_cls][1], "__doc__", None)
     model_cls.hamilton = _hamilton
     model_cls.eigenval = _eigenval
+    if _originals[model_cls][2] is not None:  # only where the class has the method (reference :942)
+        _construct_kdotp.__doc__ = getattr(_originals[model_cls][2], "__doc__", None)
+        model_cls.construct_kdotp = _construct_kdotp
     return model_cls
 
 
@@ -124,9 +142,9 @@ def uninstall(model_cls=None):
         orig = _originals.pop(cls, None)
         if orig is None:
             continue
-        for name, fn in zip(("hamilton", "eigenval"), orig):
+        for name, fn in zip(("hamilton", "eigenval", "construct_kdotp"), orig):
             if fn is None:
-                if name in cls.__dict__:
+                if name in cls.__dict__ and (name != "construct_kdotp" or cls.__dict__[name] is _construct_kdotp):
                     delattr(cls, name)
             else:
                 setattr(cls, name, fn)

@@ -144,7 +144,8 @@ struct tbk_model {
     double* wsAB = nullptr;   // [lines][2 nclass][n*n] line coefficients (stage A output)
     double* wsQz = nullptr;   // [n_z][2 nclass] cos / sin along the last mesh dimension
     double* wsK = nullptr;    // explicit k-points of a mesh range (ordinary-path fallback)
-    size_t ab_bytes = 0, qz_bytes = 0, k_bytes = 0;
+    double* wsKp = nullptr;   // construct_kdotp: [n_terms] prefactors followed by the int powers [n_terms][dim]
+    size_t ab_bytes = 0, qz_bytes = 0, k_bytes = 0, kp_bytes = 0;
     long chunk = 0;
     size_t ws_bytes = 0;
     size_t model_bytes = 0;
@@ -364,6 +365,37 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
             LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
         }
         LAUNCH(2, st, launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
+    }
+    return TBK_OK;
+}
+
+// Model.construct_kdotp (reference _tb_model.py:942-982): prefactors on the host, everything else in one kernel.
+int run_kdotp_coeff(tbk_model* m, const double* k, long nk, const int32_t* powers, int n_terms, double* out, cudaStream_t st) {
+    const ModelDev& md = m->md;
+    if (nk <= 0 || n_terms <= 0) return TBK_OK;
+    const size_t fb = (size_t)n_terms * 8, pb = (size_t)n_terms * md.dim * sizeof(int);
+    if (int rc = grow(&m->wsKp, &m->kp_bytes, fb + pb)) return rc;
+    std::vector<double> stage((fb + pb + 7) / 8, 0.0);
+    for (int t = 0; t < n_terms; ++t) {
+        int order = 0;
+        double f = 1.0;
+        for (int d = 0; d < md.dim; ++d) {
+            const int p = powers[(size_t)t * md.dim + d];
+            order += p;
+            for (int q = 2; q <= p; ++q) f /= (double)q;  // 1 / p_d!
+        }
+        for (int q = 0; q < order; ++q) f *= 2.0 * 3.14159265358979323846;
+        const int flips = (order & 1) ? (order + 1) / 2 : order / 2;  // i^|p| (even) or i^(|p|+1) (odd) = (-1)^flips
+        stage[t] = (flips & 1) ? -f : f;
+    }
+    memcpy(reinterpret_cast<char*>(stage.data()) + fb, powers, pb);
+    // pageable source: the copy is staged by the driver before the call returns, so `stage` may go out of scope
+    CU(cudaMemcpyAsync(m->wsKp, stage.data(), fb + pb, cudaMemcpyHostToDevice, st));
+    const int* dpw = reinterpret_cast<const int*>(reinterpret_cast<const char*>(m->wsKp) + fb);
+    for (long c0 = 0; c0 < nk; c0 += 32768) {
+        const long cn = std::min<long>(32768, nk - c0);
+        LAUNCH(2, st, launch_kdotp_coeff(md, k + c0 * md.dim, cn, dpw, m->wsKp, n_terms,
+                                         out + (size_t)c0 * n_terms * md.n * md.n * 2, st));
     }
     return TBK_OK;
 }
@@ -683,6 +715,7 @@ int tbk_model_destroy(tbk_model* m) {
     cudaFree(m->wsAB);
     cudaFree(m->wsQz);
     cudaFree(m->wsK);
+    cudaFree(m->wsKp);
     for (int b = 0; b < 2; ++b) {
         cudaFree(m->hk[b]);
         cudaFree(m->ho[b]);
@@ -752,6 +785,55 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims) {
     if (!m || !dims) return 0;
     return mesh_factorised(m, dims) ? 1 : 0;
+}
+
+static int kdotp_args_ok(tbk_model* m, const void* k, int64_t n_k, const int32_t* powers, int n_terms, const void* out,
+                         const char* who) {
+    if (!m) return fail(TBK_E_INVALID, "%s: null handle", who);
+    if (m->md.kind != 0) return fail(TBK_E_INVALID, "%s: the handle is a k.p model (construct_kdotp is a Model method)", who);
+    if (n_k < 0 || n_terms < 0 || (n_k > 0 && n_terms > 0 && (!k || !out || !powers)))
+        return fail(TBK_E_INVALID, "%s: bad buffers", who);
+    if (n_terms > 65535) return fail(TBK_E_UNSUPPORTED, "%s: %d Taylor terms (limit 65535)", who, n_terms);
+    if ((size_t)2 * m->md.nR * 8 > 200 * 1024) return fail(TBK_E_UNSUPPORTED, "%s: %d stored R vectors (limit 12800)", who, m->md.nR);
+    for (long i = 0; i < (long)n_terms * m->md.dim; ++i)
+        if (powers[i] < 0 || powers[i] > 64) return fail(TBK_E_INVALID, "%s: powers must be in [0, 64]", who);
+    return TBK_OK;
+}
+
+int tbk_kdotp_coefficients(tbk_model* m, const double* k_dev, int64_t n_k, const int32_t* powers, int n_terms,
+                           double* out_dev, void* stream) {
+    if (int rc = kdotp_args_ok(m, k_dev, n_k, powers, n_terms, out_dev, "tbk_kdotp_coefficients")) return rc;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
+    if (int rc = run_kdotp_coeff(m, k_dev, (long)n_k, powers, n_terms, out_dev, (cudaStream_t)stream)) return rc;
+    return scratch_release(m, (cudaStream_t)stream);
+}
+
+int tbk_kdotp_coefficients_host(tbk_model* m, const double* k_host, int64_t n_k, const int32_t* powers, int n_terms,
+                                double* out_host) {
+    if (int rc = kdotp_args_ok(m, k_host, n_k, powers, n_terms, out_host, "tbk_kdotp_coefficients_host")) return rc;
+    if (n_k == 0 || n_terms == 0) return TBK_OK;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = ensure_pipeline(m, 0, 0)) return rc;
+    const size_t kb = (size_t)n_k * m->md.dim * 8, ob = (size_t)n_k * n_terms * m->md.n * m->md.n * 16;
+    double *dk = nullptr, *dout = nullptr;
+    CU(cudaMalloc(&dk, kb));
+    if (cudaMalloc(&dout, ob) != cudaSuccess) {
+        cudaFree(dk);
+        return fail(TBK_E_CUDA, "tbk_kdotp_coefficients_host: cannot allocate %zu bytes of device memory", ob);
+    }
+    int rc = scratch_acquire(m, m->s_comp);
+    if (!rc) rc = cudaMemcpyAsync(dk, k_host, kb, cudaMemcpyHostToDevice, m->s_comp) == cudaSuccess ? TBK_OK : fail(TBK_E_CUDA, "H2D copy failed");
+    if (!rc) rc = run_kdotp_coeff(m, dk, (long)n_k, powers, n_terms, dout, m->s_comp);
+    if (!rc) rc = cudaMemcpyAsync(out_host, dout, ob, cudaMemcpyDeviceToHost, m->s_comp) == cudaSuccess ? TBK_OK : fail(TBK_E_CUDA, "D2H copy failed");
+    if (!rc) rc = scratch_release(m, m->s_comp);
+    const cudaError_t e = cudaStreamSynchronize(m->s_comp);
+    cudaFree(dk);
+    cudaFree(dout);
+    if (!rc && e != cudaSuccess) rc = fail(TBK_E_CUDA, "tbk_kdotp_coefficients_host: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 int tbk_hamilton_host(tbk_model* m, const double* k_host, int64_t n_k, int convention, double* out_host) {

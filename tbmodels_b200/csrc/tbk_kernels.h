@@ -81,6 +81,10 @@ size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);
 // packed H -> full complex128 [nk][n][n]; convention 1 applies the orbital-position phases.
 cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention,
                           double* out, cudaStream_t st);
+// Taylor coefficients of Model.construct_kdotp (kdotp_construct.cu): out [nk][n_terms][n][n] c128; powers [n_terms][dim]
+// and fac [n_terms] (the real prefactor of every term) are device arrays.
+cudaError_t launch_kdotp_coeff(const ModelDev& md, const double* k, long nk, const int* powers, const double* fac,
+                               int n_terms, double* out, cudaStream_t st);
 // Regular k-mesh path (hk_mesh.cu): lines along the last mesh dimension; see the file header.
 cudaError_t launch_mesh_phase(const ModelDev& m, const int64_t* dims, const double* shift, long line0, long n_lines,
                               double* Qt, cudaStream_t st);

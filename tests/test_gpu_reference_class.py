@@ -39,12 +39,13 @@ def ref():
     tb = ref_shim.import_reference()
     import tbmodels_b200 as tbk
 
-    orig = (tb.Model.hamilton, tb.Model.eigenval, tb.kdotp.KdotpModel.hamilton, tb.kdotp.KdotpModel.eigenval)
+    orig = (tb.Model.hamilton, tb.Model.eigenval, tb.kdotp.KdotpModel.hamilton, tb.kdotp.KdotpModel.eigenval,
+            tb.Model.construct_kdotp)
     tbk.install()
-    assert tb.Model.hamilton is not orig[0] and tb.Model.eigenval is not orig[1]
+    assert tb.Model.hamilton is not orig[0] and tb.Model.eigenval is not orig[1] and tb.Model.construct_kdotp is not orig[4]
     yield tb, orig
     tbk.uninstall()
-    assert tb.Model.hamilton is orig[0] and tb.Model.eigenval is orig[1]
+    assert tb.Model.hamilton is orig[0] and tb.Model.eigenval is orig[1] and tb.Model.construct_kdotp is orig[4]
 
 
 def get_model(tb, t1, t2, sparse, **kwargs):
@@ -170,10 +171,22 @@ def test_kdotp_model(ref):
     """``Model.construct_kdotp`` (reference :942-982) -> real ``KdotpModel`` -> installed GPU methods (kdotp.py:51-100)."""
     tb, orig = ref
     model = get_model(tb, 0.2, 0.5, sparse=False)
+    with strict():
+        kp = model.construct_kdotp((0.1, 0.2, 0.3), order=3)  # the installed GPU version
+    assert isinstance(kp, tb.kdotp.KdotpModel)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        kp = model.construct_kdotp((0.1, 0.2, 0.3), order=3)
-    assert isinstance(kp, tb.kdotp.KdotpModel)
+        kp_ref = orig[4](model, (0.1, 0.2, 0.3), order=3)  # the reference's numpy version
+    assert list(kp.taylor_coefficients) == list(kp_ref.taylor_coefficients)
+    for key, want in kp_ref.taylor_coefficients.items():
+        assert np.abs(kp.taylor_coefficients[key] - want).max() <= 1e-11 * (2 * np.pi) ** sum(key)
+    with pytest.raises(ValueError):
+        model.construct_kdotp((0.1, 0.2, 0.3), order=-1)
+    sparse_model = get_model(tb, 0.2, 0.5, sparse=True)
+    with strict():
+        kp_sparse = sparse_model.construct_kdotp((0.1, 0.2, 0.3), order=2)
+    for key, want in kp_sparse.taylor_coefficients.items():
+        assert np.array_equal(want, kp.taylor_coefficients[key])
     k = np.array([[0.01, -0.02, 0.03], [0.0, 0.0, 0.0], [0.05, 0.04, -0.01]])
     with strict():
         h = kp.hamilton(k)

@@ -153,6 +153,49 @@ def test_kdotp_golden():
     assert np.allclose(orc.kdotp_eigenval(tc, [(0, 0), (0, 0), (0, 0.5)]), [[1, 1], [1, 1], [0.75, 1.25]])
 
 
+KDOTP_CASES = ["haldane", "silicon", "simple3d", "syn12", "syn2d", "syn36", "syn5"]
+
+
+def test_construct_kdotp_golden():
+    """Model.construct_kdotp restatement (reference :942-982) against the reference's output: same operations in the
+    same order, so the coefficients are bit-equal; the constructed model's eigenvalues within the parity bound."""
+    d = load_golden("construct_kdotp.npz")
+    assert sorted(d["names"]) == KDOTP_CASES
+    for name in KDOTP_CASES:
+        order = int(d[f"{name}_order"])
+        for i, k in enumerate(d[f"{name}_k"]):
+            tc = orc.construct_kdotp(d[f"{name}_R"], d[f"{name}_hop"], d[f"{name}_pos"], k, order)
+            assert np.array_equal(np.array(list(tc), dtype=np.int32), d[f"{name}_powers"])
+            assert np.array_equal(np.stack(list(tc.values())), d[f"{name}_coeff{i}"]), (name, i)
+            assert_eig_close(np.array(orc.kdotp_eigenval(tc, d[f"{name}_dk{i}"])), d[f"{name}_eig{i}"], name)
+    with pytest.raises(ValueError):
+        orc.construct_kdotp(d["syn5_R"], d["syn5_hop"], d["syn5_pos"], (0, 0, 0), -1)  # reference :961-962
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree only exists in the build container")
+def test_construct_kdotp_equals_live_reference():
+    import warnings
+
+    from tbmodels_b200 import pack_model
+
+    warnings.simplefilter("ignore")
+    tb = import_reference()
+    rng = np.random.default_rng(6)
+    hop = {R: rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3)) for R in [(0, 0), (1, 0), (0, 2), (2, -3)]}
+    m = tb.Model(hop=hop, pos=rng.random((3, 2)), contains_cc=False)
+    p = pack_model(m)
+    k = (0.37, -1.2)
+    want = m.construct_kdotp(k, 3).taylor_coefficients
+    got = orc.construct_kdotp(p.R, p.hop, p.pos, k, 3)
+    assert list(want) == list(got)
+    for key in want:
+        assert np.array_equal(want[key], got[key])
+    # the Taylor series reproduces H(k + dk) to the truncation order (what the reference tests check, tests/test_kdotp.py)
+    dk = np.array([1e-4, -2e-4])  # fourth-order remainder ~ (2 pi |R| |dk|)^4 / 24 ~ 1e-11
+    h = orc.kdotp_hamilton(got, dk)
+    assert np.abs(h - m.hamilton(np.array(k) + dk)).max() < 1e-9
+
+
 WANNIER_TAGS = ["hr_only_w90", "hr_only_w90v2", "hr_only_si", "hr_wsvec_si", "hr_wsvec_bi", "all_si", "all_bi", "all_bi_nearest"]
 
 
