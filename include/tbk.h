@@ -84,6 +84,15 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
                       double* out_dev, void* stream);
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims);
 
+/* Eigenvalues AND eigenvectors of the convention-2 H(k) (what scipy.linalg.eigh returns where
+ * Model.eigenval calls scipy.linalg.eigvalsh, _tb_model.py:1149): Householder reduction with the unitary accumulated,
+ * implicit QL with the rotations applied to it, ascending order.
+ *   eig_dev [n_k][n_orb]          f64   device, ascending
+ *   vec_dev [n_k][n_orb][n_orb]   c128  device, vec[k][i][j] = component i of the eigenvector of eig[k][j] (numpy layout);
+ *                                       unit norm, phase arbitrary */
+int tbk_eigh(tbk_model* m, const double* k_dev, int64_t n_k, double* eig_dev, double* vec_dev, void* stream);
+int tbk_eigh_host(tbk_model* m, const double* k_host, int64_t n_k, double* eig_host, double* vec_host);
+
 /* Model.construct_kdotp (reference src/tbmodels/_tb_model.py:942-982), batched over expansion points: the Taylor
  * coefficients C_p = (2 pi i)^|p| / p! * sum_R [R^p e^{2 pi i k.R} T_R + (-R)^p e^{-2 pi i k.R} T_R^H] of H around k
  * (convention 2), the same Fourier sum as tbk_hamilton with R^p weights.
@@ -107,11 +116,12 @@ int tbk_model_check(tbk_model* m);
 /* Number of kernels launched through this handle so far. */
 int64_t tbk_launch_count(const tbk_model* m);
 /* Per-kernel-class device timing with CUDA events recorded on the launching stream.
- * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand, 3 tridiagonalisation, 4 tridiagonal QL,
- * 5 phase tiles for the GEMM (and the small mesh helper kernels), 6 line expansion of the regular-mesh path.
+ * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand (and the k.p coefficient kernel), 3 tridiagonalisation,
+ * 4 tridiagonal QL, 5 phase tiles for the GEMM (and the small mesh helper kernels), 6 line expansion of the regular-mesh
+ * path, 7 eigen-decomposition with eigenvectors.
  * tbk_profile(m, 1) starts recording; tbk_profile_read synchronises, returns the accumulated milliseconds
  * and launch counts per class since the last read (arrays of TBK_PROFILE_CLASSES) and resets them. */
-#define TBK_PROFILE_CLASSES 7
+#define TBK_PROFILE_CLASSES 8
 int tbk_profile(tbk_model* m, int enable);
 int tbk_profile_read(tbk_model* m, double* ms, int64_t* count);
 /* Bytes of device scratch currently held by the handle. */

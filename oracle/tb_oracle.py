@@ -95,6 +95,19 @@ def eigenval_array(R, hop, pos, k, chunk=4096):
     return out
 
 
+def eigh(R, hop, pos, k):
+    """Eigenvalues AND eigenvectors, the step after the path: ``scipy.linalg.eigh`` (LAPACK zheevr,
+    JOBZ='V', UPLO='L') on every convention-2 ``hamilton(k)[i]`` exactly where ``eigenval`` (reference :1147-1149) calls
+    ``eigvalsh``.  Returns ``(w [n_k, N], v [n_k, N, N])`` (or the squeezed pair for a single k-point)."""
+    hamiltonians = hamilton(R, hop, pos, k)
+    if hamiltonians.ndim == 3:
+        pairs = [la.eigh(ham) for ham in hamiltonians]
+        size = hamiltonians.shape[1]
+        return (np.array([p[0] for p in pairs]).reshape(len(pairs), size),
+                np.array([p[1] for p in pairs]).reshape(len(pairs), size, size))
+    return la.eigh(hamiltonians)
+
+
 def construct_kdotp(R, hop, pos, k, order):
     """Restates ``Model.construct_kdotp`` (reference src/tbmodels/_tb_model.py:942-982) on the packed arrays: the
     ``taylor_coefficients`` dict ``{power tuple: matrix}`` of the k.p expansion of the convention-2 Hamiltonian at ``k``,

@@ -24,6 +24,8 @@ SYMBOLS = (
     "tbk_eigenval",
     "tbk_eigenval_mesh",
     "tbk_mesh_factorised",
+    "tbk_eigh",
+    "tbk_eigh_host",
     "tbk_kdotp_coefficients",
     "tbk_kdotp_coefficients_host",
     "tbk_hamilton_host",
@@ -89,6 +91,10 @@ def load() -> C.CDLL:
     lib.tbk_eigenval_mesh.restype = C.c_int
     lib.tbk_mesh_factorised.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.tbk_mesh_factorised.restype = C.c_int
+    lib.tbk_eigh.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
+    lib.tbk_eigh.restype = C.c_int
+    lib.tbk_eigh_host.argtypes = [vp, vp, C.c_int64, vp, vp]
+    lib.tbk_eigh_host.restype = C.c_int
     lib.tbk_kdotp_coefficients.argtypes = [vp, vp, C.c_int64, vp, C.c_int, vp, vp]
     lib.tbk_kdotp_coefficients.restype = C.c_int
     lib.tbk_kdotp_coefficients_host.argtypes = [vp, vp, C.c_int64, vp, C.c_int, vp]

@@ -154,7 +154,7 @@ class Evaluator:
     def workspace_bytes(self) -> int:
         return int(self._lib.tbk_workspace_bytes(self._handle))
 
-    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase", "mesh_lines")
+    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase", "mesh_lines", "eigh")
 
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on its stream (read back with :meth:`profile_read`)."""
@@ -268,6 +268,48 @@ class Evaluator:
         if single_point:
             return res[0]
         return list(res)
+
+    # ------------------------------------------------------------------ eigenvectors
+    def eigh(self, k):
+        """Eigenvalues and eigenvectors of the convention-2 ``H(k)``: ``(w, v)`` like ``scipy.linalg.eigh`` applied to
+        every ``Model.hamilton(k)[i]`` -- ``w`` ascending ``[n_k, N]``, ``v`` complex128 ``[n_k, N, N]`` with ``v[i][:, j]``
+        the unit-norm eigenvector of ``w[i][j]`` (phase arbitrary).  A single k-point gives ``([N], [N, N])``."""
+        k_array, single_point = _normalise_k(k, self.dim)
+        n_k = k_array.shape[0]
+        w = np.empty((n_k, self.size), dtype=np.float64)
+        v = np.empty((n_k, self.size, self.size), dtype=np.complex128)
+        _capi.check(
+            self._lib.tbk_eigh_host(
+                self._handle, k_array.ctypes.data_as(C.c_void_p), n_k, w.ctypes.data_as(C.c_void_p),
+                v.ctypes.data_as(C.c_void_p),
+            )
+        )
+        if single_point:
+            return w[0], v[0]
+        return w, v
+
+    def eigh_device(self, k_dev, out_w=None, out_v=None):
+        """Device-buffer form of :meth:`eigh`: float64 ``[n_k, dim]`` CUDA tensor -> ``(w [n_k, N], v [n_k, N, N])`` tensors,
+        asynchronous on torch's current stream."""
+        import torch
+
+        k_dev = self._check_k_dev(k_dev)
+        n_k = k_dev.shape[0]
+        if out_w is None:
+            out_w = torch.empty((n_k, self.size), dtype=torch.float64, device=k_dev.device)
+        if out_v is None:
+            out_v = torch.empty((n_k, self.size, self.size), dtype=torch.complex128, device=k_dev.device)
+        if (tuple(out_w.shape) != (n_k, self.size) or out_w.dtype != torch.float64 or not out_w.is_contiguous()
+                or tuple(out_v.shape) != (n_k, self.size, self.size) or out_v.dtype != torch.complex128
+                or not out_v.is_contiguous()):
+            raise ValueError("out_w / out_v must be contiguous float64 [n_k, N] / complex128 [n_k, N, N] tensors")
+        _capi.check(
+            self._lib.tbk_eigh(
+                self._handle, C.c_void_p(k_dev.data_ptr()), n_k, C.c_void_p(out_w.data_ptr()),
+                C.c_void_p(out_v.data_ptr()), self._stream(),
+            )
+        )
+        return out_w, out_v
 
     # ------------------------------------------------------------------ k.p expansion (Model.construct_kdotp)
     def kdotp_coefficients(self, k, order: int):

@@ -78,3 +78,7 @@ class KModel:
         from ._kdotp import KdotpModel
 
         return KdotpModel(self.evaluator().construct_kdotp(k, order), device=self._device)
+
+    def eigh(self, k):
+        """Eigenvalues and eigenvectors of the convention-2 H(k) (extension, see :meth:`Evaluator.eigh`)."""
+        return self.evaluator().eigh(k)

@@ -144,6 +144,8 @@ struct tbk_model {
     double* wsAB = nullptr;   // [lines][2 nclass][n*n] line coefficients (stage A output)
     double* wsQz = nullptr;   // [n_z][2 nclass] cos / sin along the last mesh dimension
     double* wsK = nullptr;    // explicit k-points of a mesh range (ordinary-path fallback)
+    double* wsV = nullptr;    // eigh, N > 82: full matrix + accumulated unitary of every matrix in flight
+    size_t v_bytes = 0;
     double* wsKp = nullptr;   // construct_kdotp: [n_terms] prefactors followed by the int powers [n_terms][dim]
     size_t ab_bytes = 0, qz_bytes = 0, k_bytes = 0, kp_bytes = 0;
     long chunk = 0;
@@ -169,8 +171,8 @@ struct tbk_model {
         int cls;
     };
     std::vector<ProfRec> prof;
-    double prof_ms[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0, 0};
-    int64_t prof_n[TBK_PROFILE_CLASSES] = {0, 0, 0, 0, 0, 0, 0};
+    double prof_ms[TBK_PROFILE_CLASSES] = {0};
+    int64_t prof_n[TBK_PROFILE_CLASSES] = {0};
 };
 
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the launch stream.
@@ -365,6 +367,30 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
             LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
         }
         LAUNCH(2, st, launch_expand(md, kc, m->wsH, cn, convention, out + c0 * NN * 2, st));
+    }
+    return TBK_OK;
+}
+
+// eigh: H(k) build of run_hamilton (packed, in wsH) followed by the eigenvector kernel, chunk by chunk.
+int run_eigh(tbk_model* m, const double* k, long nk, double* eig, double* vec, cudaStream_t st) {
+    const ModelDev& md = m->md;
+    if (nk <= 0) return TBK_OK;
+    if (int rc = ensure_workspace(m, nk)) return rc;
+    const long NN = (long)md.n * md.n;
+    long chunk = m->chunk;
+    if (!eigh_in_smem(md.n)) {  // matrices in flight live in global scratch: 32 N^2 bytes each, at most 1 GiB
+        chunk = std::max<long>(1, std::min<long>(chunk, (1L << 30) / (32L * NN)));
+        if (int rc = grow(&m->wsV, &m->v_bytes, (size_t)std::min(chunk, nk) * NN * 32)) return rc;
+    }
+    for (long c0 = 0; c0 < nk; c0 += chunk) {
+        const long cn = std::min(chunk, nk - c0);
+        const double* kc = k + c0 * md.dim;
+        if (md.small_ok) LAUNCH(1, st, launch_hk_small(md, kc, cn, m->wsH, nullptr, nullptr, st));
+        else {
+            LAUNCH(5, st, launch_hk_phase(md, kc, cn, m->wsQ, st));
+            LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
+        }
+        LAUNCH(7, st, launch_eigh(md.n, m->wsH, cn, eig + c0 * md.n, vec + (size_t)c0 * NN * 2, m->wsV, m->dFail, st));
     }
     return TBK_OK;
 }
@@ -716,6 +742,7 @@ int tbk_model_destroy(tbk_model* m) {
     cudaFree(m->wsQz);
     cudaFree(m->wsK);
     cudaFree(m->wsKp);
+    cudaFree(m->wsV);
     for (int b = 0; b < 2; ++b) {
         cudaFree(m->hk[b]);
         cudaFree(m->ho[b]);
@@ -785,6 +812,56 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims) {
     if (!m || !dims) return 0;
     return mesh_factorised(m, dims) ? 1 : 0;
+}
+
+int tbk_eigh(tbk_model* m, const double* k_dev, int64_t n_k, double* eig_dev, double* vec_dev, void* stream) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigh: null handle");
+    if (n_k < 0 || (n_k > 0 && (!k_dev || !eig_dev || !vec_dev))) return fail(TBK_E_INVALID, "tbk_eigh: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
+    if (int rc = run_eigh(m, k_dev, (long)n_k, eig_dev, vec_dev, (cudaStream_t)stream)) return rc;
+    return scratch_release(m, (cudaStream_t)stream);
+}
+
+int tbk_eigh_host(tbk_model* m, const double* k_host, int64_t n_k, double* eig_host, double* vec_host) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigh_host: null handle");
+    if (n_k < 0 || (n_k > 0 && (!k_host || !eig_host || !vec_host))) return fail(TBK_E_INVALID, "tbk_eigh_host: bad buffers");
+    if (n_k == 0) return TBK_OK;
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = ensure_pipeline(m, 0, 0)) return rc;
+    const ModelDev& md = m->md;
+    const size_t NN = (size_t)md.n * md.n;
+    const long hchunk = std::max<long>(1, std::min<long>((long)n_k, (long)(((size_t)md.tune.host_chunk_mb << 20) / (NN * 16))));
+    double *dk = nullptr, *de = nullptr, *dv = nullptr;
+    auto release = [&]() {
+        cudaFree(dk);
+        cudaFree(de);
+        cudaFree(dv);
+    };
+    if (cudaMalloc(&dk, (size_t)hchunk * md.dim * 8) != cudaSuccess || cudaMalloc(&de, (size_t)hchunk * md.n * 8) != cudaSuccess ||
+        cudaMalloc(&dv, (size_t)hchunk * NN * 16) != cudaSuccess) {
+        release();
+        return fail(TBK_E_CUDA, "tbk_eigh_host: cannot allocate the device staging buffers");
+    }
+    int rc = scratch_acquire(m, m->s_comp);
+    for (long c0 = 0; !rc && c0 < n_k; c0 += hchunk) {
+        const long cn = std::min<long>(hchunk, n_k - c0);
+        cudaError_t e = cudaMemcpyAsync(dk, k_host + c0 * md.dim, (size_t)cn * md.dim * 8, cudaMemcpyHostToDevice, m->s_comp);
+        if (e == cudaSuccess) rc = run_eigh(m, dk, cn, de, dv, m->s_comp);
+        if (!rc && e == cudaSuccess)
+            e = cudaMemcpyAsync(eig_host + c0 * md.n, de, (size_t)cn * md.n * 8, cudaMemcpyDeviceToHost, m->s_comp);
+        if (!rc && e == cudaSuccess)
+            e = cudaMemcpyAsync(vec_host + (size_t)c0 * NN * 2, dv, (size_t)cn * NN * 16, cudaMemcpyDeviceToHost, m->s_comp);
+        if (!rc && e == cudaSuccess) e = cudaStreamSynchronize(m->s_comp);
+        if (!rc && e != cudaSuccess) rc = fail(TBK_E_CUDA, "tbk_eigh_host: %s", cudaGetErrorString(e));
+    }
+    if (!rc) rc = scratch_release(m, m->s_comp);
+    cudaStreamSynchronize(m->s_comp);
+    release();
+    if (rc) return rc;
+    return check_fail_flag(m);
 }
 
 static int kdotp_args_ok(tbk_model* m, const void* k, int64_t n_k, const int32_t* powers, int n_terms, const void* out,

@@ -104,6 +104,12 @@ cudaError_t launch_tridiag_reg(int n, const double* Hp, long nk, double* D, doub
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
 bool tridiag_panel_fits(int n);
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
+// Eigenvalues AND eigenvectors (eig_vectors.cu): Hp packed Hermitian [nk][n*n] (kept), eig [nk][n] ascending, vec
+// [nk][n][n] c128 with column j belonging to eig[j]; scratch = 2 nk n^2 complex numbers of global memory when
+// !eigh_in_smem(n).
+bool eigh_in_smem(int n);
+cudaError_t launch_eigh(int n, const double* Hp, long nk, double* eig, double* vec, double* scratch, int* fail_count,
+                        cudaStream_t st);
 // Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, const Tuning& tune);
 // Matrices per full wave of the QL kernel on the current device (chunks are sized in whole waves); 0 if n/a.

@@ -502,6 +502,81 @@ def test_kdotp_models(tbk, tag):
         tbk.KdotpModel({(0, 0): [[0, 1], [2, 0]]})  # tests/test_kdotp.py:40-46
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 2), (1, 3, 1), (3, 5, 3), (8, 20, 3), (12, 10, 3), (31, 9, 3), (32, 9, 3), (33, 9, 3),
+                                   (36, 60, 3), (64, 8, 3), (82, 5, 3), (83, 5, 3), (130, 4, 2), (260, 3, 3)])
+def test_eigh_eigenvectors(tbk, shape):
+    """Eigenvalues + eigenvectors (scipy.linalg.eigh where the reference calls eigvalsh): eigenvalues
+    within the parity bound of the oracle's, residual ||H v - v w|| and orthonormality at rounding level, every size class
+    of the kernel (one warp, several warps, shared-memory limit 82 / 83, global scratch), fused and GEMM H(k) builds."""
+    import torch
+
+    from oracle import workloads as wl
+
+    n_orb, n_half, dim = shape
+    packed = wl.synthetic(n_orb, n_half, seed=400 + n_orb, dim=dim)
+    orc = _oracle()
+    n_k = 9 if n_orb <= 100 else 3
+    k = np.random.default_rng(n_orb).uniform(-1, 1, size=(n_k, dim))
+    ev = tbk.Evaluator(packed)
+    w, v = ev.eigh(k)
+    assert w.shape == (n_k, n_orb) and v.shape == (n_k, n_orb, n_orb) and v.dtype == np.complex128
+    H = orc.hamilton(packed.R, packed.hop, packed.pos, k)
+    want_w, _ = orc.eigh(packed.R, packed.hop, packed.pos, k)
+    assert_eig_close(w, want_w, f"eigh N={n_orb}")
+    assert np.all(np.diff(w, axis=1) >= 0)
+    assert_eig_close(w, ev.eigenval_array(k), f"eigh vs eigenval N={n_orb}")
+    rho = float(np.abs(want_w).max())
+    resid = np.abs(H @ v - v * w[:, None, :]).max()
+    assert resid <= 1e-10 * rho, f"N={n_orb}: residual {resid:.3e}"
+    gram = np.abs(v.conj().transpose(0, 2, 1) @ v - np.eye(n_orb)).max()
+    assert gram <= 1e-12 * max(n_orb, 8), f"N={n_orb}: V^H V - I = {gram:.3e}"
+    # non-degenerate spectrum: the spectral projectors are unique -> compare them with the oracle's (phase-free)
+    _, want_v = orc.eigh(packed.R, packed.hop, packed.pos, k[:1])
+    gaps = np.diff(want_w[0]).min() if n_orb > 1 else 1.0
+    if gaps > 1e-6 * rho:
+        proj = np.abs(np.einsum("ij,ik->jk", want_v[0].conj(), v[0]))  # |<u_j | v_k>| = delta_jk
+        assert np.abs(proj - np.eye(n_orb)).max() <= 1e-8 / min(1.0, gaps / rho)
+    # single point: squeezed pair; device-buffer entry point: same bits
+    w0, v0 = ev.eigh(tuple(k[2]))
+    assert w0.shape == (n_orb,) and v0.shape == (n_orb, n_orb)
+    assert np.array_equal(w0, w[2]) and np.array_equal(v0, v[2])
+    wd, vd = ev.eigh_device(torch.from_numpy(k).cuda())
+    ev.check()
+    assert np.array_equal(wd.cpu().numpy(), w) and np.array_equal(vd.cpu().numpy(), v)
+    ev.close()
+
+
+def test_eigh_degenerate_and_kdotp(tbk):
+    """Degenerate spectra (empty model: H = 0; a model with two identical decoupled blocks) still give an orthonormal
+    eigenbasis with zero residual; k.p handles take the same path; KModel exposes the method."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    empty = tbk.pack_arrays(np.zeros((0, 3), dtype=np.int32), np.zeros((0, 5, 5), dtype=complex), np.zeros((5, 3)))
+    w, v = tbk.Evaluator(empty).eigh(np.zeros((2, 3)))
+    assert np.array_equal(w, np.zeros((2, 5))) and np.abs(v.conj().transpose(0, 2, 1) @ v - np.eye(5)).max() <= 1e-14
+    base = wl.synthetic(6, 5, seed=77)
+    hop = np.zeros((base.n_R, 12, 12), dtype=complex)
+    hop[:, :6, :6] = base.hop
+    hop[:, 6:, 6:] = base.hop
+    double = tbk.pack_arrays(base.R, hop, np.vstack([base.pos, base.pos]))
+    k = np.random.default_rng(3).random((5, 3))
+    m = tbk.KModel.from_packed(double)
+    w, v = m.eigh(k)
+    H = orc.hamilton(double.R, double.hop, double.pos, k)
+    rho = float(np.abs(w).max())
+    assert np.abs(w[:, 0::2] - w[:, 1::2]).max() <= 1e-12 * rho  # every level twice
+    assert np.abs(H @ v - v * w[:, None, :]).max() <= 1e-10 * rho
+    assert np.abs(v.conj().transpose(0, 2, 1) @ v - np.eye(12)).max() <= 1e-12 * 12
+    m.evaluator().close()
+    d = load_golden("kdotp.npz")
+    tc = {tuple(int(x) for x in p): c for p, c in zip(d["si1_powers"], d["si1_coeff"])}
+    kp = tbk.KdotpModel(tc)
+    w, v = kp.evaluator().eigh(d["si1_k"])
+    assert_eig_close(w, d["si1_eig"], "k.p eigh")
+    assert np.abs(d["si1_H"] @ v - v * w[:, None, :]).max() <= 1e-10 * max(float(np.abs(w).max()), 1.0)
+
+
 def _kdotp_term_scales(d, name, powers):
     """Upper bound of |C_p| per Taylor term: (2 pi)^|p| / p! * sum_r |R_r^p| * 2 max|T_r| -- the parity bound scales with it."""
     from math import factorial, pi
