@@ -57,6 +57,16 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
  * tbk_eigenval[_host] (kdotp.py:84-100). */
 int tbk_kdotp_create(int dim, int n_orb, int n_terms, const int32_t* powers, const double* coeff, int device,
                      tbk_model** out);
+/* Model.supercell (reference src/tbmodels/_tb_model.py:1645-1724) + packing, for a BASE model given like tbk_model_create
+ * and size[dim] >= 1 cells per direction.  The n_R' dense N' x N' matrices the reference
+ * builds (N' = n_orb * prod(size)) are never materialised: the host enumerates the block list, a kernel gathers the
+ * weights straight into the GEMM's tiles, and the all-zero (column tile, K-chunk) stages of the block-sparse result
+ * are skipped by the H(k) GEMM.  The handle behaves like one from tbk_model_create on the supercell model (lattice
+ * vectors folded onto the half set as Model(..., contains_cc=False) does, positions divided by size, :1670-1678).
+ * tbk_model_info reports N' and n_R'; tbk_model_vectors copies the stored lattice vectors [n_R][dim] to the host. */
+int tbk_supercell_create(int dim, int n_orb, int n_R, const int32_t* R, const double* hop, const double* pos,
+                         const int32_t* size, int device, tbk_model** out);
+int tbk_model_vectors(const tbk_model* m, int32_t* R_out);
 int tbk_model_destroy(tbk_model* m);
 /* path: 0 = fused thread-per-k kernel (N <= 8), 1 = DMMA GEMM + batched tridiagonal/QL eigensolver,
  *       2 = fused trigonometric-product kernel (N <= 2, dim <= 3, nearest-cell lattice vectors). */

@@ -18,6 +18,8 @@ SYMBOLS = (
     "tbk_last_error",
     "tbk_model_create",
     "tbk_kdotp_create",
+    "tbk_supercell_create",
+    "tbk_model_vectors",
     "tbk_model_destroy",
     "tbk_model_info",
     "tbk_hamilton",
@@ -79,6 +81,10 @@ def load() -> C.CDLL:
     lib.tbk_model_create.restype = C.c_int
     lib.tbk_kdotp_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.POINTER(vp)]
     lib.tbk_kdotp_create.restype = C.c_int
+    lib.tbk_supercell_create.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(vp)]
+    lib.tbk_supercell_create.restype = C.c_int
+    lib.tbk_model_vectors.argtypes = [vp, vp]
+    lib.tbk_model_vectors.restype = C.c_int
     lib.tbk_model_destroy.argtypes = [vp]
     lib.tbk_model_destroy.restype = C.c_int
     lib.tbk_model_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 4

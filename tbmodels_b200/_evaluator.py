@@ -139,6 +139,43 @@ class Evaluator:
         self._finalizer = weakref.finalize(self, self._lib.tbk_model_destroy, handle)
         return self
 
+    @classmethod
+    def from_supercell(cls, packed: PackedModel, size, device=None) -> "Evaluator":
+        """Evaluator of ``Model.supercell(size)`` (reference src/tbmodels/_tb_model.py:1645-1724) built ON THE DEVICE from the
+        base model's packed arrays: the dense ``[n_R', N', N']`` hopping tensor of the supercell is
+        never materialised, and the H(k) GEMM skips the all-zero blocks of its weights."""
+        size_arr = np.ascontiguousarray(np.array(size).astype(np.int32, casting="same_kind"))
+        if size_arr.shape != (packed.dim,):
+            raise ValueError(
+                "The given 'size' has incorrect shape {}, should be {}.".format(size_arr.shape, (packed.dim,))
+            )
+        self = cls.__new__(cls)
+        self._lib = _capi.load()
+        self.packed = None
+        self.dim = packed.dim
+        self.size = packed.size * int(np.prod(size_arr))
+        self.device = int(_default_device() if device is None else device)
+        handle = C.c_void_p()
+        _capi.check(
+            self._lib.tbk_supercell_create(
+                packed.dim, packed.size, packed.n_R, packed.R.ctypes.data_as(C.c_void_p),
+                packed.hop.ctypes.data_as(C.c_void_p), packed.pos.ctypes.data_as(C.c_void_p),
+                size_arr.ctypes.data_as(C.c_void_p), self.device, C.byref(handle),
+            )
+        )
+        self._handle = handle
+        self._finalizer = weakref.finalize(self, self._lib.tbk_model_destroy, handle)
+        return self
+
+    @property
+    def lattice_vectors(self) -> np.ndarray:
+        """The stored (half-set) lattice vectors of the handle, int32 ``[n_R, dim]`` in summation order."""
+        n_R = C.c_int()
+        _capi.check(self._lib.tbk_model_info(self._handle, None, None, C.byref(n_R), None))
+        out = np.zeros((max(n_R.value, 1), self.dim), dtype=np.int32)
+        _capi.check(self._lib.tbk_model_vectors(self._handle, out.ctypes.data_as(C.c_void_p)))
+        return out[: n_R.value]
+
     # ------------------------------------------------------------------ info
     @property
     def path(self) -> str:

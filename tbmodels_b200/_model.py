@@ -82,3 +82,53 @@ class KModel:
     def eigh(self, k):
         """Eigenvalues and eigenvectors of the convention-2 H(k) (extension, see :meth:`Evaluator.eigh`)."""
         return self.evaluator().eigh(k)
+
+    def supercell(self, size) -> "SupercellKModel":
+        """``Model.supercell(size)`` (reference :1645-1724) evaluated without building the supercell's dense hopping
+        matrices: see :meth:`Evaluator.from_supercell`."""
+        return SupercellKModel(pack_model(self), size, device=self._device)
+
+
+class SupercellKModel:
+    """Supercell of a packed base model, device-packed.  Duck-type of the evaluated part of
+    ``tbmodels.Model``: ``size``, ``dim``, ``pos`` plus ``hamilton`` / ``eigenval`` / ``eigh``.  There is no ``hop`` dict --
+    build the supercell with the reference's ``Model.supercell`` when the dense matrices themselves are needed."""
+
+    def __init__(self, base: PackedModel, size, device=None):
+        import itertools
+
+        size_arr = np.array(size).astype(dtype=int, casting="safe")
+        if size_arr.shape != (base.dim,):
+            raise ValueError("The given 'size' has incorrect shape {}, should be {}.".format(size_arr.shape, (base.dim,)))
+        if np.any(size_arr < 1):
+            raise ValueError("supercell sizes must be >= 1")
+        self.base = base
+        self.supercell_size = tuple(int(x) for x in size_arr)
+        self.dim = base.dim
+        self.size = base.size * int(np.prod(size_arr))
+        reduced = base.pos / size_arr  # reference :1670-1678
+        self.pos = np.concatenate([reduced + np.array(off) / size_arr
+                                   for off in itertools.product(*[range(n) for n in size_arr])])
+        self._device = device
+        self._ev = None
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_ev"] = None
+        return state
+
+    def evaluator(self) -> Evaluator:
+        if self._ev is None:
+            self._ev = Evaluator.from_supercell(self.base, self.supercell_size, device=self._device)
+        return self._ev
+
+    def hamilton(self, k, convention=2):
+        if convention not in [1, 2]:
+            raise ValueError("Invalid value '{}' for 'convention': must be either '1' or '2'".format(convention))
+        return self.evaluator().hamilton(k, convention=convention)
+
+    def eigenval(self, k):
+        return self.evaluator().eigenval(k)
+
+    def eigh(self, k):
+        return self.evaluator().eigh(k)

@@ -143,10 +143,13 @@ hk_phase_kernel(const double* __restrict__ kpts, long nk, const double* __restri
     }
 }
 
-template <int NA>
+// SP = true: block-sparse weights (supercells): kc_cnt[n_tile] stages of this column tile hold a
+// non-zero block of W; their K-chunk indices are kc_idx[n_tile * kchunks + 0 .. cnt).  All other stages are skipped --
+// they would add exact zeros -- so the K loop, the TMA traffic and the DMMA count shrink with the fill of the tile.
+template <int NA, bool SP>
 __global__ void __launch_bounds__(THREADS, 1)
 hk_gemm_kernel(const double* __restrict__ Qt, long nk, const double* __restrict__ Wt, int kchunks, int n_tiles, int NN,
-               double* __restrict__ Hp) {
+               double* __restrict__ Hp, const int* __restrict__ kc_cnt, const int* __restrict__ kc_idx) {
     using C = Cfg<NA>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stages = reinterpret_cast<double*>(smem_raw);
@@ -173,6 +176,8 @@ hk_gemm_kernel(const double* __restrict__ Qt, long nk, const double* __restrict_
 
     const double* asrc = Qt + ((size_t)m_tile * kchunks) * A_TILE;
     const double* wsrc = Wt + ((size_t)n_tile * kchunks) * C::B_STAGE;
+    const int* klist = SP ? kc_idx + (size_t)n_tile * kchunks : nullptr;
+    const int kcount = SP ? __ldg(kc_cnt + n_tile) : kchunks;
 
     // one elected thread feeds the ring: two TMA bulk copies per stage, completion counted in bytes on the mbarrier
     auto produce = [&](int c) {
@@ -180,9 +185,10 @@ hk_gemm_kernel(const double* __restrict__ Qt, long nk, const double* __restrict_
             const int s = c % STAGES;
             double* As = stages + (size_t)s * C::STAGE;
             const uint32_t bar = smem_u32(&bars[s]);
+            const int ci = SP ? __ldg(klist + c) : c;
             mbar_expect_tx(bar, (A_TILE + C::B_STAGE) * 8);
-            tma_bulk_g2s(smem_u32(As), asrc + (size_t)c * A_TILE, A_TILE * 8, bar);
-            tma_bulk_g2s(smem_u32(As + C::A_STAGE), wsrc + (size_t)c * C::B_STAGE, C::B_STAGE * 8, bar);
+            tma_bulk_g2s(smem_u32(As), asrc + (size_t)ci * A_TILE, A_TILE * 8, bar);
+            tma_bulk_g2s(smem_u32(As + C::A_STAGE), wsrc + (size_t)ci * C::B_STAGE, C::B_STAGE * 8, bar);
         }
     };
 
@@ -192,13 +198,13 @@ hk_gemm_kernel(const double* __restrict__ Qt, long nk, const double* __restrict_
 #pragma unroll
         for (int j = 0; j < NA; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int c = 0; c < STAGES - 1 && c < kchunks; ++c) produce(c);
+    for (int c = 0; c < STAGES - 1 && c < kcount; ++c) produce(c);
 
-    for (int c = 0; c < kchunks; ++c) {
+    for (int c = 0; c < kcount; ++c) {
         const int s = c % STAGES;
         mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / STAGES) & 1));
         __syncthreads();  // every warp is done with the stage refilled below
-        if (c + STAGES - 1 < kchunks) produce(c + STAGES - 1);
+        if (c + STAGES - 1 < kcount) produce(c + STAGES - 1);
 
         const double* As = stages + (size_t)s * C::STAGE;
         const double* Bs = As + C::A_STAGE;
@@ -247,11 +253,19 @@ cudaError_t launch_na(const ModelDev& md, long nk, const double* Qt, double* Hp,
     const long m_tiles = (nk + BM - 1) / BM;
     if (m_tiles <= 0) return cudaSuccess;
     const size_t smem = C::smem_bytes();
-    cudaError_t err = cudaFuncSetAttribute(hk_gemm_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
     const long grid = m_tiles * md.n_tiles;
     if (grid > 2147483647L) return cudaErrorInvalidConfiguration;
-    hk_gemm_kernel<NA><<<(unsigned)grid, THREADS, smem, st>>>(Qt, nk, md.Wt, md.kchunks, md.n_tiles, md.n * md.n, Hp);
+    if (md.kc_cnt) {
+        cudaError_t err = cudaFuncSetAttribute(hk_gemm_kernel<NA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        hk_gemm_kernel<NA, true><<<(unsigned)grid, THREADS, smem, st>>>(Qt, nk, md.Wt, md.kchunks, md.n_tiles, md.n * md.n, Hp,
+                                                                      md.kc_cnt, md.kc_idx);
+        return cudaGetLastError();
+    }
+    cudaError_t err = cudaFuncSetAttribute(hk_gemm_kernel<NA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    hk_gemm_kernel<NA, false><<<(unsigned)grid, THREADS, smem, st>>>(Qt, nk, md.Wt, md.kchunks, md.n_tiles, md.n * md.n, Hp,
+                                                                   nullptr, nullptr);
     return cudaGetLastError();
 }
 

@@ -120,6 +120,7 @@ Tuning read_tuning() {
     t.panel_lpr = env_int("TBK_PANEL_LPR", 0);
     t.panel_pfd = env_int("TBK_PANEL_PFD", 1);
     t.ql_bisect_min = env_int("TBK_QL_BISECT_MIN", 0);
+    t.gemm_dense = getenv("TBK_GEMM_DENSE") ? 1 : 0;
     return t;
 }
 }  // namespace tbk
@@ -134,6 +135,8 @@ struct tbk_model {
     double* dWt = nullptr;
     double* dPos = nullptr;
     int* dFail = nullptr;
+    int* dKcCnt = nullptr;  // block-sparse weights: non-zero K-chunks per column tile (hk_gemm.cu, SP = true)
+    int* dKcIdx = nullptr;
     // scratch for the device-pointer entry points
     double* wsH = nullptr;  // [chunk][n*n] packed H(k)
     double* wsE = nullptr;  // [chunk][n]   sub-diagonals
@@ -194,11 +197,9 @@ struct tbk_model {
 
 namespace {
 
-// Tile the weight rows W[n_rows][n*n] for the GEMM (column tiles x 16-row K stages, padding baked in) and upload.
-int upload_gemm_weights(tbk_model* m, const std::vector<double>& W, int n_rows) {
-    ModelDev& md = m->md;
+// Column-tile width that wastes the fewest padded columns (ties -> wider), tile and K-chunk counts.
+void choose_gemm_tiling(ModelDev& md, int n_rows) {
     const long NN = (long)md.n * md.n;
-    // choose the column-tile width that wastes the fewest padded columns (ties -> wider)
     const int cands[3] = {4, 8, 9};
     long best_cols = -1;
     for (int c : cands) {
@@ -209,28 +210,86 @@ int upload_gemm_weights(tbk_model* m, const std::vector<double>& W, int n_rows) 
             md.na = c;
         }
     }
-    const int bn = 16 * md.na, sb = bn + 4;
-    md.n_tiles = (int)((NN + bn - 1) / bn);
+    md.n_tiles = (int)((NN + 16 * md.na - 1) / (16 * md.na));
     md.kchunks = (n_rows + kGemmKC - 1) / kGemmKC;
+}
+
+// Block-sparse weights: nz[tile * kchunks + c] says whether stage (tile, c) of Wt holds anything non-zero.  If some
+// stage is empty the GEMM gets the per-tile lists of populated K-chunks and skips the rest (hk_gemm.cu, SP = true).
+int upload_stage_lists(tbk_model* m, const std::vector<unsigned char>& nz) {
+    ModelDev& md = m->md;
+    const size_t total = (size_t)md.n_tiles * md.kchunks;
+    size_t populated = 0;
+    for (size_t i = 0; i < total; ++i) populated += nz[i] ? 1 : 0;
+    if (populated == total || md.tune.gemm_dense) return TBK_OK;
+    std::vector<int> cnt((size_t)md.n_tiles, 0), idx(std::max<size_t>(total, 1), 0);
+    for (int nt = 0; nt < md.n_tiles; ++nt)
+        for (int c = 0; c < md.kchunks; ++c)
+            if (nz[(size_t)nt * md.kchunks + c]) idx[(size_t)nt * md.kchunks + cnt[nt]++] = c;
+    CU(cudaMalloc(&m->dKcCnt, cnt.size() * sizeof(int)));
+    CU(cudaMemcpy(m->dKcCnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&m->dKcIdx, idx.size() * sizeof(int)));
+    CU(cudaMemcpy(m->dKcIdx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    md.kc_cnt = m->dKcCnt;
+    md.kc_idx = m->dKcIdx;
+    m->model_bytes += (cnt.size() + idx.size()) * sizeof(int);
+    return TBK_OK;
+}
+
+// Tile the weight rows W[n_rows][n*n] for the GEMM (column tiles x 16-row K stages, padding baked in) and upload.
+int upload_gemm_weights(tbk_model* m, const std::vector<double>& W, int n_rows) {
+    ModelDev& md = m->md;
+    const long NN = (long)md.n * md.n;
+    choose_gemm_tiling(md, n_rows);
+    const int bn = 16 * md.na, sb = bn + 4;
     const size_t stage = (size_t)kGemmKC * sb;
     std::vector<double> Wt((size_t)std::max(md.n_tiles * md.kchunks, 1) * stage, 0.0);
+    std::vector<unsigned char> nz((size_t)std::max(md.n_tiles * md.kchunks, 1), 0);
     for (int nt = 0; nt < md.n_tiles; ++nt)
         for (int c = 0; c < md.kchunks; ++c) {
             double* blk = Wt.data() + ((size_t)nt * md.kchunks + c) * stage;
+            unsigned char any = 0;
             for (int kk = 0; kk < kGemmKC; ++kk) {
                 const long q = (long)c * kGemmKC + kk;
                 if (q >= n_rows) continue;
                 const double* src = W.data() + (size_t)q * NN;
                 for (int col = 0; col < bn; ++col) {
                     const long e = (long)nt * bn + col;
-                    if (e < NN) blk[(size_t)kk * sb + col] = src[e];
+                    if (e < NN) {
+                        blk[(size_t)kk * sb + col] = src[e];
+                        any |= src[e] != 0.0;
+                    }
                 }
             }
+            nz[(size_t)nt * md.kchunks + c] = any;
         }
     CU(cudaMalloc(&m->dWt, Wt.size() * 8));
     CU(cudaMemcpy(m->dWt, Wt.data(), Wt.size() * 8, cudaMemcpyHostToDevice));
     md.Wt = m->dWt;
     m->model_bytes += Wt.size() * 8;
+    return upload_stage_lists(m, nz);
+}
+
+// Classes of the stored R vectors by their last component (regular k-mesh path, hk_mesh.cu).
+int setup_mesh_classes(tbk_model* m, const int32_t* R, int n_R) {
+    ModelDev& md = m->md;
+    const int dim = md.dim;
+    if (dim < 2 || n_R <= 0) return TBK_OK;
+    std::vector<int> zs;
+    for (int r = 0; r < n_R; ++r) zs.push_back(R[(size_t)r * dim + dim - 1]);
+    std::vector<int> uniq(zs);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    std::vector<int> Rc((size_t)md.kchunks * 8, -1);
+    for (int r = 0; r < n_R; ++r) Rc[r] = (int)(std::lower_bound(uniq.begin(), uniq.end(), zs[r]) - uniq.begin());
+    std::vector<double> zc(uniq.begin(), uniq.end());
+    CU(cudaMalloc(&m->dRc, Rc.size() * sizeof(int)));
+    CU(cudaMemcpy(m->dRc, Rc.data(), Rc.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&m->dZc, zc.size() * 8));
+    CU(cudaMemcpy(m->dZc, zc.data(), zc.size() * 8, cudaMemcpyHostToDevice));
+    md.Rc = m->dRc;
+    md.zc = m->dZc;
+    md.nclass = (int)uniq.size();
     return TBK_OK;
 }
 
@@ -644,27 +703,221 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
         md.Ri = m->dRi;
     } else {
         if (int rc = upload_gemm_weights(m, W, 2 * n_R)) return bail(rc);
-        if (dim >= 2 && n_R > 0) {  // classes of the stored R by their last component (hk_mesh.cu)
-            std::vector<int> zs;
-            for (int r = 0; r < n_R; ++r) zs.push_back(R[(size_t)r * dim + dim - 1]);
-            std::vector<int> uniq(zs);
-            std::sort(uniq.begin(), uniq.end());
-            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
-            std::vector<int> Rc((size_t)md.kchunks * 8, -1);
-            for (int r = 0; r < n_R; ++r)
-                Rc[r] = (int)(std::lower_bound(uniq.begin(), uniq.end(), zs[r]) - uniq.begin());
-            std::vector<double> zc(uniq.begin(), uniq.end());
-            CUB(cudaMalloc(&m->dRc, Rc.size() * sizeof(int)));
-            CUB(cudaMemcpy(m->dRc, Rc.data(), Rc.size() * sizeof(int), cudaMemcpyHostToDevice));
-            CUB(cudaMalloc(&m->dZc, zc.size() * 8));
-            CUB(cudaMemcpy(m->dZc, zc.data(), zc.size() * 8, cudaMemcpyHostToDevice));
-            md.Rc = m->dRc;
-            md.zc = m->dZc;
-            md.nclass = (int)uniq.size();
-        }
+        if (int rc = setup_mesh_classes(m, R, n_R)) return bail(rc);
     }
 #undef CUB
     *out = m;
+    return TBK_OK;
+}
+
+int tbk_supercell_create(int dim, int n_orb, int n_R, const int32_t* R, const double* hop, const double* pos,
+                         const int32_t* size, int device, tbk_model** out) {
+    if (!out) return fail(TBK_E_INVALID, "tbk_supercell_create: out is null");
+    *out = nullptr;
+    if (n_orb < 1 || dim < 1) return fail(TBK_E_INVALID, "tbk_supercell_create: bad sizes");
+    if (dim > kMaxDim) return fail(TBK_E_UNSUPPORTED, "tbk_supercell_create: dim = %d > %d is not supported", dim, kMaxDim);
+    if (n_R < 0 || (n_R > 0 && (!R || !hop)) || !pos || !size) return fail(TBK_E_INVALID, "tbk_supercell_create: bad arrays");
+    long vol = 1;
+    for (int d = 0; d < dim; ++d) {
+        if (size[d] < 1) return fail(TBK_E_INVALID, "tbk_supercell_create: size[%d] = %d must be >= 1", d, size[d]);
+        vol *= size[d];
+        if (vol > 4096) return fail(TBK_E_UNSUPPORTED, "tbk_supercell_create: more than 4096 cells");
+    }
+    const long N = (long)n_orb * vol;
+    if (N > 8192) return fail(TBK_E_UNSUPPORTED, "tbk_supercell_create: %ld orbitals (limit 8192)", N);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(TBK_E_CUDA, "tbk_supercell_create: no CUDA device available (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TBK_E_INVALID, "tbk_supercell_create: device %d out of range", device);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "tbk_supercell_create: cudaSetDevice(%d) failed", device);
+
+    // ---- host: enumerate the blocks (reference :1687-1710) and fold onto the half set (:281-298) ----
+    struct Raw {
+        int q, a, b, r, herm;
+        double scale;
+    };
+    std::vector<std::vector<int>> keys;  // folded lattice vectors in order of first appearance
+    auto key_index = [&](const std::vector<int>& key) {
+        for (size_t i = 0; i < keys.size(); ++i)
+            if (keys[i] == key) return (int)i;
+        keys.push_back(key);
+        return (int)keys.size() - 1;
+    };
+    std::vector<long> mult((size_t)dim, 1);  // cell index = sum_d offset_d * prod_{e > d} size_e (itertools.product order)
+    for (int d = dim - 2; d >= 0; --d) mult[d] = mult[d + 1] * size[d + 1];
+    std::vector<Raw> raws;
+    std::vector<int> off((size_t)dim), newR((size_t)dim);
+    // pass 1 in the reference's loop order (cells outermost) so that the folded keys appear in the same order as in
+    // Model(hop=new_hop, contains_cc=False): first the order of raw keys, then their folded images
+    std::vector<std::vector<int>> raw_keys;
+    for (long a = 0; a < vol; ++a) {
+        long rem = a;
+        for (int d = 0; d < dim; ++d) {
+            off[d] = (int)(rem / mult[d]);
+            rem %= mult[d];
+        }
+        for (int r = 0; r < n_R; ++r) {
+            for (int d = 0; d < dim; ++d) {
+                const int full = off[d] + R[(size_t)r * dim + d];
+                int q = full / size[d];
+                if (full % size[d] < 0) --q;  // floor division
+                newR[d] = q;
+            }
+            bool seen = false;
+            for (const auto& k : raw_keys) seen = seen || k == newR;
+            if (!seen) raw_keys.push_back(newR);
+        }
+    }
+    for (const auto& k : raw_keys) {
+        int first = 0;
+        for (int d = 0; d < dim && first == 0; ++d) first = k[d];
+        std::vector<int> key(k);
+        if (first < 0)
+            for (int& x : key) x = -x;
+        key_index(key);
+    }
+    for (long a = 0; a < vol; ++a) {
+        long rem = a;
+        for (int d = 0; d < dim; ++d) {
+            off[d] = (int)(rem / mult[d]);
+            rem %= mult[d];
+        }
+        for (int r = 0; r < n_R; ++r) {
+            long b = 0;
+            int first = 0;
+            for (int d = 0; d < dim; ++d) {
+                const int full = off[d] + R[(size_t)r * dim + d];
+                int q = full / size[d], md_ = full % size[d];
+                if (md_ < 0) {
+                    --q;
+                    md_ += size[d];
+                }
+                newR[d] = q;
+                b += md_ * mult[d];
+                if (first == 0) first = q;
+            }
+            std::vector<int> key(newR);
+            if (first < 0)
+                for (int& x : key) x = -x;
+            const int q = key_index(key);
+            if (first == 0) {  // R' = 0: 0.5 X + 0.5 X^H
+                raws.push_back({q, (int)a, (int)b, r, 0, 0.5});
+                raws.push_back({q, (int)b, (int)a, r, 1, 0.5});
+            } else if (first > 0) raws.push_back({q, (int)a, (int)b, r, 0, 1.0});
+            else raws.push_back({q, (int)b, (int)a, r, 1, 1.0});
+        }
+    }
+    const int nq = (int)keys.size();
+    if ((size_t)nq * vol * vol > (size_t)1 << 26) return fail(TBK_E_UNSUPPORTED, "tbk_supercell_create: block table too large");
+    std::stable_sort(raws.begin(), raws.end(), [&](const Raw& x, const Raw& y) {
+        if (x.q != y.q) return x.q < y.q;
+        if (x.a != y.a) return x.a < y.a;
+        return x.b < y.b;
+    });
+    std::vector<int2> table((size_t)std::max(nq, 1) * vol * vol, make_int2(0, 0));
+    std::vector<SupEntry> entries(std::max<size_t>(raws.size(), 1));
+    for (size_t i = 0; i < raws.size(); ++i) {
+        entries[i] = {raws[i].r, raws[i].herm, raws[i].scale};
+        int2& t = table[((size_t)raws[i].q * vol + raws[i].a) * vol + raws[i].b];
+        if (t.y == 0) t.x = (int)i;
+        t.y += 1;
+    }
+
+    tbk_model* m = new (std::nothrow) tbk_model();
+    if (!m) return fail(TBK_E_INVALID, "out of host memory");
+    m->device = device;
+    ModelDev& md = m->md;
+    md.tune = read_tuning();
+    md.n = (int)N;
+    md.dim = dim;
+    md.nR = nq;
+    md.nRpad = (nq + 7) & ~7;
+    md.small_ok = 0;
+    auto bail = [&](int rc) {
+        tbk_model_destroy(m);
+        return rc;
+    };
+#define CUB(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return bail(fail(TBK_E_CUDA, "%s -> %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    std::vector<double> Rd((size_t)std::max(md.nRpad, 1) * dim, 0.0);
+    std::vector<int32_t> Rn((size_t)std::max(nq, 1) * dim, 0);
+    for (int q = 0; q < nq; ++q)
+        for (int d = 0; d < dim; ++d) {
+            Rd[(size_t)q * dim + d] = (double)keys[q][d];
+            Rn[(size_t)q * dim + d] = keys[q][d];
+        }
+    CUB(cudaMalloc(&m->dRd, Rd.size() * 8));
+    CUB(cudaMemcpy(m->dRd, Rd.data(), Rd.size() * 8, cudaMemcpyHostToDevice));
+    md.Rd = m->dRd;
+    // positions normalised to the supercell (reference :1670-1678): cell offsets outermost
+    std::vector<double> npos((size_t)N * dim);
+    for (long a = 0; a < vol; ++a) {
+        long rem = a;
+        for (int d = 0; d < dim; ++d) {
+            off[d] = (int)(rem / mult[d]);
+            rem %= mult[d];
+        }
+        for (int i = 0; i < n_orb; ++i)
+            for (int d = 0; d < dim; ++d)
+                npos[((size_t)a * n_orb + i) * dim + d] = pos[(size_t)i * dim + d] / (double)size[d] + (double)off[d] / (double)size[d];
+    }
+    CUB(cudaMalloc(&m->dPos, npos.size() * 8));
+    CUB(cudaMemcpy(m->dPos, npos.data(), npos.size() * 8, cudaMemcpyHostToDevice));
+    md.pos = m->dPos;
+    CUB(cudaMalloc(&m->dFail, sizeof(int)));
+    CUB(cudaMemset(m->dFail, 0, sizeof(int)));
+
+    // ---- device: gather the Hermitian-split weights straight into the GEMM stage tiles ----
+    choose_gemm_tiling(md, 2 * nq);
+    const int bn = 16 * md.na;
+    const size_t stage = (size_t)kGemmKC * (bn + 4);
+    const size_t n_stages = (size_t)std::max(md.n_tiles * md.kchunks, 1);
+    CUB(cudaMalloc(&m->dWt, n_stages * stage * 8));
+    CUB(cudaMemset(m->dWt, 0, n_stages * stage * 8));
+    md.Wt = m->dWt;
+    m->model_bytes += n_stages * stage * 8;
+    double* d_hop = nullptr;
+    int2* d_table = nullptr;
+    SupEntry* d_entries = nullptr;
+    unsigned char* d_flags = nullptr;
+    auto drop_tmp = [&]() {
+        cudaFree(d_hop);
+        cudaFree(d_table);
+        cudaFree(d_entries);
+        cudaFree(d_flags);
+    };
+    std::vector<unsigned char> nz(n_stages, 0);
+    cudaError_t e = cudaMalloc(&d_hop, std::max<size_t>((size_t)n_R * n_orb * n_orb * 16, 16));
+    if (e == cudaSuccess) e = cudaMalloc(&d_table, table.size() * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_entries, entries.size() * sizeof(SupEntry));
+    if (e == cudaSuccess) e = cudaMalloc(&d_flags, n_stages);
+    if (e == cudaSuccess && n_R > 0) e = cudaMemcpy(d_hop, hop, (size_t)n_R * n_orb * n_orb * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_table, table.data(), table.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_entries, entries.data(), entries.size() * sizeof(SupEntry), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_supercell_pack(n_orb, (int)vol, nq, bn, md.kchunks, d_hop, d_table, d_entries, m->dWt, nullptr);
+    if (e == cudaSuccess) e = launch_stage_flags(m->dWt, (long)n_stages, (int)stage, d_flags, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(nz.data(), d_flags, n_stages, cudaMemcpyDeviceToHost);
+    drop_tmp();
+    if (e != cudaSuccess) return bail(fail(TBK_E_CUDA, "tbk_supercell_create: %s", cudaGetErrorString(e)));
+    m->launches += 2;
+    if (int rc = upload_stage_lists(m, nz)) return bail(rc);
+    if (int rc = setup_mesh_classes(m, Rn.data(), nq)) return bail(rc);
+#undef CUB
+    *out = m;
+    return TBK_OK;
+}
+
+int tbk_model_vectors(const tbk_model* m, int32_t* R_out) {
+    if (!m || !R_out) return fail(TBK_E_INVALID, "tbk_model_vectors: null argument");
+    if (m->md.kind != 0) return fail(TBK_E_INVALID, "tbk_model_vectors: the handle is a k.p model");
+    DeviceGuard guard(m->device);
+    std::vector<double> Rd((size_t)std::max(m->md.nR, 1) * m->md.dim);
+    if (m->md.nR > 0) CU(cudaMemcpy(Rd.data(), m->md.Rd, (size_t)m->md.nR * m->md.dim * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < (size_t)m->md.nR * m->md.dim; ++i) R_out[i] = (int32_t)Rd[i];
     return TBK_OK;
 }
 
@@ -733,6 +986,8 @@ int tbk_model_destroy(tbk_model* m) {
     cudaFree(m->dWt);
     cudaFree(m->dPos);
     cudaFree(m->dFail);
+    cudaFree(m->dKcCnt);
+    cudaFree(m->dKcIdx);
     cudaFree(m->wsH);
     cudaFree(m->wsE);
     cudaFree(m->wsQ);

@@ -33,6 +33,7 @@ struct Tuning {
     int panel_lpr = 0;          // TBK_PANEL_LPR: lanes per row
     int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
     int ql_bisect_min = 0;      // TBK_QL_BISECT_MIN: bisection instead of QL from this N on (0 = default)
+    int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)
 };
 Tuning read_tuning();
 
@@ -51,6 +52,10 @@ struct ModelDev {
     int na = 0;        // GEMM: n-atoms (8 columns) per warp -> bn = 16 * na
     int n_tiles = 0;   // GEMM: column tiles
     int kchunks = 0;   // GEMM: nRpad / 8
+    // GEMM, block-sparse weights (supercells): per column tile the K-chunks whose stage block of Wt is not all zero;
+    // null when every stage is populated (then the dense K loop runs)
+    const int* kc_cnt = nullptr;  // [n_tiles]
+    const int* kc_idx = nullptr;  // [n_tiles][kchunks], first kc_cnt[t] entries valid (ascending)
     int small_ok = 0;  // fused thread-per-k kernel usable
     // N <= 2, dim <= 3, all |R_d| <= 1: H(k) as a linear combination of the 3^dim products of {1, cos 2 pi k_d,
     // sin 2 pi k_d} (hk_small.cu, hk_basis_kernel); basis[b * n * n + e], b = sum_d t_d 3^d, t_d in {0: 1, 1: cos, 2: sin}
@@ -104,6 +109,17 @@ cudaError_t launch_tridiag_reg(int n, const double* Hp, long nk, double* D, doub
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
 bool tridiag_panel_fits(int n);
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
+// Supercell packing on the device (supercell_pack.cu).  One SupEntry per base hopping matrix that lands in a block of a
+// folded supercell matrix: base matrix index, Hermitian-transposed or not, scale (1/2 for the R' = 0 symmetrisation).
+// table[(q * vol + a) * vol + b] = (first entry, count) of block (a, b) of new lattice vector q.
+struct SupEntry {
+    int r;
+    int herm;
+    double scale;
+};
+cudaError_t launch_supercell_pack(int n_base, int vol, int nq, int bn, int kchunks, const double* base_hop,
+                                  const int2* table, const SupEntry* entries, double* Wt, cudaStream_t st);
+cudaError_t launch_stage_flags(const double* Wt, long n_stages, int stage_doubles, unsigned char* flags, cudaStream_t st);
 // Eigenvalues AND eigenvectors (eig_vectors.cu): Hp packed Hermitian [nk][n*n] (kept), eig [nk][n] ascending, vec
 // [nk][n][n] c128 with column j belonging to eig[j]; scratch = 2 nk n^2 complex numbers of global memory when
 // !eigh_in_smem(n).

@@ -577,6 +577,64 @@ def test_eigh_degenerate_and_kdotp(tbk):
     assert np.abs(d["si1_H"] @ v - v * w[:, None, :]).max() <= 1e-10 * max(float(np.abs(w).max()), 1.0)
 
 
+@pytest.mark.parametrize("case", [("silicon", (2, 2, 2)), ("silicon", (4, 4, 4)), ("silicon", (1, 3, 2)), ("syn5", (2, 1, 3)),
+                                  ("syn2d", (3, 2)), ("syn1d", (5,)), ("syn12", (1, 1, 1))])
+def test_supercell_device_pack(tbk, case, monkeypatch):
+    """Model.supercell packed on the device (reference :1645-1724) against the host-packed supercell
+    of the oracle's restatement (itself pinned to the reference in make_golden.py): same lattice vectors in the same
+    order, H(k) both conventions and eigenvalues BIT-equal to the handle made from the dense supercell arrays (the
+    gathered weights are the same numbers), and within the parity bounds of the oracle; block-sparse GEMM == dense GEMM."""
+    from oracle import workloads as wl
+
+    name, size = case
+    base = {"silicon": lambda: packed_from(load_golden("silicon.npz")), "syn5": lambda: wl.synthetic(5, 9, seed=21),
+            "syn2d": lambda: wl.synthetic(4, 6, seed=22, dim=2), "syn1d": lambda: wl.synthetic(3, 4, seed=23, dim=1),
+            "syn12": lambda: wl.synthetic(12, 8, seed=24)}[name]()
+    big = wl.supercell(base, size)  # dense host arrays, reference semantics
+    orc = _oracle()
+    m = tbk.KModel.from_packed(base).supercell(size)
+    assert m.size == big.size and np.array_equal(m.pos, big.pos)
+    ev = m.evaluator()
+    assert ev.path == "gemm+tridiag-ql"
+    assert np.array_equal(ev.lattice_vectors, big.R)
+    monkeypatch.setenv("TBK_FORCE_GEMM", "1")
+    ev_host = tbk.Evaluator(big)  # the same model through tbk_model_create on the dense arrays
+    k = np.random.default_rng(7).uniform(-1, 1, size=(5 if big.size > 200 else 40, base.dim))
+    for conv in (1, 2):
+        got = ev.hamilton(k, convention=conv)
+        assert np.array_equal(got, ev_host.hamilton(k, convention=conv)), f"conv {conv}: device pack != host pack"
+        assert_h_close(got, orc.hamilton(big.R, big.hop, big.pos, k, conv), big, f"{name}{size} H conv{conv}")
+    e = ev.eigenval_array(k)
+    assert np.array_equal(e, ev_host.eigenval_array(k))
+    assert_eig_close(e, orc.eigenval_array(big.R, big.hop, big.pos, k), f"{name}{size} eig")
+    assert isinstance(m.eigenval(k), list) and m.hamilton(tuple(k[0])).shape == (big.size, big.size)
+    # block-sparse stage skipping off: identical values (the skipped stages only ever add zeros)
+    monkeypatch.setenv("TBK_GEMM_DENSE", "1")
+    ev_dense = tbk.Evaluator.from_supercell(base, size)
+    assert np.array_equal(ev_dense.eigenval_array(k), e)
+    monkeypatch.delenv("TBK_GEMM_DENSE")
+    for x in (ev, ev_host, ev_dense):
+        x.close()
+    with pytest.raises(ValueError):
+        tbk.KModel.from_packed(base).supercell((2,) * (base.dim + 1))  # reference :1656-1662
+
+
+def test_supercell_band_folding(tbk):
+    """Reference tests/test_supercell.py:24-82: every eigenvalue of the base model at k + (shift / size) appears in the
+    supercell spectrum at size * k (atol 1e-7 there; the parity bound here)."""
+    from oracle import workloads as wl
+
+    base = wl.synthetic(4, 10, seed=31)
+    size = (2, 3, 1)
+    sup = tbk.KModel.from_packed(base).supercell(size)
+    kb = np.random.default_rng(1).random((6, 3))
+    e_sup = np.array(sup.eigenval(kb * np.array(size)))
+    ev = tbk.Evaluator(base)
+    shifts = [np.array(o) / np.array(size) for o in np.ndindex(*size)]
+    folded = np.sort(np.concatenate([ev.eigenval_array(kb + s) for s in shifts], axis=1), axis=1)
+    assert_eig_close(e_sup, folded, "band folding")
+
+
 def _kdotp_term_scales(d, name, powers):
     """Upper bound of |C_p| per Taylor term: (2 pi)^|p| / p! * sum_r |R_r^p| * 2 max|T_r| -- the parity bound scales with it."""
     from math import factorial, pi
