@@ -115,8 +115,8 @@ constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers ar
 // (N <= 32 + XMAX); 0 for N <= 32.
 template <int NREG, int XMAX, int BW, int OCC>
 __global__ void __launch_bounds__(32, reg_min_blocks<NREG, OCC>())
-tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
-                   double* __restrict__ E, int ldo, int off) {
+tridiag_reg_kernel(double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
+                   double* __restrict__ E, int ldo, int off, int n_stop) {
     static_assert(NREG % 4 == 0 && NREG <= 32, "NREG must be a multiple of 4, at most 32");
     static_assert(XMAX == 0 || NREG == 32, "extra rows only behind a full warp of register rows");
     constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;  // entries of v / w (every lane writes its own; a multiple of 8)
@@ -305,7 +305,8 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
     }
 
     // ---- lean steps: pivot columns min(N-1, 31) .. 1; active rows = lanes 0 .. p-1, active columns = registers 0 .. p-1 ----
-    for (; p >= 1; --p) {
+    const int p_last = n_stop > 1 ? n_stop : 1;  // staged: stop with an n_stop x n_stop block left (n_stop <= 32)
+    for (; p >= p_last; --p) {
         double xr, xi;
         get_col<NREG>(ar, ai, p, xr, xi);
         if (lane == p) DS[p] = xr;
@@ -344,6 +345,33 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
         row_update<NREG, BW>(ar, ai, V, W, p, vr, vi, wr, wi);
         __syncwarp();
     }
+    double* Dk = D + kk * (long)ldo + off;
+    double* Ek = E + kk * (long)ldo + off;
+    if (n_stop > 1) {
+        // ---- staged hand-over: d / e of the eliminated rows, and the remaining leading block of B stored as the packed
+        // matrix A'[I][J] = B[n'-1-I][n'-1-J] (= the trailing block of A in natural order) at the start of this matrix'
+        // own region; the next launch (tridiag_reg_half_kernel) finishes it with two matrices per warp ----
+        __syncwarp();
+        const int np = n_stop;
+        for (int i = lane; i < N - np; i += 32) {
+            Dk[i] = DS[N - 1 - i];
+            Ek[i] = ES[N - 2 - i];
+        }
+        double* out = Hp + kk * mstride;
+        const int ntp = itri(np);
+        if (lane < np) {
+            const int I = np - 1 - lane;
+#pragma unroll
+            for (int b = 0; b < NREG; ++b) {
+                if (b >= lane && b < np) {
+                    const int J = np - 1 - b;
+                    out[itri(I) + J] = ar[b];
+                    if (b > lane) out[ntp + itrs(I) + J] = ai[b];
+                }
+            }
+        }
+        return;
+    }
     {
         double xr, xi;
         get_col<NREG>(ar, ai, 0, xr, xi);
@@ -352,8 +380,6 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
     __syncwarp();
 
     // ---- store, undoing the index reversal: d_A[i] = d_B[N-1-i], e_A[i] = e_B[N-2-i] ----
-    double* Dk = D + kk * (long)ldo + off;
-    double* Ek = E + kk * (long)ldo + off;
     for (int i = lane; i < N; i += 32) {
         Dk[i] = DS[N - 1 - i];
         if (i < N - 1) Ek[i] = ES[N - 2 - i];
@@ -361,9 +387,131 @@ tridiag_reg_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, 
     if (lane == 0) Ek[N - 1] = 0.0;
 }
 
+// ---- N <= 16: two matrices per warp (lanes 0-15 / 16-31), the tail of the staged reduction ----
+// Below ~16 rows a step is all latency (reductions, the reflector, a few FMAs): half the lanes of a warp-per-matrix kernel
+// idle and its 160+ registers leave three warps per scheduler to hide it.  Here a half-warp owns a matrix (16 columns =
+// 64 registers), so every scheduler holds >= 4 warps = 8 matrices.  Both halves run the same step sequence (N is the
+// same), so control flow stays warp uniform; a step whose reflector is trivial (tau = 0) is executed with v = w = 0
+// instead of being skipped.
+__device__ __forceinline__ double half_sum(double a) {
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off, 16);
+    return a;
+}
+
+__global__ void __launch_bounds__(32, 16)
+tridiag_reg_half_kernel(const double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
+                        double* __restrict__ E, int ldo, int off) {
+    constexpr int NREG = 16;
+    __shared__ __align__(16) double smem[2][NREG * NREG + 4 * NREG + 2 * NREG];
+    const int lane = threadIdx.x & 15;
+    const int sub = threadIdx.x >> 4;
+    long kk = 2L * blockIdx.x + sub;
+    const bool live = kk < nk;
+    if (!live) kk = nk - 1;  // the idle half shadows the last matrix (no stores) so that the warp stays convergent
+    const int ntri = itri(N);
+    const int nn = N * N;
+    double* S = smem[sub];
+    double2* V = reinterpret_cast<double2*>(S + NREG * NREG);
+    double2* W = V + NREG;
+    double* DS = reinterpret_cast<double*>(W + NREG);
+    double* ES = DS + NREG;
+    {
+        const double* src = Hp + kk * mstride;
+        for (int e = lane; e < nn; e += 16) S[e] = src[e];
+        V[lane] = make_double2(0.0, 0.0);
+        W[lane] = make_double2(0.0, 0.0);
+    }
+    __syncwarp();
+    double ar[NREG], ai[NREG];
+    {
+        const int I = N - 1 - lane;
+        const bool row_ok = lane < N;
+        const double* Si = S + ntri;
+        const int Ic = row_ok ? I : 0;
+        const int triI = itri(Ic), trsI = itrs(Ic);
+#pragma unroll
+        for (int b = 0; b < NREG; ++b) {
+            const int J = b < N ? N - 1 - b : 0;
+            const bool own = b >= lane;
+            const int ire = own ? triI + J : itri(J) + Ic;
+            int iim = own ? trsI + J : itrs(J) + Ic;
+            const bool diag = b == lane;
+            iim = diag ? 0 : iim;
+            const double re = S[ire];
+            const double im = Si[iim];
+            const bool ok = row_ok && b < N;
+            ar[b] = ok ? re : 0.0;
+            ai[b] = (ok && !diag) ? (own ? im : -im) : 0.0;
+        }
+    }
+    __syncwarp();
+    for (int p = N - 1; p >= 1; --p) {
+        double xr, xi;
+        get_col<NREG>(ar, ai, p, xr, xi);
+        if (lane == p) DS[p] = xr;
+        const double alr = __shfl_sync(0xffffffffu, xr, p - 1, 16);
+        const double ali = __shfl_sync(0xffffffffu, xi, p - 1, 16);
+        double xn = lane < p - 1 ? fma(xr, xr, xi * xi) : 0.0;
+        xn = half_sum(xn);
+        double beta, tr, ti, sr, si;
+        householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
+        if (lane == 0) ES[p - 1] = beta;
+        const bool trivial = tr == 0.0 && ti == 0.0;  // v = w = 0: the update below is a no-op
+        double vr = 0.0, vi = 0.0;
+        if (lane < p - 1) {
+            vr = xr * sr - xi * si;
+            vi = xr * si + xi * sr;
+        } else if (lane == p - 1) {
+            vr = trivial ? 0.0 : 1.0;
+        }
+        V[lane] = make_double2(vr, vi);
+        __syncwarp();
+        double qr, qi;
+        row_dot<NREG, 4>(ar, ai, V, p, qr, qi);
+        const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+        double dr = pr * vr + pi * vi;
+        double di = pr * vi - pi * vr;
+        dr = half_sum(dr);
+        di = half_sum(di);
+        const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
+        double wr = 0.0, wi = 0.0;
+        if (lane < p) {
+            wr = pr + cr * vr - ci * vi;
+            wi = pi + cr * vi + ci * vr;
+        }
+        W[lane] = make_double2(wr, wi);
+        __syncwarp();
+        row_update<NREG, 4>(ar, ai, V, W, p, vr, vi, wr, wi);
+        __syncwarp();
+    }
+    {
+        double xr, xi;
+        get_col<NREG>(ar, ai, 0, xr, xi);
+        if (lane == 0) DS[0] = xr;
+    }
+    __syncwarp();
+    if (!live) return;
+    double* Dk = D + kk * (long)ldo + off;
+    double* Ek = E + kk * (long)ldo + off;
+    if (lane < N) {
+        Dk[lane] = DS[N - 1 - lane];
+        Ek[lane] = lane < N - 1 ? ES[N - 2 - lane] : 0.0;
+    }
+}
+
+cudaError_t launch_reg_half(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
+                            int off) {
+    if (nk <= 0) return cudaSuccess;
+    const long blocks = (nk + 1) / 2;
+    if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+    tridiag_reg_half_kernel<<<(unsigned)blocks, 32, 0, st>>>(Hp, n, mstride, nk, D, E, ldo, off);
+    return cudaGetLastError();
+}
+
 template <int NREG, int XMAX, int BW, int OCC>
-cudaError_t launch_reg_bw(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
-                          int off) {
+cudaError_t launch_reg_bw(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
+                          int off, int n_stop) {
     constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;
     const size_t smem = (size_t)(((n * n + 1) & ~1)) * 8 + (size_t)(3 * NV + XMAX * XMAX + XMAX * 32) * 16;
     cudaError_t err =
@@ -371,36 +519,44 @@ cudaError_t launch_reg_bw(int n, const double* Hp, long nk, double* D, double* E
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_reg_kernel<NREG, XMAX, BW, OCC><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off);
+    tridiag_reg_kernel<NREG, XMAX, BW, OCC><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off, n_stop);
     return cudaGetLastError();
 }
 
 template <int NREG, int XMAX>
-cudaError_t launch_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
-                       int off, int bw) {
+cudaError_t launch_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
+                       int off, int bw, int n_stop) {
     // bw: tuning hook.  8 = the 255-register build (8 resident warps per SM instead of 12), NREG = 32 only
-    if (bw == 8 && NREG == 32) return launch_reg_bw<NREG, XMAX, 4, (NREG == 32 ? 8 : 0)>(n, Hp, nk, D, E, st, mstride, ldo, off);
-    return launch_reg_bw<NREG, XMAX, 4, 0>(n, Hp, nk, D, E, st, mstride, ldo, off);
+    if (bw == 8 && NREG == 32)
+        return launch_reg_bw<NREG, XMAX, 4, (NREG == 32 ? 8 : 0)>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    return launch_reg_bw<NREG, XMAX, 4, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
 }
 
 }  // namespace
 
 bool tridiag_reg_fits(int n) { return n >= 2 && n <= kTridiagRegMaxN; }
 
-cudaError_t launch_tridiag_reg(int n, const double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
-                               int ldo, int off, int bw) {
+// stop: staged reduction -- the warp-per-matrix kernel stops with a stop x stop block left (2 <= stop <= 16), which the
+// half-warp kernel finishes; 0 = single launch.  Sizes follow from n only, so results never depend on the batch.
+cudaError_t launch_tridiag_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
+                               int ldo, int off, int bw, int stop) {
     if (mstride == 0) mstride = (long)n * n;
     if (ldo == 0) ldo = n;
-    if (n <= 12) return launch_reg<12, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 16) return launch_reg<16, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 20) return launch_reg<20, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 24) return launch_reg<24, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 28) return launch_reg<28, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 32) return launch_reg<32, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 36) return launch_reg<32, 4>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 40) return launch_reg<32, 8>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    if (n <= 48) return launch_reg<32, 16>(n, Hp, nk, D, E, st, mstride, ldo, off, bw);
-    return cudaErrorInvalidValue;
+    if (stop > 16) stop = 16;
+    if (stop >= 2 && n <= 16) return launch_reg_half(n, Hp, nk, D, E, st, mstride, ldo, off);
+    const int n_stop = (stop >= 2 && n >= stop + 4) ? stop : 0;
+    cudaError_t err = cudaErrorInvalidValue;
+    if (n <= 12) err = launch_reg<12, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 16) err = launch_reg<16, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 20) err = launch_reg<20, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 24) err = launch_reg<24, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 28) err = launch_reg<28, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 32) err = launch_reg<32, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 36) err = launch_reg<32, 4>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 40) err = launch_reg<32, 8>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    else if (n <= 48) err = launch_reg<32, 16>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
+    if (err != cudaSuccess || n_stop == 0) return err;
+    return launch_reg_half(n_stop, Hp, nk, D, E, st, mstride, ldo, off + (n - n_stop));
 }
 
 }  // namespace tbk

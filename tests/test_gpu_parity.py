@@ -469,6 +469,30 @@ def test_staged_tridiag_ratios(tbk, monkeypatch, ratio):
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"staged N={n_orb} ratio={ratio}")
 
 
+@pytest.mark.parametrize("stop", ["0", "2", "9", "12", "16"])
+def test_register_tridiag_staged_tail(tbk, monkeypatch, stop):
+    """Register-resident reduction handing its last `stop` rows to the two-matrices-per-warp kernel (eig_tridiag_reg.cu):
+    every hand-over size incl. none, sizes around the kernel's register / corner classes, odd batch sizes (the idle
+    half-warp shadows the last matrix), a larger model whose shared-memory stages end in the register kernel; the
+    staged and the single-launch reductions are the same sequence of reflectors, so they agree to rounding."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_REG_STOP", stop)
+    for n_orb in (21, 24, 29, 32, 33, 36, 40, 64):
+        p = wl.synthetic(n_orb, 3, seed=600 + n_orb)
+        k = np.random.default_rng(n_orb).uniform(-1, 1, size=(13, 3))
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"reg tail N={n_orb} stop={stop}")
+    # bits do not depend on the batch (one matrix alone == the same matrix inside a batch), staged or not
+    p = wl.synthetic(36, 5, seed=636)
+    k = np.random.default_rng(1).random((7, 3))
+    ev = tbk.Evaluator(p)
+    full = ev.eigenval_array(k)
+    for i in range(7):
+        assert np.array_equal(ev.eigenval_array(k[i : i + 1])[0], full[i])
+    ev.close()
+
+
 @pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
 def test_unblocked_large_kernels_still_agree(tbk, monkeypatch, n_orb):
     """The shared-memory / row-sweep kernels the blocked one replaced stay reachable (sizes 601..640, tuning hook)."""
