@@ -688,6 +688,28 @@ def run_gpu_arm(args) -> None:
         r = measure("c3", packed, total, steps, 3, ctx, None, peaks, args.e2e_nk, use_mesh=True)
         extra["c3_kgrid"] = brief(r, "c3", packed, with_cpu=False)
         extra["c3_kgrid"]["workload"] += " via eigenval_mesh"
+        if world == 1:
+            # eigenvalues + eigenvectors (extension API): 2^18 points of the same mesh
+            import torch
+
+            import tbmodels_b200 as tbk
+
+            ev = tbk.Evaluator(packed, device=dev.index)
+            n_e = 1 << 18
+            k_e = shard_k_device("c3", cfg["dims"], total, 0, n_e, packed.dim, dev, 0)
+            w_e = torch.empty((n_e, packed.size), dtype=torch.float64, device=dev)
+            v_e = torch.empty((n_e, packed.size, packed.size), dtype=torch.complex128, device=dev)
+            ev.profile(True)
+            ms_e, l_e, prof_e = time_device_steps(ev, lambda: ev.eigh_device(k_e, out_w=w_e, out_v=v_e), 2, 3, None, dev)
+            resid = (torch.linalg.norm(v_e[:8].mH @ v_e[:8] - torch.eye(packed.size, dtype=torch.complex128, device=dev)))
+            assert float(resid) < 1e-10, "eigh: eigenvectors not orthonormal"
+            extra["c3_eigh"] = {"workload": f"c3 model, eigenvalues AND eigenvectors (Evaluator.eigh_device) of {n_e} k-points per step",
+                                "value": n_e * 2 / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / 2, "steps": 2, "warmup": 3,
+                                "gpu_launches": int(l_e), "kernel_ms_per_step": {c: v[0] / 2 for c, v in prof_e.items() if v[1]},
+                                "output_bytes_per_kpoint": 8 * packed.size + 16 * packed.size**2}
+            ev.close()
+            del k_e, w_e, v_e
+            torch.cuda.empty_cache()
         # C5: N_k sweep of the strong-scaling configuration (explicit k-points of 2^m-point meshes)
         p5 = build_model("c5")
         sweep = {}

@@ -60,8 +60,7 @@ ql_global_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk,
 // Large N (> 128): the serial QL recurrence leaves the GPU idle (shared memory allows only a few threads per SM), so
 // the eigenvalues are found by bisection instead -- one CTA per matrix, one thread per eigenvalue, every thread runs
 // the same Sturm recurrence on the broadcast (d, e^2) in shared memory.  ~50 N^2 divisions per matrix, all parallel.
-constexpr int TPB_BISECT = 256;
-
+template <int TPB_BISECT>
 __global__ void __launch_bounds__(TPB_BISECT)
 bisect_kernel(double* __restrict__ D, const double* __restrict__ E, int N, long nk) {
     extern __shared__ __align__(16) double sm[];
@@ -151,21 +150,42 @@ cudaError_t launch_t(int n, double* D, double* E, long nk, int* fail_count, cuda
     return cudaGetLastError();
 }
 
+// Crossover measured on B200 (tools/tridiag_sweep.py default,bisect; ms per 1000 matrices, QL / bisection with 256 threads):
+// N = 96: 0.204 / 0.387, 112: 0.542 / 0.603, 128: 0.701 / 0.691 -- the QL kernel falls off an occupancy cliff above N = 96
+// (batch of 8192 = a partial wave); 128-thread CTAs for N <= 128 measured the same as 256 (0.688 at N = 128), so QL stays
+// up to N = 128.
 constexpr int kBisectMinN = 129;
+
+template <int TPB>
+cudaError_t launch_bisect(int n, double* D, const double* E, long nk, cudaStream_t st) {
+    const size_t smem = (size_t)2 * n * 8;
+    cudaError_t err = cudaFuncSetAttribute(bisect_kernel<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
+    bisect_kernel<TPB><<<(unsigned)nk, TPB, smem, st>>>(D, E, n, nk);
+    return cudaGetLastError();
+}
 
 cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, long* wave, const Tuning& tune) {
     const int bisect_min = tune.ql_bisect_min > 0 ? tune.ql_bisect_min : kBisectMinN;
+    if (tune.ql_global_min > 0 && n >= tune.ql_global_min) {  // experiment hook: thread-per-matrix QL in place in global memory
+        if (wave) {
+            *wave = 0;
+            return cudaSuccess;
+        }
+        const long blocks = (nk + TPB_GLOBAL - 1) / TPB_GLOBAL;
+        if (blocks > 2147483647L) return cudaErrorInvalidConfiguration;
+        ql_global_kernel<<<(unsigned)blocks, TPB_GLOBAL, 0, st>>>(D, E, n, nk, fail_count);
+        return cudaGetLastError();
+    }
     if (n >= bisect_min && (size_t)2 * n * 8 <= 200 * 1024) {
         if (wave) {
             *wave = 0;  // one CTA per matrix: no wave quantisation to respect
             return cudaSuccess;
         }
-        const size_t smem = (size_t)2 * n * 8;
-        cudaError_t err = cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-        bisect_kernel<<<(unsigned)nk, TPB_BISECT, smem, st>>>(D, E, n, nk);
-        return cudaGetLastError();
+        if (n <= 64) return launch_bisect<64>(n, D, E, nk, st);
+        if (n <= 128) return launch_bisect<128>(n, D, E, nk, st);
+        return launch_bisect<256>(n, D, E, nk, st);
     }
     switch (ql_pick_threads(n)) {
         case 128: return launch_t<128>(n, D, E, nk, fail_count, st, wave);

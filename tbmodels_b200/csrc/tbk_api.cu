@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges cost a few ns unless a profiler is attached
+
 #include "../../include/tbk.h"
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
@@ -122,6 +124,7 @@ Tuning read_tuning() {
     t.panel_pfd = env_int("TBK_PANEL_PFD", 1);
     t.ql_bisect_min = env_int("TBK_QL_BISECT_MIN", 0);
     t.gemm_dense = getenv("TBK_GEMM_DENSE") ? 1 : 0;
+    t.ql_global_min = env_int("TBK_QL_GLOBAL_MIN", 0);
     return t;
 }
 }  // namespace tbk
@@ -179,9 +182,18 @@ struct tbk_model {
     int64_t prof_n[TBK_PROFILE_CLASSES] = {0};
 };
 
+// NVTX range names of the kernel classes (tracing) -- visible in Nsight Systems / ncu --nvtx.
+static const char* const kClassName[TBK_PROFILE_CLASSES] = {"tbk:hk_gemm", "tbk:hk_small", "tbk:expand", "tbk:tridiag",
+                                                           "tbk:ql", "tbk:hk_phase", "tbk:mesh_lines", "tbk:eigh"};
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the launch stream.
 #define LAUNCH(cls, st, call)                                        \
     do {                                                             \
+        NvtxRange nvtx_(kClassName[(cls)]);                          \
         tbk_model::ProfRec rec_{nullptr, nullptr, (cls)};            \
         if (m->prof_on) {                                            \
             CU(cudaEventCreate(&rec_.a));                            \
@@ -333,6 +345,7 @@ int ensure_workspace(tbk_model* m, long nk) {
 }
 
 int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream_t st) {
+    NvtxRange nvtx_call_("tbk:eigenval");
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (md.small_ok) {
@@ -414,6 +427,7 @@ int run_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, lo
 }
 
 int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double* out, cudaStream_t st) {
+    NvtxRange nvtx_call_("tbk:hamilton");
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (int rc = ensure_workspace(m, nk)) return rc;
@@ -433,6 +447,7 @@ int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double*
 
 // eigh: H(k) build of run_hamilton (packed, in wsH) followed by the eigenvector kernel, chunk by chunk.
 int run_eigh(tbk_model* m, const double* k, long nk, double* eig, double* vec, cudaStream_t st) {
+    NvtxRange nvtx_call_("tbk:eigh_call");
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (int rc = ensure_workspace(m, nk)) return rc;
@@ -534,6 +549,7 @@ int ensure_pipeline(tbk_model* m, size_t kbytes, size_t obytes) {
 // Chunked, double-buffered host pipeline shared by the two _host entry points.
 // out_per_k: doubles written per k-point (n for eigenval, 2 n^2 for hamilton).
 int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int convention /*0 = eigenval*/) {
+    NvtxRange nvtx_call_("tbk:host_pipeline (H2D | kernels | D2H)");
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     const size_t out_per_k = convention ? (size_t)2 * md.n * md.n : (size_t)md.n;
@@ -607,6 +623,7 @@ int tbk_model_create(int dim, int n_orb, int n_R, const int32_t* R, const double
     DeviceGuard guard(device);
     if (!guard.ok) return fail(TBK_E_CUDA, "tbk_model_create: cudaSetDevice(%d) failed", device);
 
+    NvtxRange nvtx_call_("tbk:model_create (pack + upload)");
     tbk_model* m = new (std::nothrow) tbk_model();
     if (!m) return fail(TBK_E_INVALID, "out of host memory");
     m->device = device;

@@ -35,6 +35,7 @@ struct Tuning {
     int panel_lpr = 0;          // TBK_PANEL_LPR: lanes per row
     int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
     int ql_bisect_min = 0;      // TBK_QL_BISECT_MIN: bisection instead of QL from this N on (0 = default)
+    int ql_global_min = 0;      // TBK_QL_GLOBAL_MIN: thread-per-matrix QL in global memory from this N on (0 = never)
     int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)
 };
 Tuning read_tuning();

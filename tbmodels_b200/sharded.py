@@ -126,6 +126,9 @@ class ShardedEvaluator:
 
         n_k = k_all.shape[0]
         lo, hi, eig = self.eigenval_local(k_all)
+        nvtx = eig.is_cuda
+        if nvtx:
+            torch.cuda.nvtx.range_push("tbk:allgather (NCCL)")
         width = max_shard(n_k, self.world_size)
         send = eig
         if hi - lo < width:
@@ -137,6 +140,8 @@ class ShardedEvaluator:
         else:  # gloo (CPU unit tests)
             parts = list(gathered.view(self.world_size, width, self.size).unbind(0))
             dist.all_gather(parts, send.contiguous(), group=self.group)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         if width * self.world_size == n_k:
             return gathered
         out = torch.empty((n_k, self.size), dtype=eig.dtype, device=eig.device)

@@ -23,6 +23,8 @@ VARIANTS = {
     "panel256": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "256"},
     "panel512": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "512"},
     "bisect": {"TBK_QL_BISECT_MIN": "2"},
+    "ql129": {"TBK_QL_BISECT_MIN": "129"},
+    "qlglobal": {"TBK_QL_GLOBAL_MIN": "2"},
     "stop0": {"TBK_TRIDIAG_REG_STOP": "0"},
     "stop8": {"TBK_TRIDIAG_REG_STOP": "8"},
     "stop12": {"TBK_TRIDIAG_REG_STOP": "12"},
