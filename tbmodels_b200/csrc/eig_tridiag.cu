@@ -945,7 +945,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         return g == 0 && tune.tridiag_reg_max > 0 && m >= tune.tridiag_reg_min && m <= tune.tridiag_reg_max &&
                tridiag_reg_fits(m);
     };
-    if (use_reg(n)) return launch_tridiag_reg(n, Hp, nk, D, E, st, 0, 0, 0, tune.tridiag_reg_bw, tune.tridiag_reg_stop);
+    if (use_reg(n)) return launch_tridiag_reg(n, Hp, nk, D, E, st, 0, 0, 0, tune.tridiag_reg_bw, tune.tridiag_reg_stop, tune.tridiag_reg_mid);
     // Staged reduction (shared-memory kernels, 25 <= N < 120): the trailing block shrinks, so after every stage the
     // remaining (smaller) problem is relaunched with several times more matrices resident per SM -- shared memory per
     // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
@@ -966,7 +966,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         }
         // a trailing block the register kernel serves is finished there (same lower-storage reduction, one launch)
         if (cur != n && use_reg(cur))
-            return launch_tridiag_reg(cur, Hp, nk, D, E, st, ms, n, done, tune.tridiag_reg_bw, tune.tridiag_reg_stop);
+            return launch_tridiag_reg(cur, Hp, nk, D, E, st, ms, n, done, tune.tridiag_reg_bw, tune.tridiag_reg_stop, tune.tridiag_reg_mid);
         const int nsteps = next ? cur - next : (1 << 30);
         int gg = g, cc = cs;
         if (gg == 0) {  // defaults, from the size only

@@ -108,7 +108,7 @@ __device__ __forceinline__ void row_update(double (&ar)[NMAX], double (&ai)[NMAX
 
 template <int NREG, int OCC>
 constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers are per SM sub-partition: 16 K each)
-    return OCC ? OCC : (NREG <= 20 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
+    return OCC ? OCC : (NREG <= 24 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
 }
 
 // NREG: columns (and rows) held in registers, a multiple of 4 up to 32.  XMAX: capacity for the rows / columns beyond 32
@@ -536,27 +536,39 @@ cudaError_t launch_reg(int n, double* Hp, long nk, double* D, double* E, cudaStr
 
 bool tridiag_reg_fits(int n) { return n >= 2 && n <= kTridiagRegMaxN; }
 
-// stop: staged reduction -- the warp-per-matrix kernel stops with a stop x stop block left (2 <= stop <= 16), which the
-// half-warp kernel finishes; 0 = single launch.  Sizes follow from n only, so results never depend on the batch.
+// Staged reduction (stop >= 2): the warp-per-matrix kernels hand a shrinking trailing block from launch to launch --
+//   n > 28:  n -> mid (24) with the 168-register build (12 warps per SM),
+//   n > 16:  -> stop (16) with the 24-column build (128 registers, 16 warps per SM),
+//   then the two-matrices-per-warp kernel finishes the stop x stop block.
+// Late steps are latency bound (two warp reductions and the reflector against a few hundred FMAs), so every stage trades
+// registers for resident warps as soon as the block allows.  mid = 0 skips the middle stage, stop = 0 is a single launch.
+// Stage sizes follow from n only, so results never depend on the batch.
 cudaError_t launch_tridiag_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
-                               int ldo, int off, int bw, int stop) {
+                               int ldo, int off, int bw, int stop, int mid) {
     if (mstride == 0) mstride = (long)n * n;
     if (ldo == 0) ldo = n;
     if (stop > 16) stop = 16;
-    if (stop >= 2 && n <= 16) return launch_reg_half(n, Hp, nk, D, E, st, mstride, ldo, off);
-    const int n_stop = (stop >= 2 && n >= stop + 4) ? stop : 0;
-    cudaError_t err = cudaErrorInvalidValue;
-    if (n <= 12) err = launch_reg<12, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 16) err = launch_reg<16, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 20) err = launch_reg<20, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 24) err = launch_reg<24, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 28) err = launch_reg<28, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 32) err = launch_reg<32, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 36) err = launch_reg<32, 4>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 40) err = launch_reg<32, 8>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    else if (n <= 48) err = launch_reg<32, 16>(n, Hp, nk, D, E, st, mstride, ldo, off, bw, n_stop);
-    if (err != cudaSuccess || n_stop == 0) return err;
-    return launch_reg_half(n_stop, Hp, nk, D, E, st, mstride, ldo, off + (n - n_stop));
+    if (stop < 2) stop = 0;
+    if (mid > 24 || mid <= stop) mid = 0;
+    int cur = n;
+    while (true) {
+        if (stop && cur <= 16) return launch_reg_half(cur, Hp, nk, D, E, st, mstride, ldo, off);
+        int next = 0;
+        if (stop && cur >= stop + 4) next = (mid && cur >= mid + 4) ? mid : stop;
+        cudaError_t err = cudaErrorInvalidValue;
+        if (cur <= 12) err = launch_reg<12, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 16) err = launch_reg<16, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 20) err = launch_reg<20, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 24) err = launch_reg<24, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 28) err = launch_reg<28, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 32) err = launch_reg<32, 0>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 36) err = launch_reg<32, 4>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 40) err = launch_reg<32, 8>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        else if (cur <= 48) err = launch_reg<32, 16>(cur, Hp, nk, D, E, st, mstride, ldo, off, bw, next);
+        if (err != cudaSuccess || next == 0) return err;
+        off += cur - next;
+        cur = next;
+    }
 }
 
 }  // namespace tbk

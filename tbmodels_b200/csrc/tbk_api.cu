@@ -119,6 +119,7 @@ Tuning read_tuning() {
     if (t.tridiag_reg_max > kTridiagRegMaxN) t.tridiag_reg_max = kTridiagRegMaxN;
     t.tridiag_reg_bw = env_int("TBK_TRIDIAG_REG_BW", t.tridiag_reg_bw);
     t.tridiag_reg_stop = env_int("TBK_TRIDIAG_REG_STOP", t.tridiag_reg_stop);
+    t.tridiag_reg_mid = env_int("TBK_TRIDIAG_REG_MID", t.tridiag_reg_mid);
     t.panel_t = env_int("TBK_PANEL_T", 0);
     t.panel_lpr = env_int("TBK_PANEL_LPR", 0);
     t.panel_pfd = env_int("TBK_PANEL_PFD", 1);

@@ -31,6 +31,8 @@ struct Tuning {
     int tridiag_reg_bw = 4;     // TBK_TRIDIAG_REG_BW: columns per unrolled block of the register kernel (4 / 8)
     int tridiag_reg_stop = 16;  // TBK_TRIDIAG_REG_STOP: staged register reduction, the two-matrices-per-warp kernel takes
                                 //   over at this block size (2 .. 16; 0 = single launch)
+    int tridiag_reg_mid = 24;   // TBK_TRIDIAG_REG_MID: middle stage of the staged register reduction (128-register build
+                                //   from this block size down to _STOP; 0 = none)
     int panel_t = 0;            // TBK_PANEL_T: blocked kernel: threads per matrix
     int panel_lpr = 0;          // TBK_PANEL_LPR: lanes per row
     int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
@@ -108,7 +110,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
 // packed n x n block at Hp + k * mstride; results go to D / E [k * ldo + off + i] (mstride = 0 -> n * n, ldo = 0 -> n).
 bool tridiag_reg_fits(int n);
 cudaError_t launch_tridiag_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
-                               int ldo, int off, int bw, int stop);
+                               int ldo, int off, int bw, int stop, int mid);
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
 bool tridiag_panel_fits(int n);
 cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);

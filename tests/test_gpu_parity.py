@@ -469,8 +469,9 @@ def test_staged_tridiag_ratios(tbk, monkeypatch, ratio):
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"staged N={n_orb} ratio={ratio}")
 
 
+@pytest.mark.parametrize("mid", ["24", "0", "21"])
 @pytest.mark.parametrize("stop", ["0", "2", "9", "12", "16"])
-def test_register_tridiag_staged_tail(tbk, monkeypatch, stop):
+def test_register_tridiag_staged_tail(tbk, monkeypatch, stop, mid):
     """Register-resident reduction handing its last `stop` rows to the two-matrices-per-warp kernel (eig_tridiag_reg.cu):
     every hand-over size incl. none, sizes around the kernel's register / corner classes, odd batch sizes (the idle
     half-warp shadows the last matrix), a larger model whose shared-memory stages end in the register kernel; the
@@ -479,7 +480,8 @@ def test_register_tridiag_staged_tail(tbk, monkeypatch, stop):
 
     orc = _oracle()
     monkeypatch.setenv("TBK_TRIDIAG_REG_STOP", stop)
-    for n_orb in (21, 24, 29, 32, 33, 36, 40, 64):
+    monkeypatch.setenv("TBK_TRIDIAG_REG_MID", mid)
+    for n_orb in (21, 24, 25, 28, 29, 32, 33, 36, 40, 64):
         p = wl.synthetic(n_orb, 3, seed=600 + n_orb)
         k = np.random.default_rng(n_orb).uniform(-1, 1, size=(13, 3))
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"reg tail N={n_orb} stop={stop}")

@@ -30,6 +30,9 @@ VARIANTS = {
     "stop12": {"TBK_TRIDIAG_REG_STOP": "12"},
     "stop16": {"TBK_TRIDIAG_REG_STOP": "16"},
     "half16": {"TBK_TRIDIAG_REG_MIN": "2"},
+    "mid0": {"TBK_TRIDIAG_REG_MID": "0"},
+    "mid20": {"TBK_TRIDIAG_REG_MID": "20"},
+    "mid24": {"TBK_TRIDIAG_REG_MID": "24"},
 }
 KEYS = sorted({k for v in VARIANTS.values() for k in v})
 
