@@ -108,7 +108,7 @@ __device__ __forceinline__ void row_update(double (&ar)[NMAX], double (&ai)[NMAX
 
 template <int NREG, int OCC>
 constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers are per SM sub-partition: 16 K each)
-    return OCC ? OCC : (NREG <= 24 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
+    return OCC ? OCC : (NREG <= 20 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
 }
 
 // NREG: columns (and rows) held in registers, a multiple of 4 up to 32.  XMAX: capacity for the rows / columns beyond 32
@@ -540,8 +540,10 @@ bool tridiag_reg_fits(int n) { return n >= 2 && n <= kTridiagRegMaxN; }
 //   n > 28:  n -> mid (24) with the 168-register build (12 warps per SM),
 //   n > 16:  -> stop (16) with the 24-column build (128 registers, 16 warps per SM),
 //   then the two-matrices-per-warp kernel finishes the stop x stop block.
-// Late steps are latency bound (two warp reductions and the reflector against a few hundred FMAs), so every stage trades
-// registers for resident warps as soon as the block allows.  mid = 0 skips the middle stage, stop = 0 is a single launch.
+// Late steps are latency bound (two warp reductions and the reflector against a few hundred FMAs), so a stage trades
+// registers for resident warps as soon as the block allows.  mid = 0 skips the middle stage (the default: measured on
+// B200 the extra hand-over costs more than the fourth warp per scheduler gains -- N = 36: 0.038 ms per 1000 matrices
+// without, 0.043 with mid = 24, gpurun_out/r02o_sweep.log), stop = 0 is a single launch.
 // Stage sizes follow from n only, so results never depend on the batch.
 cudaError_t launch_tridiag_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride,
                                int ldo, int off, int bw, int stop, int mid) {

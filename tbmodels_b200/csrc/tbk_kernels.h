@@ -31,8 +31,8 @@ struct Tuning {
     int tridiag_reg_bw = 4;     // TBK_TRIDIAG_REG_BW: columns per unrolled block of the register kernel (4 / 8)
     int tridiag_reg_stop = 16;  // TBK_TRIDIAG_REG_STOP: staged register reduction, the two-matrices-per-warp kernel takes
                                 //   over at this block size (2 .. 16; 0 = single launch)
-    int tridiag_reg_mid = 24;   // TBK_TRIDIAG_REG_MID: middle stage of the staged register reduction (128-register build
-                                //   from this block size down to _STOP; 0 = none)
+    int tridiag_reg_mid = 0;    // TBK_TRIDIAG_REG_MID: optional middle stage of the staged register reduction (a smaller
+                                //   build from this block size down to _STOP; 0 = none, the measured best)
     int panel_t = 0;            // TBK_PANEL_T: blocked kernel: threads per matrix
     int panel_lpr = 0;          // TBK_PANEL_LPR: lanes per row
     int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
