@@ -928,17 +928,23 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
 
 }  // namespace
 
+constexpr int kPanelMinN = 161;   // blocked kernel from this size on (re-measured in round 2, see below)
+constexpr int kStagedMaxN = 160;  // staged shared-memory reduction while the packed matrix + work vectors fit 227 KB
+
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
     const int g = tune.tridiag_g, cs = tune.tridiag_cs;  // tuning hooks: threads per matrix / column slices
     if (g == 1) return launch_mma(n, Hp, nk, D, E, st);
-    if (tune.tridiag_panel_min > 0) {  // tuning hook: blocked kernel from this size on
-        if (n >= tune.tridiag_panel_min && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
-    }
+    const int panel_from = tune.tridiag_panel_min > 0 ? tune.tridiag_panel_min : kPanelMinN;  // tuning hook
+    if (tune.tridiag_panel_min > 0 && n >= panel_from && tridiag_panel_fits(n))
+        return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
     // (the tensor-core variant launch_mma is correct for n <= 64 but, with only ~9 single-warp CTAs resident per
     //  SM, it is latency bound and measured 35 % slower than the packed kernel on B200: opt-in via TBK_TRIDIAG_G=1)
-    // blocked kernel (eig_tridiag_panel.cu) from N = 120 on: measured on B200, ms per 1000 matrices smem / blocked:
-    // N = 100: 1.47 / 1.95, 128: 3.65 / 3.31, 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125
-    if (g == 0 && n >= 120 && !tune.tridiag_nopanel && tridiag_panel_fits(n))
+    // blocked kernel (eig_tridiag_panel.cu) where the packed matrix no longer fits in shared memory (N > 160).  Measured
+    // on B200, ms per 1000 matrices, single-launch smem / blocked (round 1): N = 100: 1.47 / 1.95, 128: 3.65 / 3.31,
+    // 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125; round 2, STAGED smem reduction ending in the register
+    // kernels / blocked: N = 120: 2.46 / 2.74, 128: 2.84 / 3.11, 136: 3.38 / 4.22, 144: 4.16 / 4.71, 160: 5.30 / 5.81
+    // (gpurun_out/r02q_sweep.log) -- so the staged reduction now serves every size that fits.
+    if (g == 0 && n >= panel_from && !tune.tridiag_nopanel && tridiag_panel_fits(n))
         return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
     // register-resident warp-per-matrix kernel (eig_tridiag_reg.cu): the whole reduction in one launch
     const auto use_reg = [&](int m) {
@@ -951,7 +957,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
     // on the batch): N -> ratio * N -> ... until <= 16.  TBK_TRIDIAG_STAGES="0" disables, "p" sets the ratio in percent.
     const int ratio = tune.tridiag_stages;
-    const bool staged = g == 0 && n >= 25 && n < 120 && ratio > 0 && ratio < 100;
+    const bool staged = g == 0 && n >= 25 && n <= kStagedMaxN && ratio > 0 && ratio < 100;  // (above: not in shared memory)
     const long ms = (long)n * n;
     int cur = n, done = 0;
     for (;;) {

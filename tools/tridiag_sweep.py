@@ -30,6 +30,18 @@ VARIANTS = {
     "stop12": {"TBK_TRIDIAG_REG_STOP": "12"},
     "stop16": {"TBK_TRIDIAG_REG_STOP": "16"},
     "half16": {"TBK_TRIDIAG_REG_MIN": "2"},
+    "nopanel": {"TBK_TRIDIAG_NOPANEL": "1"},
+    "panel200": {"TBK_TRIDIAG_PANEL_MIN": "200"},
+    "panel120": {"TBK_TRIDIAG_PANEL_MIN": "120"},
+    "g512c4": {"TBK_TRIDIAG_G": "512", "TBK_TRIDIAG_CS": "4"},
+    "g512c8": {"TBK_TRIDIAG_G": "512", "TBK_TRIDIAG_CS": "8"},
+    "g256c8": {"TBK_TRIDIAG_G": "256", "TBK_TRIDIAG_CS": "8"},
+    "g256c2": {"TBK_TRIDIAG_G": "256", "TBK_TRIDIAG_CS": "2"},
+    "st50": {"TBK_TRIDIAG_STAGES": "50"},
+    "st80": {"TBK_TRIDIAG_STAGES": "80"},
+    "st75": {"TBK_TRIDIAG_STAGES": "75"},
+    "st85": {"TBK_TRIDIAG_STAGES": "85"},
+    "st90": {"TBK_TRIDIAG_STAGES": "90"},
     "mid0": {"TBK_TRIDIAG_REG_MID": "0"},
     "mid20": {"TBK_TRIDIAG_REG_MID": "20"},
     "mid24": {"TBK_TRIDIAG_REG_MID": "24"},
