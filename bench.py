@@ -7,8 +7,11 @@ Default workload: BASELINE.json configs[2] (C3: synthetic 36-orbital Wannier mod
 256^3 k-grid), the configuration the north_star target is quoted on.  One "step" = one pass of the hot path over the
 WHOLE k-set of the configuration: the k-points are cut into contiguous shards, one per GPU (strong scaling: total work
 is fixed as N grows), every rank evaluates its shard with the CUDA kernels and -- for N > 1 -- the eigenvalue shards
-are gathered with NCCL (all_gather_into_tensor over NVLink) so that every rank holds the full [N_k, N] result.  The
-gather is INSIDE the timed region.  Rank 0 prints ONE JSON line.
+are exchanged so that every rank holds the full [N_k, N] result, INSIDE the timed region.
+The exchange is fused behind the eigensolver: every finished chunk is stored straight into all peers' result buffers
+over NVLink / NVSwitch (tbk_eigenval_push on a symmetric-memory buffer) while the next chunk computes, then one
+device-side barrier; the plain "compute, then NCCL all_gather_into_tensor" variant is timed next to it
+(`nccl_variant_ms_per_step`) and the two results are compared bit for bit.  Rank 0 prints ONE JSON line.
 
   value        device-resident throughput: k [N_k, D] already in HBM -> gathered eigenvalues in HBM; CUDA events on the
                launching stream, max over ranks
@@ -517,17 +520,39 @@ def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=Non
     else:
         compute = lambda: ev.eigenval_device(k_dev, out=out_dev)  # noqa: E731
 
-    def step():
-        compute()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out_dev)
+    # N > 1: the exchange step.  Product path = FUSED gather: every chunk's rows are stored straight into all peers'
+    # result buffers over NVLink while the next chunk computes (tbk_eigenval_push on a symmetric-memory buffer), then one
+    # device-side barrier.  Baseline variant = compute, then NCCL all_gather_into_tensor; timed too and compared bit for bit.
+    gather_kind, fused_err, pg = "none", None, None
+    if world > 1 and not use_mesh and not args_no_fused():
+        try:
+            from tbmodels_b200.sharded import PeerGather
 
+            pg = PeerGather(total, packed.size, device=dev)
+            gather_kind = "fused peer stores (tbk_eigenval_push over symmetric memory) + device-side barrier"
+        except Exception as e:  # noqa: BLE001 -- recorded in the JSON line, never silent
+            fused_err = f"{type(e).__name__}: {e}"
+            pg = None
+    if world > 1 and pg is None:
+        gather_kind = "NCCL all_gather_into_tensor after the local evaluation"
+
+    def step_nccl():
+        compute()
+        dist.all_gather_into_tensor(gathered, out_dev)
+
+    def step_fused():
+        ev.eigenval_push_device(k_dev, pg.buffer[lo:hi], pg.peer_ptrs, lo)
+        pg.barrier()
+
+    step = compute if world == 1 else (step_fused if pg is not None else step_nccl)
     ms, launches, prof = time_device_steps(ev, step, steps, warmup, dist, dev, sampler)
     value = total * steps / (ms * 1e-3)
 
-    # gather time alone (same buffers), for the record
-    gather_ms = None
+    # the NCCL variant of the same step, for the record (and the gather alone)
+    gather_ms = nccl_ms_per_step = None
     if world > 1:
+        ms_n, _, _ = time_device_steps(ev, step_nccl, steps, 1, dist, dev, None)
+        nccl_ms_per_step = ms_n / steps
         torch.cuda.synchronize()
         dist.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -536,6 +561,9 @@ def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=Non
         g1.record()
         torch.cuda.synchronize()
         gather_ms = g0.elapsed_time(g1)
+        if pg is not None:
+            assert torch.equal(pg.buffer, gathered), "fused peer-store gather and NCCL all-gather disagree"
+            out_dev.copy_(pg.buffer[lo:hi])
 
     # ---- parity inside the bench: sorted + finite; the NCCL-gathered rows of EVERY rank's shard against a single-rank
     # evaluation of the same k-points on this GPU (bit-exact: a k-point's bits do not depend on batch or shard) ----
@@ -619,14 +647,25 @@ def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=Non
         "kernels": kern,
         "kernel_ms_per_step": {c: v[0] / steps for c, v in prof.items() if v[1]},
         "allgather_ms": gather_ms,
+        "gather": gather_kind,
+        "gather_fallback_reason": fused_err,
+        "nccl_variant_ms_per_step": nccl_ms_per_step,
         "gather_rows_checked": gather_checked,
         "fl": fl,
         "mesh": mesh_cfg,
     }
     ev.close()
     del k_dev, out_dev, gathered, k_host, out_host
+    pg = None
     torch.cuda.empty_cache()
     return res
+
+
+_NO_FUSED = [False]
+
+
+def args_no_fused() -> bool:
+    return _NO_FUSED[0]
 
 
 def l2_note(res, packed):
@@ -674,7 +713,8 @@ def run_gpu_arm(args) -> None:
 
     def brief(res, workload, pk, with_cpu=True):
         rec = {k: res[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "kpoints_total", "kpoints_per_gpu", "path",
-                                   "gpu_launches", "e2e", "roofline", "kernel_ms_per_step", "allgather_ms")}
+                                   "gpu_launches", "e2e", "roofline", "kernel_ms_per_step", "allgather_ms", "gather",
+                                   "nccl_variant_ms_per_step")}
         rec["workload"] = f"{workload}: {WORKLOADS[workload]['desc']}"
         if res.get("mesh"):
             rec["mesh"] = res["mesh"]
@@ -717,7 +757,7 @@ def run_gpu_arm(args) -> None:
             if (1 << e) % world:
                 continue
             r = measure("c5", p5, 1 << e, 3 if e <= 16 else 1, 3 if e <= 16 else 1, ctx, None, peaks, 1 << 14)
-            sweep[f"2^{e}"] = {k: r[k] for k in ("value", "ms_per_step", "kpoints_per_gpu", "kernel_ms_per_step", "allgather_ms", "steps", "warmup")}
+            sweep[f"2^{e}"] = {k: r[k] for k in ("value", "ms_per_step", "kpoints_per_gpu", "kernel_ms_per_step", "allgather_ms", "gather", "nccl_variant_ms_per_step", "steps", "warmup")}
             if e == 14 or (e == 16 and "c5" not in extra):
                 extra["c5"] = brief(r, "c5", p5, with_cpu=(e == 14))
         extra["c5_sweep"] = {"workload": "c5: " + WORKLOADS["c5"]["desc"].split(",")[0] + ", N_k = 2^14 .. 2^20 (total, strong scaling)",
@@ -761,7 +801,7 @@ def run_gpu_arm(args) -> None:
                 "n_R_stored": packed.n_R,
                 "dim": packed.dim,
                 "path": main["path"],
-                "parallelism": f"contiguous k-shards x{world}" + (", NCCL all_gather_into_tensor of the eigenvalue shards inside the timed region" if world > 1 else ""),
+                "parallelism": f"contiguous k-shards x{world}" + (f", exchange inside the timed region: {main['gather']}" if world > 1 else ""),
                 "l2": l2_note(main, packed),
                 **({"mesh": main["mesh"]} if main.get("mesh") else {}),
             },
@@ -774,6 +814,9 @@ def run_gpu_arm(args) -> None:
             "fp64_peak_tflops": peaks,
             "kernel_ms_per_step": main["kernel_ms_per_step"],
             "allgather_ms": main["allgather_ms"],
+            "gather": main["gather"],
+            "gather_fallback_reason": main["gather_fallback_reason"],
+            "nccl_variant_ms_per_step": main["nccl_variant_ms_per_step"],
             "gather_rows_checked_bit_exact": main["gather_rows_checked"],
             "extra": extra,
         }
@@ -796,7 +839,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-peaks", action="store_true")
     ap.add_argument("--mesh", action="store_true", help="c1 / c3 / c5: evaluate the workload's k-grid through eigenval_mesh")
+    ap.add_argument("--no-fused-gather", action="store_true", help="N > 1: NCCL all-gather after the evaluation instead of the fused peer stores")
     args = ap.parse_args()
+    _NO_FUSED[0] = args.no_fused_gather
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -81,6 +81,17 @@ int tbk_hamilton(tbk_model* m, const double* k_dev, int64_t n_k, int convention,
  *   out_dev [n_k][n_orb] f64 device */
 int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* stream);
 
+/* Multi-GPU form of tbk_eigenval (the all-gather fused behind the eigensolver).  out_dev is this
+ * rank's slice -- starting at row `row_offset` -- of a result buffer that exists on every GPU; peer_bases[p] are the
+ * base addresses of the OTHER ranks' buffers, peer-mapped into this process (e.g. the buffer_ptrs of a
+ * torch.distributed._symmetric_memory rendezvous, or cudaIpc / cuMem handles).  After every workspace chunk its rows are
+ * stored into all peers at the same row offset by a copy kernel on a side stream (16-byte stores over NVLink /
+ * NVSwitch), overlapping the next chunk's kernels; `stream` continues once the last store has completed.  The CALLER
+ * synchronises the ranks afterwards (a device-side barrier of the symmetric-memory handle, or any collective) before
+ * any rank reads rows it did not compute.  n_peers = 0 degenerates to tbk_eigenval. */
+int tbk_eigenval_push(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* const* peer_bases, int n_peers,
+                      int64_t row_offset, void* stream);
+
 /* Model.eigenval on a regular k-mesh without an explicit k array: the mesh has dims[d]
  * points in dimension d, k_d = (i_d + shift_d) / dims[d] (shift may be NULL), ordered like
  * numpy.meshgrid(..., indexing="ij") flattened in C order -- the layout of the reference's k-grid workloads.  A LINE
@@ -128,10 +139,10 @@ int64_t tbk_launch_count(const tbk_model* m);
 /* Per-kernel-class device timing with CUDA events recorded on the launching stream.
  * Classes: 0 H(k) DMMA GEMM, 1 fused small-N kernel, 2 expand (and the k.p coefficient kernel), 3 tridiagonalisation,
  * 4 tridiagonal QL, 5 phase tiles for the GEMM (and the small mesh helper kernels), 6 line expansion of the regular-mesh
- * path, 7 eigen-decomposition with eigenvectors.
+ * path, 7 eigen-decomposition with eigenvectors, 8 peer stores of tbk_eigenval_push.
  * tbk_profile(m, 1) starts recording; tbk_profile_read synchronises, returns the accumulated milliseconds
  * and launch counts per class since the last read (arrays of TBK_PROFILE_CLASSES) and resets them. */
-#define TBK_PROFILE_CLASSES 8
+#define TBK_PROFILE_CLASSES 9
 int tbk_profile(tbk_model* m, int enable);
 int tbk_profile_read(tbk_model* m, double* ms, int64_t* count);
 /* Bytes of device scratch currently held by the handle. */

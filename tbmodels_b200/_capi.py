@@ -24,6 +24,7 @@ SYMBOLS = (
     "tbk_model_info",
     "tbk_hamilton",
     "tbk_eigenval",
+    "tbk_eigenval_push",
     "tbk_eigenval_mesh",
     "tbk_mesh_factorised",
     "tbk_eigh",
@@ -93,6 +94,8 @@ def load() -> C.CDLL:
     lib.tbk_hamilton.restype = C.c_int
     lib.tbk_eigenval.argtypes = [vp, vp, C.c_int64, vp, vp]
     lib.tbk_eigenval.restype = C.c_int
+    lib.tbk_eigenval_push.argtypes = [vp, vp, C.c_int64, vp, C.POINTER(vp), C.c_int, C.c_int64, vp]
+    lib.tbk_eigenval_push.restype = C.c_int
     lib.tbk_eigenval_mesh.argtypes = [vp, C.POINTER(C.c_int64), dp, C.c_int64, C.c_int64, vp, vp]
     lib.tbk_eigenval_mesh.restype = C.c_int
     lib.tbk_mesh_factorised.argtypes = [vp, C.POINTER(C.c_int64)]

@@ -191,7 +191,7 @@ class Evaluator:
     def workspace_bytes(self) -> int:
         return int(self._lib.tbk_workspace_bytes(self._handle))
 
-    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase", "mesh_lines", "eigh")
+    PROFILE_CLASSES = ("hk_gemm", "hk_small", "expand", "tridiag", "ql", "hk_phase", "mesh_lines", "eigh", "peer_push")
 
     def profile(self, enable: bool = True) -> None:
         """Bracket every kernel launch with CUDA events on its stream (read back with :meth:`profile_read`)."""
@@ -451,6 +451,27 @@ class Evaluator:
             )
         )
         return out
+
+
+def _eigenval_push(self, k_dev, out, peer_ptrs, row_offset):
+    """``eigenval_device`` whose chunks are also stored into the peers' result buffers (``tbk_eigenval_push``)."""
+    k_dev = self._check_k_dev(k_dev)
+    n_k = k_dev.shape[0]
+    import torch
+
+    if tuple(out.shape) != (n_k, self.size) or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float64 tensor [n_k, N]")
+    arr = (C.c_void_p * max(len(peer_ptrs), 1))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+    _capi.check(
+        self._lib.tbk_eigenval_push(
+            self._handle, C.c_void_p(k_dev.data_ptr()), n_k, C.c_void_p(out.data_ptr()), arr, len(peer_ptrs),
+            int(row_offset), self._stream(),
+        )
+    )
+    return out
+
+
+Evaluator.eigenval_push_device = _eigenval_push
 
 
 def _default_device() -> int:

@@ -956,7 +956,7 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     // remaining (smaller) problem is relaunched with several times more matrices resident per SM -- shared memory per
     // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
     // on the batch): N -> ratio * N -> ... until <= 16.  TBK_TRIDIAG_STAGES="0" disables, "p" sets the ratio in percent.
-    const int ratio = tune.tridiag_stages;
+    const int ratio = tune.tridiag_stages >= 0 ? tune.tridiag_stages : ((n >= 88 && n <= 140) ? 80 : 67);
     const bool staged = g == 0 && n >= 25 && n <= kStagedMaxN && ratio > 0 && ratio < 100;  // (above: not in shared memory)
     const long ms = (long)n * n;
     int cur = n, done = 0;

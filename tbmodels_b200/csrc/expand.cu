@@ -85,6 +85,50 @@ expand_block_kernel(const double* __restrict__ Hp, const double* __restrict__ kp
 
 }  // namespace
 
+// Multi-GPU exchange step fused behind the eigensolver: the rows one chunk just produced are
+// stored straight into the result buffers of the peer GPUs (peer-mapped memory over NVLink / NVSwitch), while the next
+// chunk computes.  One grid-stride pass, 16-byte stores, every peer gets the same rows at the same offset.
+constexpr int kMaxPeers = 15;
+struct PeerList {
+    double* base[kMaxPeers];
+    int n;
+};
+
+__global__ void __launch_bounds__(256)
+push_rows_kernel(const double* __restrict__ src, long n_doubles, PeerList peers, long dst_offset) {
+    const long stride = (long)gridDim.x * blockDim.x;
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((unsigned long long)src | (unsigned long long)(dst_offset * 8)) & 15ull) == 0) {
+        const long n2 = n_doubles >> 1;
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        for (long i = i0; i < n2; i += stride) {
+            const double2 v = s2[i];
+            for (int p = 0; p < peers.n; ++p) reinterpret_cast<double2*>(peers.base[p] + dst_offset)[i] = v;
+        }
+        if ((n_doubles & 1) && i0 == 0)
+            for (int p = 0; p < peers.n; ++p) peers.base[p][dst_offset + n_doubles - 1] = src[n_doubles - 1];
+    } else {
+        for (long i = i0; i < n_doubles; i += stride) {
+            const double v = src[i];
+            for (int p = 0; p < peers.n; ++p) peers.base[p][dst_offset + i] = v;
+        }
+    }
+}
+
+cudaError_t launch_push_rows(const double* src, long n_doubles, double* const* peer_bases, int n_peers, long dst_offset,
+                             cudaStream_t st) {
+    if (n_doubles <= 0 || n_peers <= 0) return cudaSuccess;
+    if (n_peers > kMaxPeers) return cudaErrorInvalidValue;
+    PeerList pl;
+    pl.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) pl.base[p] = peer_bases[p];
+    long blocks = (n_doubles / 2 + 255) / 256;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    if (blocks < 1) blocks = 1;
+    push_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_doubles, pl, dst_offset);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention, double* out,
                           cudaStream_t st) {
     if (nk <= 0 || md.n <= 0) return cudaSuccess;

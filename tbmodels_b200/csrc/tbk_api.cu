@@ -166,6 +166,9 @@ struct tbk_model {
     double* ho[2] = {nullptr, nullptr};
     size_t hk_bytes = 0, ho_bytes = 0;
     int64_t launches = 0;
+    // peer push of the multi-GPU entry point (tbk_eigenval_push): side stream + events ordering it against the chunks
+    cudaStream_t s_push = nullptr;
+    cudaEvent_t ev_chunk = nullptr, ev_push = nullptr;
     // The handle has ONE scratch set (wsH / wsE / wsQ / ...).  Every entry point records ev_busy on the stream it used
     // when its launches are queued and makes its stream wait on the previous record first, so calls on different
     // streams (a device-pointer call on a torch stream followed by a _host call on s_comp, two torch streams, ...)
@@ -185,7 +188,8 @@ struct tbk_model {
 
 // NVTX range names of the kernel classes (tracing) -- visible in Nsight Systems / ncu --nvtx.
 static const char* const kClassName[TBK_PROFILE_CLASSES] = {"tbk:hk_gemm", "tbk:hk_small", "tbk:expand", "tbk:tridiag",
-                                                           "tbk:ql", "tbk:hk_phase", "tbk:mesh_lines", "tbk:eigh"};
+                                                           "tbk:ql", "tbk:hk_phase", "tbk:mesh_lines", "tbk:eigh",
+                                                           "tbk:peer_push"};
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
@@ -345,12 +349,35 @@ int ensure_workspace(tbk_model* m, long nk) {
     return TBK_OK;
 }
 
-int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream_t st) {
+// Peer destinations of tbk_eigenval_push: after every chunk its rows are stored into the peers' buffers on a side stream.
+struct PushPlan {
+    double* const* bases = nullptr;
+    int n = 0;
+    long row_offset = 0;  // row of out[0] inside the peers' buffers
+};
+
+int push_chunk(tbk_model* m, const PushPlan& plan, const double* rows, long first_row, long n_rows, cudaStream_t st) {
+    if (plan.n <= 0 || n_rows <= 0) return TBK_OK;
+    CU(cudaEventRecord(m->ev_chunk, st));
+    CU(cudaStreamWaitEvent(m->s_push, m->ev_chunk, 0));
+    LAUNCH(8, m->s_push, launch_push_rows(rows, n_rows * m->md.n, plan.bases, plan.n, (plan.row_offset + first_row) * m->md.n,
+                                          m->s_push));
+    return TBK_OK;
+}
+
+int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream_t st, const PushPlan* plan = nullptr) {
     NvtxRange nvtx_call_("tbk:eigenval");
     const ModelDev& md = m->md;
     if (nk <= 0) return TBK_OK;
     if (md.small_ok) {
-        LAUNCH(1, st, launch_hk_small(md, k, nk, nullptr, out, m->dFail, st));
+        // fused small-N kernel: cut the batch into a few launches so that the peer stores overlap the next launch
+        const long step = plan ? std::max<long>(1L << 20, (nk + 7) / 8) : nk;
+        for (long c0 = 0; c0 < nk; c0 += step) {
+            const long cn = std::min(step, nk - c0);
+            LAUNCH(1, st, launch_hk_small(md, k + c0 * md.dim, cn, nullptr, out + c0 * md.n, m->dFail, st));
+            if (plan)
+                if (int rc = push_chunk(m, *plan, out + c0 * md.n, c0, cn, st)) return rc;
+        }
         return TBK_OK;
     }
     if (int rc = ensure_workspace(m, nk)) return rc;
@@ -361,6 +388,8 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
         LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
         LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st, md.tune));
         LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st, md.tune));
+        if (plan)
+            if (int rc = push_chunk(m, *plan, D, c0, cn, st)) return rc;
     }
     return TBK_OK;
 }
@@ -1025,6 +1054,9 @@ int tbk_model_destroy(tbk_model* m) {
         if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
     }
     if (m->ev_busy) cudaEventDestroy(m->ev_busy);
+    if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
+    if (m->ev_push) cudaEventDestroy(m->ev_push);
+    if (m->s_push) cudaStreamDestroy(m->s_push);
     if (m->s_in) cudaStreamDestroy(m->s_in);
     if (m->s_comp) cudaStreamDestroy(m->s_comp);
     if (m->s_out) cudaStreamDestroy(m->s_out);
@@ -1061,6 +1093,35 @@ int tbk_eigenval(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev
     if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
     if (int rc = run_eigenval(m, k_dev, (long)n_k, out_dev, (cudaStream_t)stream)) return rc;
     return scratch_release(m, (cudaStream_t)stream);
+}
+
+int tbk_eigenval_push(tbk_model* m, const double* k_dev, int64_t n_k, double* out_dev, void* const* peer_bases, int n_peers,
+                      int64_t row_offset, void* stream) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigenval_push: null handle");
+    if (n_k < 0 || (n_k > 0 && (!k_dev || !out_dev))) return fail(TBK_E_INVALID, "tbk_eigenval_push: bad buffers");
+    if (n_peers < 0 || n_peers > 15 || (n_peers > 0 && !peer_bases) || row_offset < 0)
+        return fail(TBK_E_INVALID, "tbk_eigenval_push: bad peer list (0 .. 15 peers)");
+    for (int p = 0; p < n_peers; ++p)
+        if (!peer_bases[p]) return fail(TBK_E_INVALID, "tbk_eigenval_push: peer %d has a null base pointer", p);
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!m->s_push) {
+        CU(cudaStreamCreateWithFlags(&m->s_push, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&m->ev_chunk, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&m->ev_push, cudaEventDisableTiming));
+    }
+    if (int rc = scratch_acquire(m, st)) return rc;
+    PushPlan plan;
+    plan.bases = reinterpret_cast<double* const*>(peer_bases);
+    plan.n = n_peers;
+    plan.row_offset = (long)row_offset;
+    if (int rc = run_eigenval(m, k_dev, (long)n_k, out_dev, st, n_peers > 0 ? &plan : nullptr)) return rc;
+    if (n_peers > 0 && n_k > 0) {  // the caller's stream continues only after the last peer store was issued and done
+        CU(cudaEventRecord(m->ev_push, m->s_push));
+        CU(cudaStreamWaitEvent(st, m->ev_push, 0));
+    }
+    return scratch_release(m, st);
 }
 
 int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,

@@ -22,7 +22,8 @@ struct Tuning {
     int tridiag_g = 0;          // TBK_TRIDIAG_G: shared-memory kernel: threads per matrix (1 = tensor-core variant)
     int tridiag_cs = 1;         // TBK_TRIDIAG_CS: column slices
     int tridiag_mpb = 0;        // TBK_TRIDIAG_MPB: matrices per CTA (0 = maximise residency)
-    int tridiag_stages = 67;    // TBK_TRIDIAG_STAGES: staged reduction, size ratio between launches in percent (0 = off)
+    int tridiag_stages = -1;    // TBK_TRIDIAG_STAGES: staged reduction, size ratio between launches in percent (0 = off,
+                                //   -1 = by size: 80 for 88 <= N <= 140, else 67 -- gpurun_out/r02s_sweep.log)
     int tridiag_panel_min = 0;  // TBK_TRIDIAG_PANEL_MIN: blocked kernel from this N on (0 = default 120)
     int tridiag_nopanel = 0;    // TBK_TRIDIAG_NOPANEL
     int tridiag_oldbig = 0;     // TBK_TRIDIAG_OLDBIG
@@ -91,6 +92,9 @@ size_t hk_small_smem_bytes(int n, int dim, int nR, int threads);
 // packed H -> full complex128 [nk][n][n]; convention 1 applies the orbital-position phases.
 cudaError_t launch_expand(const ModelDev& md, const double* k, const double* Hp, long nk, int convention,
                           double* out, cudaStream_t st);
+// Peer push (expand.cu): src[0 .. n_doubles) -> peer_bases[p][dst_offset ..] for every peer (peer-mapped device memory).
+cudaError_t launch_push_rows(const double* src, long n_doubles, double* const* peer_bases, int n_peers, long dst_offset,
+                             cudaStream_t st);
 // Taylor coefficients of Model.construct_kdotp (kdotp_construct.cu): out [nk][n_terms][n][n] c128; powers [n_terms][dim]
 // and fac [n_terms] (the real prefactor of every term) are device arrays.
 cudaError_t launch_kdotp_coeff(const ModelDev& md, const double* k, long nk, const int* powers, const double* fac,

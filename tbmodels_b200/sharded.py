@@ -61,6 +61,34 @@ def broadcast_model(packed, src: int = 0, group=None, device=None) -> PackedMode
     return pack_arrays(R.cpu().numpy(), hop_c, pos.cpu().numpy())
 
 
+class PeerGather:
+    """Result buffer ``[n_rows, n_cols]`` float64 that exists on every GPU of the group and is peer-mapped into every
+    process (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged once at rendezvous).  It is the
+    destination of the FUSED gather: ``Evaluator.eigenval_push_device`` writes a rank's rows into
+    its own copy and, chunk by chunk, into all peers' copies with plain stores over NVLink / NVSwitch while the next chunk
+    computes; :meth:`barrier` (a device-side barrier through the handle's signal pads, enqueued on the current stream)
+    then makes every rank's rows visible everywhere.  No NCCL call on the data path."""
+
+    def __init__(self, n_rows: int, n_cols: int, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world_size = dist.get_world_size(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.buffer = symm_mem.empty((int(n_rows), int(n_cols)), dtype=torch.float64, device=dev)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        if len(ptrs) != self.world_size or int(ptrs[self.rank]) != self.buffer.data_ptr():
+            raise RuntimeError("symmetric-memory rendezvous returned an unexpected pointer table")
+        self.peer_ptrs = [int(p) for r, p in enumerate(ptrs) if r != self.rank]
+
+    def barrier(self) -> None:
+        self.handle.barrier()
+
+
 class ShardedEvaluator:
     """Shards a k-batch over the ranks of a process group.
 
@@ -119,8 +147,28 @@ class ShardedEvaluator:
         lo, hi = self.bounds(k_all.shape[0])
         return lo, hi, self.local.hamilton_device(k_all[lo:hi].contiguous(), convention=convention)
 
+    def eigenval_allgather_fused(self, k_all):
+        """Eigenvalues of the whole batch on every rank with the exchange FUSED behind the eigensolver: every workspace
+        chunk a rank finishes is stored straight into all peers' result buffers over NVLink while the next chunk
+        computes (``tbk_eigenval_push``), then one device-side barrier.  Shards may be uneven (no padding).  Returns the
+        symmetric ``[n_k, N]`` tensor, valid until the next call with the same batch size.  Same bits as
+        :meth:`eigenval_allgather` (a k-point's result does not depend on the rank that computed it)."""
+        n_k = int(k_all.shape[0])
+        key = (n_k, self.size)
+        cache = getattr(self, "_peer_gather", None)
+        if cache is None or cache[0] != key:
+            cache = (key, PeerGather(n_k, self.size, group=self.group, device=k_all.device))
+            self._peer_gather = cache
+        pg = cache[1]
+        lo, hi = self.bounds(n_k)
+        pg.barrier()  # nobody is still reading the buffer of the previous call
+        self.local.eigenval_push_device(k_all[lo:hi].contiguous(), pg.buffer[lo:hi], pg.peer_ptrs, lo)
+        pg.barrier()
+        self._check()
+        return pg.buffer
+
     def eigenval_allgather(self, k_all):
-        """Eigenvalues of the whole batch on every rank: local shards + one all-gather (padded, then trimmed)."""
+        """Eigenvalues of the whole batch on every rank: local shards + one NCCL all-gather (padded, then trimmed)."""
         import torch
         import torch.distributed as dist
 

@@ -37,15 +37,17 @@ def _worker(rank, world, port, n_k, out_dir):
         k_all = torch.rand((n_k, 3), dtype=torch.float64, device=f"cuda:{rank}", generator=g)
         lo, hi, e_loc = sh.eigenval_local(k_all)
         full = sh.eigenval_allgather(k_all)
+        fused = sh.eigenval_allgather_fused(k_all).clone()   # peer stores over NVLink + device-side barrier
+        fused2 = sh.eigenval_allgather_fused(k_all).clone()  # buffer reuse
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), lo=lo, hi=hi, e_loc=e_loc.cpu().numpy(), full=full.cpu().numpy(),
-                 k=k_all.cpu().numpy())
+                 k=k_all.cpu().numpy(), fused=fused.cpu().numpy(), fused2=fused2.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_k", [4096, 5001])
-def test_two_gpu_nccl_sharding(tmp_path, n_k):
+@pytest.mark.parametrize("n_k,ws_mb", [(4096, None), (5001, None), (30001, "1")])
+def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb):
     import torch
     import torch.multiprocessing as mp
 
@@ -54,12 +56,16 @@ def test_two_gpu_nccl_sharding(tmp_path, n_k):
     import tbmodels_b200 as tbk
     from oracle import workloads as wl
 
+    if ws_mb:  # tiny workspace: many chunks per rank, so the peer stores of the fused gather interleave with compute
+        monkeypatch.setenv("TBK_WORKSPACE_MB", ws_mb)
     mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path)), nprocs=2, join=True)
+    monkeypatch.delenv("TBK_WORKSPACE_MB", raising=False)
     d0 = np.load(tmp_path / "r0.npz")
     d1 = np.load(tmp_path / "r1.npz")
     want = tbk.Evaluator(wl.synthetic(12, 10), device=0).eigenval_array(d0["k"])
     assert np.array_equal(d0["k"], d1["k"])
     for d in (d0, d1):
         assert np.array_equal(d["full"], want)  # bit-identical regardless of the shard a k-point landed in
+        assert np.array_equal(d["fused"], want) and np.array_equal(d["fused2"], want)  # fused peer-store gather too
         assert np.array_equal(d["e_loc"], want[int(d["lo"]) : int(d["hi"])])
     assert int(d0["hi"]) == int(d1["lo"]) and int(d1["hi"]) == n_k
