@@ -7,6 +7,8 @@
 // coalesced global loads/stores and a thread-strided (conflict-free) layout; only when even 8 matrices do not
 // fit does each thread work in place on its row of D/E in global memory.
 // N > 128 switches to bisection (bisect_kernel below).  Eigenvalues come out ascending, like LAPACK's.
+#include <algorithm>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -46,6 +48,50 @@ ql_smem_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk, i
     for (long idx = tid; idx < total; idx += T) {
         const int mat = (int)(idx / N), i = (int)(idx - (long)mat * N);
         Do[idx] = ds[i * LDS + mat];
+    }
+}
+
+// Background variant: a FEW persistent CTAs (sized to fit beside the H(k) GEMM's shared-memory ring) pull groups of T
+// matrices from an atomic counter.  tbk_api.cu runs it on a side stream for chunk i while the main stream builds and
+// tridiagonalises chunk i + 1: the QL recurrence is latency bound (one dependent FP64 chain per thread), so it costs the
+// co-resident kernels almost nothing, and its 12 % of the step disappears behind them.  Same per-matrix arithmetic as
+// ql_smem_kernel (bits do not depend on which CTA picks a matrix up).
+template <int T>
+__global__ void __launch_bounds__(T)
+ql_background_kernel(double* __restrict__ D, double* __restrict__ E, int N, long nk, int* __restrict__ fail_count,
+                     unsigned long long* __restrict__ counter) {
+    constexpr int LDS = T + 1;
+    extern __shared__ __align__(16) double sm[];
+    double* ds = sm;
+    double* es = sm + (size_t)N * LDS;
+    __shared__ long s_base;
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_base = (long)atomicAdd(counter, (unsigned long long)T);
+        __syncthreads();
+        const long k0 = s_base;
+        if (k0 >= nk) break;
+        const int nmat = (int)((nk - k0) < T ? (nk - k0) : T);
+        const long total = (long)nmat * N;
+        const double* Dg = D + k0 * N;
+        const double* Eg = E + k0 * N;
+        for (long idx = tid; idx < total; idx += T) {
+            const int mat = (int)(idx / N), i = (int)(idx - (long)mat * N);
+            ds[i * LDS + mat] = Dg[idx];
+            es[i * LDS + mat] = Eg[idx];
+        }
+        __syncthreads();
+        if (tid < nmat) {
+            const int fails = tridiag_ql(N, ds + tid, es + tid, LDS);
+            if (fails && fail_count) atomicAdd(fail_count, fails);
+        }
+        __syncthreads();
+        double* Do = D + k0 * N;
+        for (long idx = tid; idx < total; idx += T) {
+            const int mat = (int)(idx / N), i = (int)(idx - (long)mat * N);
+            Do[idx] = ds[i * LDS + mat];
+        }
+        __syncthreads();  // s_base and the staging buffers are reused by the next group
     }
 }
 
@@ -205,7 +251,51 @@ cudaError_t dispatch(int n, double* D, double* E, long nk, int* fail_count, cuda
     return cudaGetLastError();
 }
 
+template <int T>
+cudaError_t launch_bg_t(int n, double* D, double* E, long nk, int* fail_count, unsigned long long* counter, int ctas,
+                        cudaStream_t st) {
+    const size_t smem = ql_smem_bytes(n, T);
+    cudaError_t err = cudaFuncSetAttribute(ql_background_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (err != cudaSuccess) return err;
+    const long groups = (nk + T - 1) / T;
+    const unsigned grid = (unsigned)std::min<long>(groups, ctas);
+    ql_background_kernel<T><<<grid, T, smem, st>>>(D, E, n, nk, fail_count, counter);
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+// Background QL (see ql_background_kernel): CTAs that together use at most smem_budget bytes of shared memory per SM.
+// Returns cudaErrorNotSupported when the size is served by bisection or no CTA shape fits the budget -- the caller then
+// runs launch_ql in stream order as before.
+cudaError_t launch_ql_background(int n, double* D, double* E, long nk, int* fail_count, unsigned long long* counter,
+                                 size_t smem_budget, cudaStream_t st, const Tuning& tune) {
+    if (nk <= 0 || n <= 0) return cudaSuccess;
+    const int bisect_min = tune.ql_bisect_min > 0 ? tune.ql_bisect_min : kBisectMinN;
+    if (n >= bisect_min || (tune.ql_global_min > 0 && n >= tune.ql_global_min)) return cudaErrorNotSupported;
+    const int full_t = ql_pick_threads(n);
+    if (full_t == 0) return cudaErrorNotSupported;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int cand[4] = {64, 32, 16, 8};
+    for (int t : cand) {
+        if (t > full_t) continue;
+        const size_t per = ql_smem_bytes(n, t) + 1024;
+        const int per_sm = (int)(smem_budget / per);
+        if (per_sm < 1) continue;
+        const int ctas = sms * per_sm;
+        switch (t) {
+            case 64: return launch_bg_t<64>(n, D, E, nk, fail_count, counter, ctas, st);
+            case 32: return launch_bg_t<32>(n, D, E, nk, fail_count, counter, ctas, st);
+            case 16: return launch_bg_t<16>(n, D, E, nk, fail_count, counter, ctas, st);
+            default: return launch_bg_t<8>(n, D, E, nk, fail_count, counter, ctas, st);
+        }
+    }
+    return cudaErrorNotSupported;
+}
 
 long ql_wave_matrices(int n, const Tuning& tune) {
     // matrices one full wave of the shared-memory QL kernel processes (0: not applicable)

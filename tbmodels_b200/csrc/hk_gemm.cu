@@ -271,6 +271,15 @@ cudaError_t launch_na(const ModelDev& md, long nk, const double* Qt, double* Hp,
 
 }  // namespace
 
+size_t hk_gemm_smem_bytes(const ModelDev& md) {
+    switch (md.na) {
+        case 4: return Cfg<4>::smem_bytes();
+        case 8: return Cfg<8>::smem_bytes();
+        case 9: return Cfg<9>::smem_bytes();
+        default: return 0;
+    }
+}
+
 size_t hk_gemm_q_doubles(const ModelDev& md, long nk) {
     return (size_t)((nk + BM - 1) / BM) * (size_t)md.kchunks * A_TILE;
 }

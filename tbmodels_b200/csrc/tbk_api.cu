@@ -126,6 +126,7 @@ Tuning read_tuning() {
     t.ql_bisect_min = env_int("TBK_QL_BISECT_MIN", 0);
     t.gemm_dense = getenv("TBK_GEMM_DENSE") ? 1 : 0;
     t.ql_global_min = env_int("TBK_QL_GLOBAL_MIN", 0);
+    t.ql_overlap = env_int("TBK_QL_OVERLAP", t.ql_overlap);
     return t;
 }
 }  // namespace tbk
@@ -166,6 +167,14 @@ struct tbk_model {
     double* ho[2] = {nullptr, nullptr};
     size_t hk_bytes = 0, ho_bytes = 0;
     int64_t launches = 0;
+    // background QL (chunk i's tridiagonal eigenvalues behind chunk i + 1's build): side stream, second E buffer, events
+    cudaStream_t s_ql = nullptr;
+    cudaEvent_t ev_td[2] = {nullptr, nullptr}, ev_ql[2] = {nullptr, nullptr};
+    double* wsE2 = nullptr;
+    unsigned long long* dCounter = nullptr;
+    bool ql_pending[2] = {false, false};
+    bool ql_bg_ok = false;
+    long eig_chunk_index = 0;
     // peer push of the multi-GPU entry point (tbk_eigenval_push): side stream + events ordering it against the chunks
     cudaStream_t s_push = nullptr;
     cudaEvent_t ev_chunk = nullptr, ev_push = nullptr;
@@ -332,7 +341,8 @@ int ensure_workspace(tbk_model* m, long nk) {
     if (m->wsH) cudaFree(m->wsH);
     if (m->wsE) cudaFree(m->wsE);
     if (m->wsQ) cudaFree(m->wsQ);
-    m->wsH = m->wsE = m->wsQ = nullptr;
+    if (m->wsE2) cudaFree(m->wsE2);
+    m->wsH = m->wsE = m->wsQ = m->wsE2 = nullptr;
     m->chunk = 0;
     m->ws_bytes = 0;
     const size_t hb = (size_t)want * m->md.n * m->md.n * 8;
@@ -344,8 +354,13 @@ int ensure_workspace(tbk_model* m, long nk) {
         qb = std::max<size_t>(hk_gemm_q_doubles(m->md, want) * 8, 16);
         CU(cudaMalloc(&m->wsQ, qb));
     }
+    size_t eb2 = 0;
+    if (!m->md.small_ok && m->md.tune.ql_overlap) {  // second sub-diagonal buffer: QL of chunk i overlaps chunk i + 1
+        eb2 = eb;
+        CU(cudaMalloc(&m->wsE2, eb2));
+    }
     m->chunk = want;
-    m->ws_bytes = hb + eb + qb;
+    m->ws_bytes = hb + eb + qb + eb2;
     return TBK_OK;
 }
 
@@ -365,6 +380,82 @@ int push_chunk(tbk_model* m, const PushPlan& plan, const double* rows, long firs
     return TBK_OK;
 }
 
+// Tridiagonalisation + tridiagonal eigenvalues of one chunk (packed H in wsH -> ascending eigenvalues in D).  With
+// TBK_QL_OVERLAP=1 and more than one chunk in the call, the QL of every chunk but the last runs as a few
+// persistent CTAs on a side stream (launch_ql_background) while the main stream already builds and tridiagonalises the
+// next chunk; two sub-diagonal buffers alternate.  (Opt-in experiment: the step is throughput bound, not latency bound --
+// the background QL slows its co-resident kernels by as much as it saves, see Tuning::ql_overlap.)  eig_begin / eig_drain bracket the chunks of one call.
+int eig_begin(tbk_model* m, long n_chunks) {
+    m->ql_pending[0] = m->ql_pending[1] = false;
+    m->eig_chunk_index = 0;
+    m->ql_bg_ok = m->md.tune.ql_overlap && n_chunks >= 2 && m->wsE2 != nullptr;
+    if (m->ql_bg_ok && !m->s_ql) {
+        CU(cudaStreamCreateWithFlags(&m->s_ql, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaEventCreateWithFlags(&m->ev_td[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&m->ev_ql[b], cudaEventDisableTiming));
+        }
+        CU(cudaMalloc(&m->dCounter, sizeof(unsigned long long)));
+    }
+    return TBK_OK;
+}
+
+int eig_chunk(tbk_model* m, double* D, long cn, bool last, cudaStream_t st, const PushPlan* plan, long first_row) {
+    const ModelDev& md = m->md;
+    const int b = (int)(m->eig_chunk_index++ & 1);
+    double* E = (m->ql_bg_ok && b) ? m->wsE2 : m->wsE;
+    if (m->ql_pending[b]) {  // the QL two chunks back still owns this sub-diagonal buffer
+        CU(cudaStreamWaitEvent(st, m->ev_ql[b], 0));
+        m->ql_pending[b] = false;
+    }
+    LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, E, st, md.tune));
+    if (m->ql_bg_ok && !last) {
+        CU(cudaEventRecord(m->ev_td[b], st));
+        CU(cudaStreamWaitEvent(m->s_ql, m->ev_td[b], 0));
+        const size_t gemm_smem = hk_gemm_smem_bytes(md);
+        const size_t budget = gemm_smem + 4096 < 227 * 1024 ? 227 * 1024 - gemm_smem - 2048 : 0;
+        tbk_model::ProfRec rec{nullptr, nullptr, 4};
+        if (m->prof_on) {
+            CU(cudaEventCreate(&rec.a));
+            CU(cudaEventCreate(&rec.b));
+            CU(cudaEventRecord(rec.a, m->s_ql));
+        }
+        const cudaError_t err = launch_ql_background(md.n, D, E, cn, m->dFail, m->dCounter, budget, m->s_ql, md.tune);
+        if (err == cudaSuccess) {
+            if (m->prof_on) {
+                CU(cudaEventRecord(rec.b, m->s_ql));
+                m->prof.push_back(rec);
+            }
+            m->launches += 1;
+            CU(cudaEventRecord(m->ev_ql[b], m->s_ql));
+            m->ql_pending[b] = true;
+            if (plan)
+                if (int rc = push_chunk(m, *plan, D, first_row, cn, m->s_ql)) return rc;
+            return TBK_OK;
+        }
+        if (m->prof_on) {
+            cudaEventDestroy(rec.a);
+            cudaEventDestroy(rec.b);
+        }
+        if (err != cudaErrorNotSupported) return fail(TBK_E_CUDA, "launch_ql_background -> %s", cudaGetErrorString(err));
+        cudaGetLastError();
+        m->ql_bg_ok = false;  // size served by bisection / no CTA shape fits: in stream order from here on
+    }
+    LAUNCH(4, st, launch_ql(md.n, D, E, cn, m->dFail, st, md.tune));
+    if (plan)
+        if (int rc = push_chunk(m, *plan, D, first_row, cn, st)) return rc;
+    return TBK_OK;
+}
+
+int eig_drain(tbk_model* m, cudaStream_t st) {
+    for (int b = 0; b < 2; ++b)
+        if (m->ql_pending[b]) {
+            CU(cudaStreamWaitEvent(st, m->ev_ql[b], 0));
+            m->ql_pending[b] = false;
+        }
+    return TBK_OK;
+}
+
 int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream_t st, const PushPlan* plan = nullptr) {
     NvtxRange nvtx_call_("tbk:eigenval");
     const ModelDev& md = m->md;
@@ -381,17 +472,15 @@ int run_eigenval(tbk_model* m, const double* k, long nk, double* out, cudaStream
         return TBK_OK;
     }
     if (int rc = ensure_workspace(m, nk)) return rc;
+    if (int rc = eig_begin(m, (nk + m->chunk - 1) / m->chunk)) return rc;
     for (long c0 = 0; c0 < nk; c0 += m->chunk) {
         const long cn = std::min(m->chunk, nk - c0);
         double* D = out + c0 * md.n;
         LAUNCH(5, st, launch_hk_phase(md, k + c0 * md.dim, cn, m->wsQ, st));
         LAUNCH(0, st, launch_hk_gemm(md, cn, m->wsQ, m->wsH, st));
-        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st, md.tune));
-        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st, md.tune));
-        if (plan)
-            if (int rc = push_chunk(m, *plan, D, c0, cn, st)) return rc;
+        if (int rc = eig_chunk(m, D, cn, c0 + cn >= nk, st, plan, c0)) return rc;
     }
-    return TBK_OK;
+    return eig_drain(m, st);
 }
 
 int grow(double** p, size_t* have, size_t want) {
@@ -441,6 +530,7 @@ int run_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, lo
     if (int rc = grow(&m->wsAB, &m->ab_bytes, (size_t)lmax * K2 * NN * 8)) return rc;
     if (int rc = grow(&m->wsQz, &m->qz_bytes, (size_t)nz * K2 * 8)) return rc;
     LAUNCH(5, st, launch_mesh_qz(md, nz, shift ? shift[md.dim - 1] : 0.0, m->wsQz, st));
+    if (int rc = eig_begin(m, (n_lines + lchunk - 1) / lchunk)) return rc;
     for (long l0 = 0; l0 < n_lines; l0 += lchunk) {
         const long ln = std::min(lchunk, n_lines - l0);
         const long cn = ln * nz;
@@ -450,10 +540,9 @@ int run_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, lo
         LAUNCH(0, st, launch_hk_gemm(md, ln * K2, m->wsQ, m->wsAB, st));
         // stage B: expand every line along the last mesh dimension
         LAUNCH(6, st, launch_mesh_lines(md, m->wsAB, m->wsQz, nz, ln, m->wsH, st));
-        LAUNCH(3, st, launch_tridiag(md.n, m->wsH, cn, D, m->wsE, st, md.tune));
-        LAUNCH(4, st, launch_ql(md.n, D, m->wsE, cn, m->dFail, st, md.tune));
+        if (int rc = eig_chunk(m, D, cn, l0 + ln >= n_lines, st, nullptr, 0)) return rc;
     }
-    return TBK_OK;
+    return eig_drain(m, st);
 }
 
 int run_hamilton(tbk_model* m, const double* k, long nk, int convention, double* out, cudaStream_t st) {
@@ -1054,6 +1143,13 @@ int tbk_model_destroy(tbk_model* m) {
         if (m->ev_out[b]) cudaEventDestroy(m->ev_out[b]);
     }
     if (m->ev_busy) cudaEventDestroy(m->ev_busy);
+    for (int b = 0; b < 2; ++b) {
+        if (m->ev_td[b]) cudaEventDestroy(m->ev_td[b]);
+        if (m->ev_ql[b]) cudaEventDestroy(m->ev_ql[b]);
+    }
+    if (m->s_ql) cudaStreamDestroy(m->s_ql);
+    cudaFree(m->wsE2);
+    cudaFree(m->dCounter);
     if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
     if (m->ev_push) cudaEventDestroy(m->ev_push);
     if (m->s_push) cudaStreamDestroy(m->s_push);
@@ -1106,11 +1202,9 @@ int tbk_eigenval_push(tbk_model* m, const double* k_dev, int64_t n_k, double* ou
     DeviceGuard guard(m->device);
     if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (!m->s_push) {
-        CU(cudaStreamCreateWithFlags(&m->s_push, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&m->ev_chunk, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&m->ev_push, cudaEventDisableTiming));
-    }
+    if (!m->s_push) CU(cudaStreamCreateWithFlags(&m->s_push, cudaStreamNonBlocking));
+    if (!m->ev_chunk) CU(cudaEventCreateWithFlags(&m->ev_chunk, cudaEventDisableTiming));
+    if (!m->ev_push) CU(cudaEventCreateWithFlags(&m->ev_push, cudaEventDisableTiming));
     if (int rc = scratch_acquire(m, st)) return rc;
     PushPlan plan;
     plan.bases = reinterpret_cast<double* const*>(peer_bases);

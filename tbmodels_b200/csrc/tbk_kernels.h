@@ -39,6 +39,9 @@ struct Tuning {
     int panel_pfd = 1;          // TBK_PANEL_PFD: L2 prefetch distance in warp trips
     int ql_bisect_min = 0;      // TBK_QL_BISECT_MIN: bisection instead of QL from this N on (0 = default)
     int ql_global_min = 0;      // TBK_QL_GLOBAL_MIN: thread-per-matrix QL in global memory from this N on (0 = never)
+    int ql_overlap = 0;         // TBK_QL_OVERLAP=1: run chunk i's QL in the background of chunk i + 1.  Off by default: measured
+                                //   on B200 the co-resident QL slows the GEMM / tridiagonalisation by what it saves (C3 explicit
+                                //   191.7 vs 189.0 ms per 2^21, k-grid 154.7 vs 128.1 ms; gpurun_out/r02u_*)
     int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)
 };
 Tuning read_tuning();
@@ -84,6 +87,7 @@ struct ModelDev {
 cudaError_t launch_hk_phase(const ModelDev& md, const double* k, long nk, double* Qt, cudaStream_t st);
 cudaError_t launch_hk_gemm(const ModelDev& md, long nk, const double* Qt, double* Hp, cudaStream_t st);
 size_t hk_gemm_q_doubles(const ModelDev& md, long nk);
+size_t hk_gemm_smem_bytes(const ModelDev& md);  // dynamic shared memory of one GEMM CTA (one CTA per SM)
 // Fused thread-per-k-point path for N <= 8: writes packed H (if Hp) and/or ascending eigenvalues (if eig).
 // fail_count (may be null): incremented by the number of eigenvalues whose QL iteration did not converge.
 cudaError_t launch_hk_small(const ModelDev& md, const double* k, long nk, double* Hp, double* eig, int* fail_count,
@@ -137,6 +141,10 @@ cudaError_t launch_eigh(int n, const double* Hp, long nk, double* eig, double* v
                         cudaStream_t st);
 // Batched tridiagonal QL: D (in: diagonal, out: ascending eigenvalues), E sub-diagonal (destroyed). fail_count may be null.
 cudaError_t launch_ql(int n, double* D, double* E, long nk, int* fail_count, cudaStream_t st, const Tuning& tune);
+// Background variant for overlapping chunk i's QL with chunk i + 1's build (eig_ql.cu); cudaErrorNotSupported = not
+// applicable at this size, use launch_ql.
+cudaError_t launch_ql_background(int n, double* D, double* E, long nk, int* fail_count, unsigned long long* counter,
+                                 size_t smem_budget, cudaStream_t st, const Tuning& tune);
 // Matrices per full wave of the QL kernel on the current device (chunks are sized in whole waves); 0 if n/a.
 long ql_wave_matrices(int n, const Tuning& tune);
 

@@ -495,6 +495,44 @@ def test_register_tridiag_staged_tail(tbk, monkeypatch, stop, mid):
     ev.close()
 
 
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_background_ql_overlap_is_bit_invariant(tbk, monkeypatch, overlap):
+    """Chunk i's tridiagonal QL runs as a few persistent CTAs on a side stream behind chunk i + 1's build (tbk_api.cu
+    eig_chunk, eig_ql.cu ql_background_kernel): same bits as the in-order path and as a single-chunk evaluation, for the
+    explicit and the mesh entry points, device and host APIs, many small chunks (tiny workspace) and a ragged last one."""
+    import torch
+
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(36, 12, seed=77)
+    k = np.random.default_rng(7).random((20011, 3))
+    want = tbk.Evaluator(p).eigenval_array(k)  # default workspace: one chunk, no overlap possible (and off by default)
+    assert_eig_close(want[:300], orc.eigenval_array(p.R, p.hop, p.pos, k[:300]), "overlap reference")
+    monkeypatch.setenv("TBK_WORKSPACE_MB", "16")  # ~1500 k-points per chunk -> 14 chunks
+    monkeypatch.setenv("TBK_QL_OVERLAP", overlap)
+    ev = tbk.Evaluator(p)
+    for _ in range(2):  # second call: buffers and events are reused
+        assert np.array_equal(ev.eigenval_array(k), want)
+    got = ev.eigenval_device(torch.from_numpy(k).cuda())
+    ev.check()
+    assert np.array_equal(got.cpu().numpy(), want)
+    dims = (7, 11, 64)
+    mesh_one = tbk.Evaluator(p)  # env captured at create: still 16 MB, chunks of whole lines
+    assert np.array_equal(ev.eigenval_mesh(dims), mesh_one.eigenval_mesh(dims))
+    monkeypatch.delenv("TBK_WORKSPACE_MB")
+    big = tbk.Evaluator(p).eigenval_mesh(dims)
+    assert np.array_equal(ev.eigenval_mesh(dims), big)
+    # N = 128: the background CTAs are the 16-thread shape; N = 200: bisection -> falls back to stream order
+    for n_orb in (128, 200):
+        q = wl.synthetic(n_orb, 3, seed=n_orb)
+        kk = np.random.default_rng(n_orb).random((700, 3))
+        ref = tbk.Evaluator(q).eigenval_array(kk)
+        monkeypatch.setenv("TBK_WORKSPACE_MB", "32")
+        assert np.array_equal(tbk.Evaluator(q).eigenval_array(kk), ref)
+        monkeypatch.delenv("TBK_WORKSPACE_MB")
+
+
 @pytest.mark.parametrize("n_orb", [121, 165, 300, 620])
 def test_unblocked_large_kernels_still_agree(tbk, monkeypatch, n_orb):
     """The shared-memory / row-sweep kernels the blocked one replaced stay reachable (sizes 601..640, tuning hook)."""

@@ -31,6 +31,7 @@ VARIANTS = {
     "stop16": {"TBK_TRIDIAG_REG_STOP": "16"},
     "half16": {"TBK_TRIDIAG_REG_MIN": "2"},
     "nopanel": {"TBK_TRIDIAG_NOPANEL": "1"},
+    "noovl": {"TBK_QL_OVERLAP": "0"},
     "panel200": {"TBK_TRIDIAG_PANEL_MIN": "200"},
     "panel120": {"TBK_TRIDIAG_PANEL_MIN": "120"},
     "g512c4": {"TBK_TRIDIAG_G": "512", "TBK_TRIDIAG_CS": "4"},
