@@ -747,8 +747,17 @@ def run_gpu_arm(args) -> None:
                                 "value": n_e * 2 / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / 2, "steps": 2, "warmup": 3,
                                 "gpu_launches": int(l_e), "kernel_ms_per_step": {c: v[0] / 2 for c, v in prof_e.items() if v[1]},
                                 "output_bytes_per_kpoint": 8 * packed.size + 16 * packed.size**2}
+            # Model.hamilton (the other half of the reference API, row a1): complex128 [n_k, N, N] out, both conventions
+            h_e = v_e  # same shape / dtype: reuse the buffer
+            ham = {}
+            for conv in (2, 1):
+                ms_h, l_h, prof_h = time_device_steps(ev, lambda: ev.hamilton_device(k_e, convention=conv, out=h_e), 2, 3, None, dev)
+                ham[f"convention_{conv}"] = {"value": n_e * 2 / (ms_h * 1e-3), "ms_per_step": ms_h / 2,
+                                             "kernel_ms_per_step": {c: v[0] / 2 for c, v in prof_h.items() if v[1]}}
+            extra["c3_hamilton"] = {"workload": f"c3 model, Model.hamilton of {n_e} k-points per step (device-resident in and out)",
+                                    "unit": "k-points/s (hamilton)", "output_bytes_per_kpoint": 16 * packed.size**2, **ham}
             ev.close()
-            del k_e, w_e, v_e
+            del k_e, w_e, v_e, h_e
             torch.cuda.empty_cache()
         # C5: N_k sweep of the strong-scaling configuration (explicit k-points of 2^m-point meshes)
         p5 = build_model("c5")
