@@ -106,6 +106,102 @@ __device__ __forceinline__ void row_update(double (&ar)[NMAX], double (&ai)[NMAX
     }
 }
 
+// ---- lookahead: the reflector of step p - 1 is generated WHILE the rank-2 update of step p is in flight ----
+// The serial chain of a Householder step (pivot column -> norm reduction over the warp -> 1/sqrt -> reciprocal -> v) is
+// ~1500 cycles of dependent shuffles and FP64 operations during which the warp issues nothing else.  The next pivot
+// column is one column of the matrix: it is brought up to date first (8 FMAs per lane, the same expression the in-place
+// update uses, so the bits agree), and the chain is cut into KSTEPS short stages that are issued between the 4-column
+// blocks of the update -- each stage's latency then hides behind the 32 independent DFMAs of the following block.
+struct Reflector {
+    double xr, xi;          // this lane's entry of the pivot column
+    double alr, ali;        // alpha = entry of lane p - 1
+    double aa, xn, h, hx, y, e;
+    double beta, binv, tr, ti, dr, q, den, sr, si;
+    bool tame;
+};
+constexpr int KSTEPS = 12;
+
+// stage j of the chain for pivot column p (lanes 0 .. p - 1 are active rows); same operation order as householder_gen
+template <int J>
+__device__ __forceinline__ void chain_step(Reflector& r, int p, int lane) {
+    if constexpr (J == 0) {
+        r.alr = __shfl_sync(0xffffffffu, r.xr, p - 1);
+        r.ali = __shfl_sync(0xffffffffu, r.xi, p - 1);
+        r.xn = lane < p - 1 ? fma(r.xr, r.xr, r.xi * r.xi) : 0.0;
+    } else if constexpr (J >= 1 && J <= 5) {
+        r.xn += __shfl_xor_sync(0xffffffffu, r.xn, 32 >> J);
+        if constexpr (J == 5) {
+            r.h = r.alr * r.alr + r.ali * r.ali + r.xn;
+            r.tame = r.h > 1e-280 && r.h < 1e280;
+            r.hx = 0.5 * r.h;
+        }
+    } else if constexpr (J == 6) {
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r.y) : "d"(r.h));
+        r.e = fma(-r.hx * r.y, r.y, 0.5);
+        r.y = fma(r.y, r.e, r.y);
+    } else if constexpr (J == 7) {
+        r.e = fma(-r.hx * r.y, r.y, 0.5);
+        r.y = fma(r.y, r.e, r.y);
+    } else if constexpr (J == 8) {
+        r.e = fma(-r.hx * r.y, r.y, 0.5);
+        r.y = fma(r.y, r.e, r.y);  // = fast_rsqrt(h)
+        const double nrm = r.h * r.y;
+        r.beta = (r.alr >= 0.0) ? -nrm : nrm;
+        r.binv = (r.alr >= 0.0) ? -r.y : r.y;
+        r.tr = (r.beta - r.alr) * r.binv;
+        r.ti = -r.ali * r.binv;
+        r.dr = r.alr - r.beta;
+        r.q = r.dr * r.dr + r.ali * r.ali;
+    } else if constexpr (J == 9) {
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r.den) : "d"(r.q));
+        r.e = fma(-r.q, r.den, 1.0);
+        r.den = fma(r.den, r.e, r.den);
+    } else if constexpr (J == 10) {
+        r.e = fma(-r.q, r.den, 1.0);
+        r.den = fma(r.den, r.e, r.den);
+    } else if constexpr (J == 11) {
+        r.e = fma(-r.q, r.den, 1.0);
+        r.den = fma(r.den, r.e, r.den);  // = fast_rcp(q)
+        r.sr = r.dr * r.den;
+        r.si = -r.ali * r.den;
+        if (!r.tame || (r.xn == 0.0 && r.ali == 0.0))  // warp uniform: huge / tiny norms and the trivial reflector
+            householder_gen(r.alr, r.ali, r.xn, r.beta, r.tr, r.ti, r.sr, r.si);
+    }
+}
+
+template <int J0>
+__device__ __forceinline__ void chain_finish(Reflector& r, int p, int lane, int done) {
+    if constexpr (J0 < KSTEPS) {
+        if (J0 >= done) chain_step<J0>(r, p, lane);
+        chain_finish<J0 + 1>(r, p, lane, done);
+    }
+}
+
+__device__ __forceinline__ void chain_all(Reflector& r, int p, int lane) { chain_finish<0>(r, p, lane, 0); }
+
+// row -= v_c conj(w_b) + w_c conj(v_b) over the columns b < m in blocks of four, one chain stage after every block;
+// returns the number of chain stages issued
+template <int NMAX, int B0>
+__device__ __forceinline__ int row_update_la(double (&ar)[NMAX], double (&ai)[NMAX], const double2* __restrict__ V,
+                                             const double2* __restrict__ W, int m, double vr, double vi, double wr,
+                                             double wi, Reflector& r, int pn, int lane) {
+    if constexpr (B0 < NMAX) {
+        if (B0 >= m) return B0 / 4 < KSTEPS ? B0 / 4 : KSTEPS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (B0 + j < NMAX) {
+                const double2 vb = V[B0 + j], wb = W[B0 + j];
+                ar[B0 + j] = fma(-vr, wb.x, fma(-vi, wb.y, fma(-wr, vb.x, fma(-wi, vb.y, ar[B0 + j]))));
+                ai[B0 + j] = fma(-vi, wb.x, fma(vr, wb.y, fma(-wi, vb.x, fma(wr, vb.y, ai[B0 + j]))));
+            }
+        }
+        if constexpr (B0 / 4 < KSTEPS) chain_step<B0 / 4>(r, pn, lane);
+        return row_update_la<NMAX, B0 + 4>(ar, ai, V, W, m, vr, vi, wr, wi, r, pn, lane);
+    } else {
+        return NMAX / 4 < KSTEPS ? NMAX / 4 : KSTEPS;
+    }
+}
+
 template <int NREG, int OCC>
 constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers are per SM sub-partition: 16 K each)
     return OCC ? OCC : (NREG <= 20 ? 16 : 12);  // 16: <= 128, 12: <= 168, 8: <= 255 registers per thread
@@ -113,7 +209,7 @@ constexpr int reg_min_blocks() {  // resident one-warp CTAs per SM (registers ar
 
 // NREG: columns (and rows) held in registers, a multiple of 4 up to 32.  XMAX: capacity for the rows / columns beyond 32
 // (N <= 32 + XMAX); 0 for N <= 32.
-template <int NREG, int XMAX, int BW, int OCC>
+template <int NREG, int XMAX, int BW, int OCC, bool LA>
 __global__ void __launch_bounds__(32, reg_min_blocks<NREG, OCC>())
 tridiag_reg_kernel(double* __restrict__ Hp, int N, long mstride, long nk, double* __restrict__ D,
                    double* __restrict__ E, int ldo, int off, int n_stop) {
@@ -306,6 +402,66 @@ tridiag_reg_kernel(double* __restrict__ Hp, int N, long mstride, long nk, double
 
     // ---- lean steps: pivot columns min(N-1, 31) .. 1; active rows = lanes 0 .. p-1, active columns = registers 0 .. p-1 ----
     const int p_last = n_stop > 1 ? n_stop : 1;  // staged: stop with an n_stop x n_stop block left (n_stop <= 32)
+    if constexpr (LA) {
+        Reflector r;
+        if (p >= p_last) {  // reflector of the first lean step, the plain way
+            get_col<NREG>(ar, ai, p, r.xr, r.xi);
+            if (lane == p) DS[p] = r.xr;
+            chain_all(r, p, lane);
+        }
+        for (; p >= p_last; --p) {
+            // r = reflector of step p (pivot column p): beta, tau, scale and this lane's pivot entry
+            if (lane == 0) ES[p - 1] = r.beta;
+            const double tr = r.tr, ti = r.ti;
+            const bool has_next = p - 1 >= p_last;
+            if (tr == 0.0 && ti == 0.0) {  // nothing to apply; the next pivot column is already up to date
+                if (has_next) {
+                    get_col<NREG>(ar, ai, p - 1, r.xr, r.xi);
+                    if (lane == p - 1) DS[p - 1] = r.xr;
+                    chain_all(r, p - 1, lane);
+                }
+                continue;
+            }
+            double vr = 0.0, vi = 0.0;
+            if (lane < p - 1) {
+                vr = r.xr * r.sr - r.xi * r.si;
+                vi = r.xr * r.si + r.xi * r.sr;
+            } else if (lane == p - 1) {
+                vr = 1.0;
+            }
+            V[lane] = make_double2(vr, vi);  // zero from p on: the block-granular loops read up to the next multiple of 4
+            __syncwarp();
+            double qr, qi;
+            row_dot<NREG, 4>(ar, ai, V, p, qr, qi);
+            const double pr = tr * qr - ti * qi, pi = tr * qi + ti * qr;
+            double dr = pr * vr + pi * vi;  // lanes >= p: v = 0
+            double di = pr * vi - pi * vr;
+            dr = warp_sum(dr);
+            di = warp_sum(di);
+            const double cr = -0.5 * (tr * dr - ti * di), ci = -0.5 * (tr * di + ti * dr);
+            double wr = 0.0, wi = 0.0;
+            if (lane < p) {
+                wr = pr + cr * vr - ci * vi;
+                wi = pi + cr * vi + ci * vr;
+            }
+            W[lane] = make_double2(wr, wi);
+            __syncwarp();
+            if (has_next) {
+                // next pivot column = column p - 1 of this lane's row after the update (same expression as row_update_la)
+                double cr0, ci0;
+                get_col<NREG>(ar, ai, p - 1, cr0, ci0);
+                const double2 vb = V[p - 1], wb = W[p - 1];
+                r.xr = fma(-vr, wb.x, fma(-vi, wb.y, fma(-wr, vb.x, fma(-wi, vb.y, cr0))));
+                r.xi = fma(-vi, wb.x, fma(vr, wb.y, fma(-wi, vb.x, fma(wr, vb.y, ci0))));
+                if (lane == p - 1) DS[p - 1] = r.xr;
+                const int done = row_update_la<NREG, 0>(ar, ai, V, W, p, vr, vi, wr, wi, r, p - 1, lane);
+                chain_finish<0>(r, p - 1, lane, done);
+            } else {
+                row_update<NREG, 4>(ar, ai, V, W, p, vr, vi, wr, wi);
+            }
+            __syncwarp();
+        }
+    } else {
     for (; p >= p_last; --p) {
         double xr, xi;
         get_col<NREG>(ar, ai, p, xr, xi);
@@ -344,6 +500,7 @@ tridiag_reg_kernel(double* __restrict__ Hp, int N, long mstride, long nk, double
         __syncwarp();
         row_update<NREG, BW>(ar, ai, V, W, p, vr, vi, wr, wi);
         __syncwarp();
+    }
     }
     double* Dk = D + kk * (long)ldo + off;
     double* Ek = E + kk * (long)ldo + off;
@@ -509,27 +666,36 @@ cudaError_t launch_reg_half(int n, const double* Hp, long nk, double* D, double*
     return cudaGetLastError();
 }
 
-template <int NREG, int XMAX, int BW, int OCC>
+template <int NREG, int XMAX, int BW, int OCC, bool LA>
 cudaError_t launch_reg_bw(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
                           int off, int n_stop) {
     constexpr int NV = NREG + XMAX < 32 ? 32 : NREG + XMAX;
     const size_t smem = (size_t)(((n * n + 1) & ~1)) * 8 + (size_t)(3 * NV + XMAX * XMAX + XMAX * 32) * 16;
     cudaError_t err =
-        cudaFuncSetAttribute(tridiag_reg_kernel<NREG, XMAX, BW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(tridiag_reg_kernel<NREG, XMAX, BW, OCC, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     if (nk <= 0) return cudaSuccess;
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
-    tridiag_reg_kernel<NREG, XMAX, BW, OCC><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off, n_stop);
+    tridiag_reg_kernel<NREG, XMAX, BW, OCC, LA><<<(unsigned)nk, 32, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off, n_stop);
     return cudaGetLastError();
 }
 
 template <int NREG, int XMAX>
 cudaError_t launch_reg(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, long mstride, int ldo,
                        int off, int bw, int n_stop) {
-    // bw: tuning hook.  8 = the 255-register build (8 resident warps per SM instead of 12), NREG = 32 only
-    if (bw == 8 && NREG == 32)
-        return launch_reg_bw<NREG, XMAX, 4, (NREG == 32 ? 8 : 0)>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
-    return launch_reg_bw<NREG, XMAX, 4, 0>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    // Default build per size class, measured on B200 (gpurun_out/r02x_sweep.log, ms per 1000 matrices, plain / lookahead
+    // at 168 registers / lookahead at 255 registers): N = 32: 0.027 / 0.033 / 0.032, 36: 0.038 / 0.045 / 0.041,
+    // 40: 0.067 / 0.073 / 0.054, 48: 0.137 / 0.143 / 0.123.  The lookahead needs ~20 more live registers; at the
+    // 168-register budget (12 warps per SM) they spill into the bulk loops and it loses, with 255 registers (8 warps per
+    // SM) it wins where a step is long enough -- the classes with a large shared-memory corner (N > 36).
+    // bw: tuning hooks.  8 = lookahead + 255 registers, 1 = plain loop at the default budget, 2 = lookahead at the
+    // default budget (A/B tests)
+    constexpr int OCC8 = NREG == 32 ? 8 : 0;
+    if (bw == 8) return launch_reg_bw<NREG, XMAX, 4, OCC8, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    if (bw == 1) return launch_reg_bw<NREG, XMAX, 4, 0, false>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    if (bw == 2) return launch_reg_bw<NREG, XMAX, 4, 0, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    if constexpr (XMAX >= 8) return launch_reg_bw<NREG, XMAX, 4, OCC8, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    return launch_reg_bw<NREG, XMAX, 4, 0, false>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
 }
 
 }  // namespace

@@ -28,8 +28,9 @@ struct Tuning {
     int tridiag_nopanel = 0;    // TBK_TRIDIAG_NOPANEL
     int tridiag_oldbig = 0;     // TBK_TRIDIAG_OLDBIG
     int tridiag_reg_min = 21;   // TBK_TRIDIAG_REG_MIN / _MAX: sizes served by the register-resident kernel
-    int tridiag_reg_max = 40;   //   (TBK_TRIDIAG_REG_MAX=0 disables it)
-    int tridiag_reg_bw = 4;     // TBK_TRIDIAG_REG_BW: columns per unrolled block of the register kernel (4 / 8)
+    int tridiag_reg_max = 40;   //   (TBK_TRIDIAG_REG_MAX=0 disables it; 41 .. 48 measured equal through the staged path)
+    int tridiag_reg_bw = 4;     // TBK_TRIDIAG_REG_BW: build of the register kernel: 4 = default per size, 8 = lookahead + 255
+                                //   registers, 1 = plain loop, 2 = lookahead at the default register budget
     int tridiag_reg_stop = 16;  // TBK_TRIDIAG_REG_STOP: staged register reduction, the two-matrices-per-warp kernel takes
                                 //   over at this block size (2 .. 16; 0 = single launch)
     int tridiag_reg_mid = 0;    // TBK_TRIDIAG_REG_MID: optional middle stage of the staged register reduction (a smaller

@@ -18,6 +18,9 @@ VARIANTS = {
     "noreg": {"TBK_TRIDIAG_REG_MAX": "0"},
     "reg48": {"TBK_TRIDIAG_REG_MAX": "48", "TBK_TRIDIAG_REG_MIN": "2"},
     "bw8": {"TBK_TRIDIAG_REG_BW": "8"},
+    "nola": {"TBK_TRIDIAG_REG_BW": "1"},
+    "la168": {"TBK_TRIDIAG_REG_BW": "2"},
+    "reg40": {"TBK_TRIDIAG_REG_MAX": "40"},
     "smem/old": {"TBK_TRIDIAG_REG_MAX": "0", "TBK_TRIDIAG_NOPANEL": "1", "TBK_TRIDIAG_PANEL_MIN": "100000", "TBK_TRIDIAG_STAGES": "0"},
     "panel128": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "128"},
     "panel256": {"TBK_TRIDIAG_PANEL_MIN": "2", "TBK_PANEL_T": "256"},
