@@ -772,6 +772,11 @@ def run_gpu_arm(args) -> None:
         extra["c5_sweep"] = {"workload": "c5: " + WORKLOADS["c5"]["desc"].split(",")[0] + ", N_k = 2^14 .. 2^20 (total, strong scaling)",
                              "unit": UNIT, "points": sweep}
         del p5
+        if world >= 8 and 10**5 % world == 0:  # C4 at its stated size: 1e5 k-points over the 8 GPUs (12 500 each)
+            pk = build_model("c4")
+            r = measure("c4", pk, 10**5, 2, 1, ctx, None, peaks, 2048)
+            extra["c4"] = brief(r, "c4", pk, with_cpu=False)
+            del pk
         if world == 1:
             for name, tot, st, wu in (("c2", 10**8, 20, 5), ("c1", 8000, 50, 5), ("c4", 12500, 2, 1)):
                 pk = build_model(name)

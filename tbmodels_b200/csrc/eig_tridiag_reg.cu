@@ -694,6 +694,8 @@ cudaError_t launch_reg(int n, double* Hp, long nk, double* D, double* E, cudaStr
     if (bw == 8) return launch_reg_bw<NREG, XMAX, 4, OCC8, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
     if (bw == 1) return launch_reg_bw<NREG, XMAX, 4, 0, false>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
     if (bw == 2) return launch_reg_bw<NREG, XMAX, 4, 0, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
+    // (9 or 10 warps per SM are no middle ground: registers are per scheduler, so any count above 8 puts three warps
+    //  on one scheduler and caps the build at 168 registers again)
     if constexpr (XMAX >= 8) return launch_reg_bw<NREG, XMAX, 4, OCC8, true>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
     return launch_reg_bw<NREG, XMAX, 4, 0, false>(n, Hp, nk, D, E, st, mstride, ldo, off, n_stop);
 }

@@ -122,8 +122,11 @@ cudaError_t launch_push_rows(const double* src, long n_doubles, double* const* p
     PeerList pl;
     pl.n = n_peers;
     for (int p = 0; p < n_peers; ++p) pl.base[p] = peer_bases[p];
+    // a SMALL grid on purpose: the copy only has to keep up with one chunk of compute (tens of MB per ~10 ms), and every
+    // CTA it occupies is taken from the phase / GEMM kernels of the next chunk it overlaps (measured at 8 GPUs with a
+    // 1184-CTA grid: the overlapped phase kernel slowed from 2.3 to 7.4 ms per 2^21 k-points)
     long blocks = (n_doubles / 2 + 255) / 256;
-    if (blocks > 148L * 8) blocks = 148L * 8;
+    if (blocks > 32) blocks = 32;
     if (blocks < 1) blocks = 1;
     push_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, n_doubles, pl, dst_offset);
     return cudaGetLastError();
