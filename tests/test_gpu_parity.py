@@ -793,6 +793,20 @@ def test_oversize_matrix_fallback(tbk):
     assert_eig_close(got, orc.eigenval_array(p.R, p.hop, p.pos, k), "N=650")
 
 
+def test_hamilton_above_the_48k_shared_memory_default(tbk):
+    """N = 3100: the convention-1 expansion keeps N phase factors (49.6 KB) in dynamic shared memory, past the 48 KB a
+    kernel gets without opting in (round-1 advisor finding); both conventions against the oracle."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(3100, 1, seed=31)
+    k = np.array([[0.13, -0.41, 0.77]])
+    ev = tbk.Evaluator(p)
+    for conv in (1, 2):
+        assert_h_close(ev.hamilton(k, convention=conv), orc.hamilton(p.R, p.hop, p.pos, k, conv), p, f"N=3100 conv{conv}")
+    ev.close()
+
+
 @pytest.mark.parametrize("verbosity", [[], ["-v"]])
 @pytest.mark.parametrize("kpoints_file_name", ["kpoints.hdf5", "silicon_eigenvals.hdf5"])
 def test_cli_eigenvals(tbk, tmp_path, capsys, kpoints_file_name, verbosity):
