@@ -80,6 +80,12 @@ def build_model(workload: str):
     raise SystemExit(f"unknown workload {workload}")
 
 
+def workload_config(workload: str, packed, total: int) -> dict:
+    """The `config` object of the JSON line: names the workload, identical for the GPU arm and the reference arm."""
+    return {"workload": f"{workload}: {WORKLOADS[workload]['desc']}", "kpoints_total": int(total), "n_orb": packed.size,
+            "n_R_stored": packed.n_R, "dim": packed.dim}
+
+
 def mesh_dims_for(total: int, dims):
     """Mesh whose point count is ``total``: the configured one, or (for an --nk override / the C5 sweep) the
     power-of-two box (2^a, 2^b, 2^c), a <= b <= c as equal as possible.  None = seeded random k-points."""
@@ -273,7 +279,7 @@ def run_reference_arm(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {cfg['desc']}"},
+        "config": workload_config(args.workload, packed, cfg["total"]),
         "cpu_baseline": {
             "value": value,
             "unit": UNIT,
@@ -807,13 +813,10 @@ def run_gpu_arm(args) -> None:
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": f"{args.workload}: {cfg['desc']}",
-                "kpoints_total": main["kpoints_total"],
+            # `config` is identical in both arms (the driver compares them); what is specific to the GPU run is in `run`
+            "config": workload_config(args.workload, packed, main["kpoints_total"]),
+            "run": {
                 "kpoints_per_gpu": main["kpoints_per_gpu"],
-                "n_orb": packed.size,
-                "n_R_stored": packed.n_R,
-                "dim": packed.dim,
                 "path": main["path"],
                 "parallelism": f"contiguous k-shards x{world}" + (f", exchange inside the timed region: {main['gather']}" if world > 1 else ""),
                 "l2": l2_note(main, packed),
