@@ -23,6 +23,7 @@ namespace tbk {
 namespace {
 
 constexpr int TPB = 256;
+constexpr size_t kSmemLimit = 220 * 1024;  // shared memory one CTA of the shared-memory kernels may use
 
 template <int G>
 __device__ __forceinline__ void group_sync(int group) {
@@ -871,8 +872,6 @@ cudaError_t launch_big(int n, double* Hp, long nk, double* D, double* E, cudaStr
     return cudaGetLastError();
 }
 
-constexpr size_t kSmemLimit = 220 * 1024;
-
 template <int G, int CS>
 cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune, long mstride = 0,
                      int ldo = 0, int off = 0, int nsteps = 1 << 30) {
@@ -910,7 +909,10 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
         tridiag_smem_kernel<G, CS><<<(unsigned)blocks, G * best_mpb, smem, st>>>(Hp, n, mstride, nk, D, E, ldo, off, nsteps);
         return cudaGetLastError();
     }
-    // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM)
+    // matrix does not fit in shared memory: in place on the packed scratch (L2 / HBM).  The kernels below reduce a whole
+    // matrix stored at its natural stride; a stage of the staged reduction (trailing block, partial step count) must never
+    // land here -- fail loudly instead of computing on the wrong layout (a tuning-hook combination can ask for it)
+    if (mstride != (long)n * n || ldo != n || off != 0 || nsteps < n - 1) return cudaErrorInvalidConfiguration;
     if (!tune.tridiag_nopanel && tridiag_panel_fits(n)) return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
     if (!tune.tridiag_oldbig) {
         if (n <= 32 * 16) return launch_big<16>(n, Hp, nk, D, E, st);
@@ -927,6 +929,37 @@ cudaError_t launch_g(int n, double* Hp, long nk, double* D, double* E, cudaStrea
 }
 
 }  // namespace
+
+// Thread group (threads per matrix, column slices) of the shared-memory kernel for a matrix / trailing block of size n,
+// and how many such matrices one SM then holds (the arithmetic of launch_g).
+void smem_default_group(int n, int& gg, int& cc) {
+    if (n <= 10) gg = 8;
+    else if (n <= 20) gg = 16;
+    else if (n <= 48) gg = 32;
+    else if (n <= 96) gg = 128;
+    else if (n <= 112) gg = 256;
+    else gg = 512;  // one matrix per SM: 16 warps on it (measured: N = 128 2.66 -> 2.50, 144 4.12 -> 3.87, 160 5.25 -> 5.02 ms
+                    // per 1000 matrices, gpurun_out/r03d_sweep.log)
+    cc = n <= 48 ? 1 : (n <= 96 ? 2 : 4);  // measured on B200: N = 36 best at (32, 1), N = 128 at (512, 4)
+}
+
+int smem_residency(int n) {
+    int G, CS;
+    smem_default_group(n, G, CS);
+    const int NW = G > 32 ? G / 32 : 1;
+    const int CTA = G > TPB ? G : TPB;
+    const size_t per_mat = (size_t)((long)n * (n + 1) / 2 + 3L * n + (CS > 1 ? (long)CS * n : 0) + 2 * NW + 1) * 16;
+    if (per_mat > kSmemLimit) return 0;
+    int best = 0;
+    for (int mpb = 1; mpb <= CTA / G && mpb <= 15; ++mpb) {
+        if (per_mat * mpb > kSmemLimit) break;
+        int ctas = (int)((228 * 1024) / (per_mat * mpb + 1024));
+        const int by_threads = 2048 / (G * mpb);
+        if (ctas > by_threads) ctas = by_threads;
+        if (ctas * mpb > best) best = ctas * mpb;
+    }
+    return best;
+}
 
 constexpr int kPanelMinN = 161;   // blocked kernel from this size on (re-measured in round 2, see below)
 constexpr int kStagedMaxN = 160;  // staged shared-memory reduction while the packed matrix + work vectors fit 227 KB
@@ -964,6 +997,17 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         int next = 0;
         if (staged && cur > 16) {
             next = (cur * ratio + 50) / 100;
+            if (tune.tridiag_stages < 0 && cur > 88) {  // (below: the ratio rule measured 1 - 3 % better)
+                // default plan for the large sizes: the kernel is latency bound and its speed is the number of matrices an
+                // SM holds, so a stage ends exactly where one more matrix fits (at least 8 steps per stage, and never
+                // later than the ratio rule would end it: a stage is also one more pass over the data)
+                const int res = smem_residency(cur);
+                for (int cand = cur - 8; cand >= next && cand > 40; --cand)
+                    if (smem_residency(cand) > res) {
+                        next = cand;
+                        break;
+                    }
+            }
             if (next < 12) next = 12;
             if (next >= cur) next = 0;
             // hand over to the register kernel at its largest size instead of staging past it
@@ -976,12 +1020,11 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
         const int nsteps = next ? cur - next : (1 << 30);
         int gg = g, cc = cs;
         if (gg == 0) {  // defaults, from the size only
-            if (cur <= 10) gg = 8;
-            else if (cur <= 20) gg = 16;
-            else if (cur <= 48) gg = 32;
-            else if (cur <= 96) gg = 128;
-            else gg = 256;
-            cc = cur <= 48 ? 1 : (cur <= 96 ? 2 : 4);  // measured on B200: N = 36 best at (32, 1), N = 128 at (256, 4)
+            smem_default_group(cur, gg, cc);
+            if (cur > 112 && tune.tridiag_g1 > 0) {  // tuning hook: thread group of the one-matrix-per-SM stages
+                gg = tune.tridiag_g1;
+                cc = tune.tridiag_cs1 > 0 ? tune.tridiag_cs1 : 4;
+            }
         }
         cudaError_t err = cudaErrorInvalidValue;
 #define TBK_CASE(G_, CS_) \

@@ -110,6 +110,8 @@ Tuning read_tuning() {
     t.tridiag_g = env_int("TBK_TRIDIAG_G", 0);
     t.tridiag_cs = env_int("TBK_TRIDIAG_CS", 1);
     t.tridiag_mpb = env_int("TBK_TRIDIAG_MPB", 0);
+    t.tridiag_g1 = env_int("TBK_TRIDIAG_G1", 0);
+    t.tridiag_cs1 = env_int("TBK_TRIDIAG_CS1", 0);
     t.tridiag_stages = env_int("TBK_TRIDIAG_STAGES", t.tridiag_stages);
     t.tridiag_panel_min = env_int("TBK_TRIDIAG_PANEL_MIN", 0);
     t.tridiag_nopanel = getenv("TBK_TRIDIAG_NOPANEL") ? 1 : 0;

@@ -21,9 +21,12 @@ struct Tuning {
     int basis_kp = 0;           // TBK_BASIS_KP: k-points per thread of the trigonometric-product kernel (0 = default)
     int tridiag_g = 0;          // TBK_TRIDIAG_G: shared-memory kernel: threads per matrix (1 = tensor-core variant)
     int tridiag_cs = 1;         // TBK_TRIDIAG_CS: column slices
+    int tridiag_g1 = 0;         // TBK_TRIDIAG_G1 / _CS1: threads / column slices of the staged kernel while N > 112 (0 = default)
+    int tridiag_cs1 = 0;
     int tridiag_mpb = 0;        // TBK_TRIDIAG_MPB: matrices per CTA (0 = maximise residency)
     int tridiag_stages = -1;    // TBK_TRIDIAG_STAGES: staged reduction, size ratio between launches in percent (0 = off,
-                                //   -1 = by size: 80 for 88 <= N <= 140, else 67 -- gpurun_out/r02s_sweep.log)
+                                //   -1 = by size: stages end where one more matrix fits an SM for blocks > 88, else ratio 67
+                                //   -- gpurun_out/r02s_sweep.log, r03f_sweep.log)
     int tridiag_panel_min = 0;  // TBK_TRIDIAG_PANEL_MIN: blocked kernel from this N on (0 = default 120)
     int tridiag_nopanel = 0;    // TBK_TRIDIAG_NOPANEL
     int tridiag_oldbig = 0;     // TBK_TRIDIAG_OLDBIG

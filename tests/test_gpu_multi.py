@@ -16,7 +16,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n_k, out_dir):
+def _model(kind):
+    from oracle import workloads as wl
+
+    return wl.haldane() if kind == "haldane" else wl.synthetic(12, 10)
+
+
+def _worker(rank, world, port, n_k, out_dir, kind="syn12"):
     import sys
 
     sys.path.insert(0, ROOT)
@@ -31,10 +37,10 @@ def _worker(rank, world, port, n_k, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        packed = broadcast_model(wl.synthetic(12, 10) if rank == 0 else None, src=0, device=f"cuda:{rank}")
+        packed = broadcast_model(_model(kind) if rank == 0 else None, src=0, device=f"cuda:{rank}")
         sh = ShardedEvaluator(packed, device=rank)
         g = torch.Generator(device=f"cuda:{rank}").manual_seed(7)  # same k-points on every rank
-        k_all = torch.rand((n_k, 3), dtype=torch.float64, device=f"cuda:{rank}", generator=g)
+        k_all = torch.rand((n_k, packed.dim), dtype=torch.float64, device=f"cuda:{rank}", generator=g)
         lo, hi, e_loc = sh.eigenval_local(k_all)
         full = sh.eigenval_allgather(k_all)
         fused = sh.eigenval_allgather_fused(k_all).clone()   # peer stores over NVLink + device-side barrier
@@ -46,8 +52,9 @@ def _worker(rank, world, port, n_k, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_k,ws_mb", [(4096, None), (5001, None), (30001, "1")])
-def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb):
+@pytest.mark.parametrize("n_k,ws_mb,kind", [(4096, None, "syn12"), (5001, None, "syn12"), (30001, "1", "syn12"),
+                                           (2_500_001, None, "haldane")])
+def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb, kind):
     import torch
     import torch.multiprocessing as mp
 
@@ -58,11 +65,11 @@ def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb):
 
     if ws_mb:  # tiny workspace: many chunks per rank, so the peer stores of the fused gather interleave with compute
         monkeypatch.setenv("TBK_WORKSPACE_MB", ws_mb)
-    mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path), kind), nprocs=2, join=True)
     monkeypatch.delenv("TBK_WORKSPACE_MB", raising=False)
     d0 = np.load(tmp_path / "r0.npz")
     d1 = np.load(tmp_path / "r1.npz")
-    want = tbk.Evaluator(wl.synthetic(12, 10), device=0).eigenval_array(d0["k"])
+    want = tbk.Evaluator(_model(kind), device=0).eigenval_array(d0["k"])
     assert np.array_equal(d0["k"], d1["k"])
     for d in (d0, d1):
         assert np.array_equal(d["full"], want)  # bit-identical regardless of the shard a k-point landed in

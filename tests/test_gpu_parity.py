@@ -397,7 +397,8 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
         _check(tbk, p, d[f"{tag}_k"], None, None, d[f"{tag}_eig"], f"{tag} G={g}")
 
 
-@pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 48, 49, 64, 65, 96, 97, 119, 120, 121, 128, 129, 164, 165, 200, 257, 300, 513, 600, 601])
+@pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 36, 37, 40, 41, 48, 49, 64, 65, 96, 97, 112, 113, 119, 120, 121, 128, 129, 144,
+                                   159, 160, 161, 164, 165, 200, 257, 300, 513, 600, 601])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
     """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection)."""
     from oracle import workloads as wl

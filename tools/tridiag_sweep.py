@@ -37,12 +37,18 @@ VARIANTS = {
     "noovl": {"TBK_QL_OVERLAP": "0"},
     "panel200": {"TBK_TRIDIAG_PANEL_MIN": "200"},
     "panel120": {"TBK_TRIDIAG_PANEL_MIN": "120"},
+    "g1_512c4": {"TBK_TRIDIAG_G1": "512", "TBK_TRIDIAG_CS1": "4"},
+    "g1_512c8": {"TBK_TRIDIAG_G1": "512", "TBK_TRIDIAG_CS1": "8"},
+    "g1_256c8": {"TBK_TRIDIAG_G1": "256", "TBK_TRIDIAG_CS1": "8"},
+    "g1_256c2": {"TBK_TRIDIAG_G1": "256", "TBK_TRIDIAG_CS1": "2"},
+    "g1_128c4": {"TBK_TRIDIAG_G1": "128", "TBK_TRIDIAG_CS1": "4"},
     "g512c4": {"TBK_TRIDIAG_G": "512", "TBK_TRIDIAG_CS": "4"},
     "g512c8": {"TBK_TRIDIAG_G": "512", "TBK_TRIDIAG_CS": "8"},
     "g256c8": {"TBK_TRIDIAG_G": "256", "TBK_TRIDIAG_CS": "8"},
     "g256c2": {"TBK_TRIDIAG_G": "256", "TBK_TRIDIAG_CS": "2"},
     "st50": {"TBK_TRIDIAG_STAGES": "50"},
     "st80": {"TBK_TRIDIAG_STAGES": "80"},
+    "st67": {"TBK_TRIDIAG_STAGES": "67"},
     "st75": {"TBK_TRIDIAG_STAGES": "75"},
     "st85": {"TBK_TRIDIAG_STAGES": "85"},
     "st90": {"TBK_TRIDIAG_STAGES": "90"},
