@@ -21,7 +21,9 @@ import os
 import shutil
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_SRC = os.path.join(os.environ.get("TBK_REFERENCE_ROOT", "/root/reference"), "src", "tbmodels")
+REF_ROOT = os.environ.get("TBK_REFERENCE_ROOT", "/root/reference")
+REF_SRC = os.path.join(REF_ROOT, "src", "tbmodels")
+REF_TESTS = os.path.join(REF_ROOT, "tests")  # the reference's own test-suite (+ its samples and regression data)
 DEST = os.path.join(HERE, "_ref")
 
 
@@ -50,9 +52,39 @@ def build(verbose: bool = True) -> str | None:
             assert manifest[rel] == _sha(os.path.join(REF_SRC, rel)), rel
     with open(os.path.join(DEST, "MANIFEST.json"), "w") as f:
         json.dump({"source": REF_SRC, "version": "1.4.4", "sha256": manifest}, f, indent=1, sort_keys=True)
+    n_tests = 0
+    if os.path.isdir(REF_TESTS):  # the reference's own tests, run against the installed GPU methods by tests/test_reference_suite.py
+        tdst = os.path.join(DEST, "tests")
+        if os.path.isdir(tdst):
+            shutil.rmtree(tdst)
+        shutil.copytree(REF_TESTS, tdst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "coverage*.sh"))
+        tman = {}
+        for root, _dirs, files in os.walk(tdst):
+            for name in sorted(files):
+                if name.endswith(".py"):
+                    pth = os.path.join(root, name)
+                    tman[os.path.relpath(pth, tdst)] = _sha(pth)
+        with open(os.path.join(DEST, "MANIFEST_tests.json"), "w") as f:
+            json.dump({"source": REF_TESTS, "sha256": tman}, f, indent=1, sort_keys=True)
+        n_tests = len(tman)
     if verbose:
-        print(f"oracle.build_ref: copied {len(manifest)} files of the unmodified reference to {pkg}")
+        print(f"oracle.build_ref: copied {len(manifest)} files of the unmodified reference to {pkg}"
+              + (f" and its test-suite ({n_tests} python files + data) to {os.path.join(DEST, 'tests')}" if n_tests else ""))
     return DEST
+
+
+def tests_dir() -> str | None:
+    """The reference's own test-suite: the live tree when present, else the verified copy under ``oracle/_ref/tests``."""
+    if os.path.isdir(REF_TESTS):
+        return REF_TESTS
+    tdst = os.path.join(DEST, "tests")
+    mf = os.path.join(DEST, "MANIFEST_tests.json")
+    if not (os.path.isdir(tdst) and os.path.exists(mf)):
+        return None
+    with open(mf) as f:
+        tman = json.load(f)["sha256"]
+    ok = all(os.path.exists(os.path.join(tdst, rel)) and _sha(os.path.join(tdst, rel)) == h for rel, h in tman.items())
+    return tdst if ok else None
 
 
 def verify() -> bool:

@@ -87,11 +87,36 @@ def _install_stubs() -> None:
             def _unavailable(*_a, **_k):
                 raise RuntimeError("fsc.hdf5_io is stubbed: HDF5 I/O is not available in this container")
 
+            def _load(path):
+                """Read-only stand-in for ``fsc.hdf5_io.load`` on the files the reference's test-suite keeps as
+                regression data (type tags builtins.number / list / str and tbmodels.model): parsed with the HDF5
+                reader of this repository (tbmodels_b200/_h5lite.py, no h5py), decoded by type tag.  ``OSError`` for a
+                missing file, like h5py (tests/conftest.py:46-50 relies on it)."""
+                if not os.path.exists(path):
+                    raise OSError(f"Unable to open file {path!r}")
+                from tbmodels_b200 import _h5lite
+
+                def decode(node):
+                    if not isinstance(node, dict) or "type_tag" not in node:
+                        raise ValueError("no type_tag")  # tbmodels.io.load falls back to the legacy decoder on ValueError
+                    tag = str(node["type_tag"])
+                    if tag in ("builtins.number", "builtins.str"):
+                        v = node["value"]
+                        return str(v) if tag == "builtins.str" else v
+                    if tag == "builtins.list":
+                        return [decode(node[str(i)]) for i in range(len(node) - 1)]
+                    if tag == "tbmodels.model":
+                        tb = sys.modules["tbmodels"]
+                        return tb.Model.from_hdf5({k: v for k, v in node.items() if k != "type_tag"})
+                    raise RuntimeError(f"type tag {tag!r} is not supported by the test shim")
+
+                return decode(_h5lite.load(path))
+
             hio.HDF5Enabled = HDF5Enabled
             hio.SimpleHDF5Mapping = SimpleHDF5Mapping
             hio.subscribe_hdf5 = subscribe_hdf5
             hio.save = _unavailable
-            hio.load = _unavailable
+            hio.load = _load
             hio.to_hdf5 = _unavailable
             hio.from_hdf5 = _unavailable
             hio.to_hdf5_file = _unavailable
