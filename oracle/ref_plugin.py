@@ -25,5 +25,12 @@ if os.environ.get("TBK_REF_INSTALL") == "1":
     tbmodels_b200.install()
 
 
+def pytest_terminal_summary(terminalreporter):
+    if os.environ.get("TBK_REF_INSTALL") == "1":
+        from tbmodels_b200 import _patch
+
+        terminalreporter.write_line("tbk-installed-calls: " + " ".join(f"{k}={v}" for k, v in _patch.stats.items()))
+
+
 def pytest_report_header(config):
     return f"reference tbmodels from {ref_shim.reference_src()}, GPU methods installed: {os.environ.get('TBK_REF_INSTALL') == '1'}"

@@ -47,11 +47,16 @@ def _run(install: bool, timeout: int):
     env["TBK_REF_INSTALL"] = "1" if install else "0"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(tests_dir), env=env)
     tail = "\n".join(r.stdout.splitlines()[-40:])
-    summary = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+    lines = [ln for ln in r.stdout.strip().splitlines() if " passed" in ln or " failed" in ln or " error" in ln]
+    summary = lines[-1] if lines else ""
     m = re.search(r"(\d+) passed", summary)
     passed = int(m.group(1)) if m else 0
     assert r.returncode == 0 and " failed" not in summary and " error" not in summary, f"reference suite:\n{tail}\n{r.stderr[-2000:]}"
     assert passed >= MIN_PASSED, f"only {passed} reference tests passed:\n{tail}"
+    if install:  # the installed methods really served the calls (counted in tbmodels_b200/_patch.py, printed by the plugin)
+        m = re.search(r"tbk-installed-calls: hamilton=(\d+) eigenval=(\d+) construct_kdotp=(\d+)", r.stdout)
+        assert m and int(m.group(1)) > 500 and int(m.group(2)) > 100 and int(m.group(3)) > 0, f"GPU methods not exercised:\n{tail}"
+        summary += " | " + m.group(0)
     return passed, summary
 
 
