@@ -608,14 +608,21 @@ def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=Non
     out_host = tbk.pinned_empty((e2e_n, packed.size))
     per_step_s = ms * 1e-3 / steps
     e2e_steps = int(max(1, min(steps, 10, 20.0 / max(per_step_s, 1e-3))))
+    if use_mesh:  # the mesh has no k array: the host API is the pipelined kernels | D2H entry point, whole lines only
+        n_last = dims[-1]
+        e2e_n = max(n_last, e2e_n - e2e_n % n_last)
+        out_host = tbk.pinned_empty((e2e_n, packed.size))
+        host_call = lambda: ev.eigenval_mesh(dims, first_line=lo // n_last, n_lines=e2e_n // n_last, out=out_host)  # noqa: E731
+    else:
+        host_call = lambda: ev.eigenval_array(k_host, out=out_host)  # noqa: E731
     for _ in range(2 if per_step_s < 1.0 else 1):
-        ev.eigenval_array(k_host, out=out_host)
+        host_call()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ev.eigenval_array(k_host, out=out_host)
+        host_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -623,19 +630,20 @@ def measure(workload, packed, total, steps, warmup, ctx, sampler=None, peaks=Non
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     ref_rows = out_dev[:64].cpu().numpy()
-    if use_mesh:  # explicit k-points (e2e arm) vs the mesh entry point: same values to rounding, not the same bits
-        assert np.abs(out_host[:64] - ref_rows).max() <= 1e-10 * float(np.abs(ref_rows).max()), "mesh and explicit paths disagree"
-    else:
-        assert np.array_equal(out_host[:64], ref_rows), "host and device entry points disagree"
+    assert np.array_equal(out_host[:64], ref_rows), "host and device entry points disagree"
+    if use_mesh:  # mesh entry point vs explicit k-points: same values to rounding, not the same bits
+        expl = ev.eigenval_device(k_dev[:64].contiguous()).cpu().numpy()
+        assert np.abs(expl - ref_rows).max() <= 1e-10 * float(np.abs(ref_rows).max()), "mesh and explicit paths disagree"
     e2e = {
         "value": world * e2e_n * e2e_steps / e2e_s,
         "unit": UNIT,
-        "h2d_bytes_per_step": int(e2e_n * packed.dim * 8),
+        "h2d_bytes_per_step": 0 if use_mesh else int(e2e_n * packed.dim * 8),
         "d2h_bytes_per_step": int(e2e_n * packed.size * 8),
         "steps": e2e_steps,
         "kpoints_per_gpu_per_step": e2e_n,
-        "api": "Evaluator.eigenval_array -> tbk_eigenval_host (pinned host buffers, chunked 3-stream pipeline); "
-               "every rank evaluates its shard into its own host buffer",
+        "api": ("Evaluator.eigenval_mesh -> tbk_eigenval_mesh_host (no k array; pinned host result, kernels | D2H pipeline); "
+                if use_mesh else "Evaluator.eigenval_array -> tbk_eigenval_host (pinned host buffers, chunked 3-stream pipeline); ")
+               + "every rank evaluates its shard into its own host buffer",
     }
     ev.profile_read()
     res = {

@@ -104,6 +104,10 @@ int tbk_eigenval_push(tbk_model* m, const double* k_dev, int64_t n_k, double* ou
 int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
                       double* out_dev, void* stream);
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims);
+/* Same with a HOST result buffer (pinned memory from tbk_host_alloc overlaps fully): groups of lines are evaluated into
+ * two device buffers whose D2H copies overlap the next group's kernels; synchronous on return. */
+int tbk_eigenval_mesh_host(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
+                           double* out_host);
 
 /* Eigenvalues AND eigenvectors of the convention-2 H(k) (what scipy.linalg.eigh returns where
  * Model.eigenval calls scipy.linalg.eigvalsh, _tb_model.py:1149): Householder reduction with the unitary accumulated,

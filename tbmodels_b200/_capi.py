@@ -26,6 +26,7 @@ SYMBOLS = (
     "tbk_eigenval",
     "tbk_eigenval_push",
     "tbk_eigenval_mesh",
+    "tbk_eigenval_mesh_host",
     "tbk_mesh_factorised",
     "tbk_eigh",
     "tbk_eigh_host",
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
     lib.tbk_eigenval_push.restype = C.c_int
     lib.tbk_eigenval_mesh.argtypes = [vp, C.POINTER(C.c_int64), dp, C.c_int64, C.c_int64, vp, vp]
     lib.tbk_eigenval_mesh.restype = C.c_int
+    lib.tbk_eigenval_mesh_host.argtypes = [vp, C.POINTER(C.c_int64), dp, C.c_int64, C.c_int64, vp]
+    lib.tbk_eigenval_mesh_host.restype = C.c_int
     lib.tbk_mesh_factorised.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.tbk_mesh_factorised.restype = C.c_int
     lib.tbk_eigh.argtypes = [vp, vp, C.c_int64, vp, vp, vp]

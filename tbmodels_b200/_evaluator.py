@@ -247,11 +247,24 @@ class Evaluator:
         )
         return out
 
-    def eigenval_mesh(self, dims, shift=None) -> np.ndarray:
-        """Host copy of :meth:`eigenval_mesh_device` for the whole mesh: ``[prod(dims), N]``."""
-        res = self.eigenval_mesh_device(dims, shift)
-        self.check()
-        return res.cpu().numpy()
+    def eigenval_mesh(self, dims, shift=None, first_line=0, n_lines=None, out=None) -> np.ndarray:
+        """Eigenvalues on the regular mesh as a HOST array ``[n_lines * dims[-1], N]`` (default: the whole mesh) through
+        ``tbk_eigenval_mesh_host``: groups of lines are evaluated into two device buffers whose D2H copies overlap the
+        next group's kernels -- there is no k array to upload.  ``out`` may be a pinned buffer (:func:`pinned_empty`)."""
+        dims, c_dims, c_shift, total = self._mesh_args(dims, shift)
+        if n_lines is None:
+            n_lines = total - first_line
+        shape = (int(n_lines) * dims[-1], self.size)
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %r" % (shape,))
+        _capi.check(
+            self._lib.tbk_eigenval_mesh_host(
+                self._handle, c_dims, c_shift, int(first_line), int(n_lines), out.ctypes.data_as(C.c_void_p)
+            )
+        )
+        return out
 
     def close(self) -> None:
         self._finalizer()

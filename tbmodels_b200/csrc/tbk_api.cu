@@ -710,6 +710,38 @@ int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int 
     return TBK_OK;
 }
 
+// Regular mesh with a HOST result buffer: lines are evaluated in host-chunk sized groups into two device buffers whose
+// D2H copies overlap the next group's kernels (the pipeline of run_host without the H2D leg: a mesh has no k array).
+int run_mesh_host(tbk_model* m, const int64_t* dims, const double* shift, long line0, long n_lines, double* out_host) {
+    NvtxRange nvtx_call_("tbk:mesh_host_pipeline (kernels | D2H)");
+    const ModelDev& md = m->md;
+    const long nz = (long)dims[md.dim - 1];
+    if (n_lines <= 0 || nz <= 0) return TBK_OK;
+    const size_t line_bytes = (size_t)nz * md.n * 8;
+    long hl = (long)(((size_t)md.tune.host_chunk_mb << 20) / line_bytes);
+    if (hl < 1) hl = 1;
+    const long lchunk = std::max<long>(1, pick_chunk(m) / nz);  // whole workspace chunks per group: no ragged last launch
+    if (hl > lchunk) hl -= hl % lchunk;
+    if (hl > n_lines) hl = n_lines;
+    if (int rc = ensure_pipeline(m, 0, (size_t)hl * line_bytes)) return rc;
+    if (int rc = scratch_acquire(m, m->s_comp)) return rc;
+    int it = 0;
+    for (long l0 = 0; l0 < n_lines; l0 += hl, ++it) {
+        const long ln = std::min(hl, n_lines - l0);
+        const int b = it & 1;
+        if (it >= 2) CU(cudaStreamWaitEvent(m->s_comp, m->ev_out[b], 0));  // D2H of group it-2 drained ho[b]
+        if (int rc = run_eigenval_mesh(m, dims, shift, line0 + l0, ln, m->ho[b], m->s_comp)) return rc;
+        CU(cudaEventRecord(m->ev_comp[b], m->s_comp));
+        CU(cudaStreamWaitEvent(m->s_out, m->ev_comp[b], 0));
+        CU(cudaMemcpyAsync(out_host + (size_t)l0 * nz * md.n, m->ho[b], (size_t)ln * line_bytes, cudaMemcpyDeviceToHost, m->s_out));
+        CU(cudaEventRecord(m->ev_out[b], m->s_out));
+    }
+    if (int rc = scratch_release(m, m->s_comp)) return rc;
+    CU(cudaStreamSynchronize(m->s_comp));
+    CU(cudaStreamSynchronize(m->s_out));
+    return TBK_OK;
+}
+
 int check_fail_flag(tbk_model* m) {
     int h = 0;
     CU(cudaMemcpy(&h, m->dFail, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1238,6 +1270,25 @@ int tbk_eigenval_mesh(tbk_model* m, const int64_t* dims, const double* shift, in
     if (int rc = scratch_acquire(m, (cudaStream_t)stream)) return rc;
     if (int rc = run_eigenval_mesh(m, dims, shift, (long)first_line, (long)n_lines, out_dev, (cudaStream_t)stream)) return rc;
     return scratch_release(m, (cudaStream_t)stream);
+}
+
+int tbk_eigenval_mesh_host(tbk_model* m, const int64_t* dims, const double* shift, int64_t first_line, int64_t n_lines,
+                           double* out_host) {
+    if (!m) return fail(TBK_E_INVALID, "tbk_eigenval_mesh_host: null handle");
+    if (!dims) return fail(TBK_E_INVALID, "tbk_eigenval_mesh_host: dims is null");
+    int64_t lines = 1;
+    for (int d = 0; d < m->md.dim; ++d) {
+        if (dims[d] < 1) return fail(TBK_E_INVALID, "tbk_eigenval_mesh_host: dims[%d] = %lld must be >= 1", d, (long long)dims[d]);
+        if (d < m->md.dim - 1) lines *= dims[d];
+    }
+    if (first_line < 0 || n_lines < 0 || first_line + n_lines > lines)
+        return fail(TBK_E_INVALID, "tbk_eigenval_mesh_host: lines [%lld, %lld) outside the mesh (%lld lines)",
+                    (long long)first_line, (long long)(first_line + n_lines), (long long)lines);
+    if (n_lines > 0 && !out_host) return fail(TBK_E_INVALID, "tbk_eigenval_mesh_host: bad buffers");
+    DeviceGuard guard(m->device);
+    if (!guard.ok) return fail(TBK_E_CUDA, "cudaSetDevice(%d) failed", m->device);
+    if (int rc = run_mesh_host(m, dims, shift, (long)first_line, (long)n_lines, out_host)) return rc;
+    return check_fail_flag(m);
 }
 
 int tbk_mesh_factorised(const tbk_model* m, const int64_t* dims) {

@@ -898,6 +898,34 @@ def test_eigenval_mesh_small_workspace_chunks_lines(tbk, monkeypatch):
         ev2.close()
 
 
+def test_eigenval_mesh_host_pipeline(tbk, monkeypatch):
+    """tbk_eigenval_mesh_host: groups of lines through two device buffers with overlapped D2H -- same bits as the
+    device entry point for many small groups (1 MB host chunk), line ranges, a pinned result buffer, both mesh paths."""
+    import torch
+
+    from oracle import workloads as wl
+
+    p = wl.synthetic(12, 10, seed=88)
+    dims = (9, 10, 48)
+    ev = tbk.Evaluator(p)
+    want = ev.eigenval_mesh_device(dims).cpu().numpy()
+    monkeypatch.setenv("TBK_HOST_CHUNK_MB", "1")
+    ev_small = tbk.Evaluator(p)
+    assert np.array_equal(ev_small.eigenval_mesh(dims), want)
+    out = tbk.pinned_empty((7 * 48, 12))
+    got = ev_small.eigenval_mesh(dims, first_line=5, n_lines=7, out=out)
+    assert got is out and np.array_equal(out, want[5 * 48 : 12 * 48])
+    monkeypatch.setenv("TBK_NO_MESH_FACTOR", "1")  # device-generated k-points through the ordinary path
+    ev_plain = tbk.Evaluator(p)
+    orc = _oracle()
+    k = wl.kgrid_points(dims)
+    assert_eig_close(ev_plain.eigenval_mesh(dims), orc.eigenval_array(p.R, p.hop, p.pos, k), "mesh host, unfactorised")
+    with pytest.raises(ValueError):
+        ev.eigenval_mesh(dims, out=np.empty((3, 12)))
+    for e in (ev, ev_small, ev_plain):
+        e.close()
+
+
 def test_eigenval_mesh_argument_errors(tbk):
     from oracle import workloads as wl
 
