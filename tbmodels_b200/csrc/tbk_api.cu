@@ -679,6 +679,10 @@ int run_host(tbk_model* m, const double* k_host, long nk, double* out_host, int 
     long hchunk = (long)((target_mb << 20) / bytes_per_k);
     if (hchunk < 1) hchunk = 1;
     if (hchunk >= 1024) hchunk &= ~127L;
+    if (!md.small_ok) {  // whole workspace chunks per host chunk: no ragged (partial-wave) last launch in every group
+        const long wchunk = pick_chunk(m);
+        if (hchunk > wchunk) hchunk -= hchunk % wchunk;
+    }
     if (hchunk > nk) hchunk = nk;
     if (int rc = ensure_pipeline(m, (size_t)hchunk * md.dim * 8, (size_t)hchunk * out_per_k * 8)) return rc;
     if (int rc = scratch_acquire(m, m->s_comp)) return rc;
