@@ -977,8 +977,24 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     // 164: 9.9 / 6.7, 256: 30.7 / 19.0, 384: 110 / 56, 512: 275 / 125; round 2, STAGED smem reduction ending in the register
     // kernels / blocked: N = 120: 2.46 / 2.74, 128: 2.84 / 3.11, 136: 3.38 / 4.22, 144: 4.16 / 4.71, 160: 5.30 / 5.81
     // (gpurun_out/r02q_sweep.log) -- so the staged reduction now serves every size that fits.
-    if (g == 0 && n >= panel_from && !tune.tridiag_nopanel && tridiag_panel_fits(n))
-        return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
+    int cur = n, done = 0;
+    if (g == 0 && n >= panel_from && !tune.tridiag_nopanel && tridiag_panel_fits(n)) {
+        // The blocked kernel is built for matrices that stream from L2 / HBM; once the trailing block fits in shared
+        // memory its steps are all latency (one 512-thread CTA per small block).  It therefore stops at the first panel
+        // boundary with at most `limit` rows left and the staged kernels below take over.
+        // Where: as soon as the staged kernels hold at least as many matrices per SM as the blocked kernel does -- two for
+        // N <= 256 (staged blocks <= 112), one above (<= 160).  Measured ms per 1000 matrices without / with the hand-over:
+        // N = 164: 6.13 / 4.78, 200: 9.37 / 7.99, 256: 17.5 / 16.2, 384: 58.2 / 54.5, 512: 131.4 / 127.5 (r03o_sweep.log)
+        int limit = tune.tridiag_panel_stop >= 0 ? tune.tridiag_panel_stop : (n <= 256 ? 112 : 160);
+        if (limit > kStagedMaxN) limit = kStagedMaxN;
+        const int np = tune.tridiag_stages != 0 ? tridiag_panel_handover(n, limit) : 0;
+        if (np < 25) return launch_tridiag_panel(n, Hp, nk, D, E, st, tune);
+        const cudaError_t err = launch_tridiag_panel(n, Hp, nk, D, E, st, tune, limit);
+        if (err != cudaSuccess) return err;
+        cur = np;
+        done = n - np;
+    }
+    const int n0 = cur;  // size the staged plan starts from
     // register-resident warp-per-matrix kernel (eig_tridiag_reg.cu): the whole reduction in one launch
     const auto use_reg = [&](int m) {
         return g == 0 && tune.tridiag_reg_max > 0 && m >= tune.tridiag_reg_min && m <= tune.tridiag_reg_max &&
@@ -989,10 +1005,9 @@ cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cud
     // remaining (smaller) problem is relaunched with several times more matrices resident per SM -- shared memory per
     // matrix ~ N^2 caps residency and the kernel is latency bound.  Stage sizes follow from N only (results never depend
     // on the batch): N -> ratio * N -> ... until <= 16.  TBK_TRIDIAG_STAGES="0" disables, "p" sets the ratio in percent.
-    const int ratio = tune.tridiag_stages >= 0 ? tune.tridiag_stages : ((n >= 88 && n <= 140) ? 80 : 67);
-    const bool staged = g == 0 && n >= 25 && n <= kStagedMaxN && ratio > 0 && ratio < 100;  // (above: not in shared memory)
+    const int ratio = tune.tridiag_stages >= 0 ? tune.tridiag_stages : ((n0 >= 88 && n0 <= 140) ? 80 : 67);
+    const bool staged = g == 0 && n0 >= 25 && n0 <= kStagedMaxN && ratio > 0 && ratio < 100;  // (above: not in shared memory)
     const long ms = (long)n * n;
-    int cur = n, done = 0;
     for (;;) {
         int next = 0;
         if (staged && cur > 16) {

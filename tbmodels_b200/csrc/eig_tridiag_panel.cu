@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -119,7 +121,8 @@ __host__ __device__ inline size_t panel_smem_doubles(int n, int warps, int maxc)
 template <int THREADS, int MAXC, int MINB, int LPR>
 __global__ void __launch_bounds__(THREADS, MINB)
 tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict__ D, double* __restrict__ E,
-                     int pfd /* L2 prefetch distance of the Hermitian product, in warp trips; 0 = off */) {
+                     int pfd /* L2 prefetch distance of the Hermitian product, in warp trips; 0 = off */,
+                     int n_stop /* staged: hand the trailing block over once at most n_stop rows are left; 0 = reduce fully */) {
     constexpr int WARPS = THREADS / 32;
     constexpr int SLOTS = WARPS / 4;
     constexpr int NSW = 1;  // (row-part planes)
@@ -162,7 +165,12 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
 #define TICKW(i)
 #endif
 
+    int k_done = N;  // rows / columns eliminated when the panel loop ends
     for (int k0 = 0; k0 < N; k0 += NB) {
+        if (n_stop > 0 && k0 > 0 && N - k0 <= n_stop) {  // panel boundary: the trailing block is fully up to date
+            k_done = k0;
+            break;
+        }
         const int nb = (N - k0 < NB) ? (N - k0) : NB;
         for (int j = 0; j < nb; ++j) {
             const int c = k0 + j;
@@ -436,6 +444,45 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
                N, tacc[0] * 1e-6, tacc[1] * 1e-6, tacc[2] * 1e-6, tacc[3] * 1e-6, tacc[4] * 1e-6, tacc[5] * 1e-6,
                tacc[6] * 1e-6);
 #endif
+    if (k_done < N) {
+        // ---- staged hand-over (launch_tridiag): d / e of the eliminated rows, and the trailing np x np block compacted
+        // into packed form at the head of this matrix' slot, where the shared-memory / register kernels continue ----
+        const int np = N - k_done;
+        for (int i = tid; i < k_done; i += THREADS) {
+            D[kk * N + i] = ds[i];
+            E[kk * N + i] = es[i];
+        }
+        // In-place compaction, no staging buffer: every target address lies below every source address that is still
+        // unread when (1) the real plane is compacted before the imaginary one (real targets < tri(np) <= tri(N) <= every
+        // imaginary source; imaginary targets may overlap real SOURCES, which are consumed by then) and (2) rows go in
+        // ascending order (target row I ends at tri(I) + I < tri(k + I) + k, the start of its own source row, and source
+        // rows ascend).  WARPS rows per round, read into registers, barrier, write, barrier.
+        constexpr int RMAX = 6;  // ceil(192 / 32): rows of the handed-over block have at most 6 elements per lane
+        const int ntp = (np * (np + 1)) >> 1;
+        for (int plane = 0; plane < 2; ++plane) {
+            const double* src_plane = plane ? Ai : Ar;
+            for (int I0 = 0; I0 < np; I0 += WARPS) {
+                const int I = I0 + w;
+                const int len = I < np ? (plane ? I : I + 1) : 0;  // row I: I + 1 real, I imaginary entries
+                const long srow = plane ? trs(k_done + I) + k_done : tri(k_done + I) + k_done;
+                double buf[RMAX];
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q) {
+                    const int J = lane + 32 * q;
+                    buf[q] = J < len ? src_plane[srow + J] : 0.0;
+                }
+                __syncthreads();
+                const int drow = plane ? ntp + ((I * (I - 1)) >> 1) : (I * (I + 1)) >> 1;
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q) {
+                    const int J = lane + 32 * q;
+                    if (J < len) Ar[drow + J] = buf[q];
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
     for (int i = tid; i < N; i += THREADS) {
         D[kk * N + i] = ds[i];
         E[kk * N + i] = (i < N - 1) ? es[i] : 0.0;
@@ -443,8 +490,9 @@ tridiag_panel_kernel(double* __restrict__ Hp, int N, long nk, double* __restrict
 }
 
 template <int THREADS, int MAXC, int MINB, int LPR>
-cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
+cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune, int n_stop) {
     const size_t smem = panel_smem_doubles(n, THREADS / 32, MAXC) * 8;
+    if (n_stop > 192) return cudaErrorInvalidValue;  // the hand-over copies rows of at most 192 entries
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(tridiag_panel_kernel<THREADS, MAXC, MINB, LPR>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -453,7 +501,7 @@ cudaError_t launch_panel_t(int n, double* Hp, long nk, double* D, double* E, cud
     if (nk > 2147483647L) return cudaErrorInvalidConfiguration;
     int pfd = tune.panel_pfd;  // measured (C4, ms per 1184 matrices): off 167, 1 trip 154, 2 trips 156, 4 trips 167, 8 trips 175
     if (pfd < 0 || pfd > 8) pfd = 1;
-    tridiag_panel_kernel<THREADS, MAXC, MINB, LPR><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd);
+    tridiag_panel_kernel<THREADS, MAXC, MINB, LPR><<<(unsigned)nk, THREADS, smem, st>>>(Hp, n, nk, D, E, pfd, n_stop);
     return cudaGetLastError();
 }
 
@@ -464,7 +512,15 @@ bool tridiag_panel_fits(int n) {  // (the 16-warp configuration has the largest 
     return n >= 2 && n <= 640 && panel_smem_doubles(n, 16, n <= 512 ? 16 : 20) * 8 <= 227 * 1024;
 }
 
-cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
+// Rows left when the blocked kernel hands over with the limit n_stop: the first panel boundary with at most n_stop rows.
+int tridiag_panel_handover(int n, int n_stop) {
+    if (n_stop <= 0 || n <= n_stop) return 0;
+    const int panels = (n - n_stop + NB - 1) / NB;
+    return n - panels * NB;
+}
+
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune,
+                                 int n_stop) {
     const int t = tune.panel_t, lpr = tune.panel_lpr;  // tuning hooks: threads per matrix, lanes per row of the product
     // template arguments: threads, column chunks (n <= chunks * lanes per row), min CTAs per SM, lanes per row.
     // Measured on B200, tridiagonalisation ms per 1000 matrices:
@@ -472,22 +528,22 @@ cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* 
     //   N = 200: 16 lanes/row 9.39, 32 lanes/row 10.47 (512 thr: 12.6);  N = 256: 17.6 / 19.2 (512 thr: 20.8)
     if (n <= 128) {
         if (lpr == 32) {
-            if (t == 128) return launch_panel_t<128, 4, 8, 32>(n, Hp, nk, D, E, st, tune);
-            if (t == 512) return launch_panel_t<512, 4, 2, 32>(n, Hp, nk, D, E, st, tune);
-            return launch_panel_t<256, 4, 4, 32>(n, Hp, nk, D, E, st, tune);
+            if (t == 128) return launch_panel_t<128, 4, 8, 32>(n, Hp, nk, D, E, st, tune, n_stop);
+            if (t == 512) return launch_panel_t<512, 4, 2, 32>(n, Hp, nk, D, E, st, tune, n_stop);
+            return launch_panel_t<256, 4, 4, 32>(n, Hp, nk, D, E, st, tune, n_stop);
         }
-        if (t == 128) return launch_panel_t<128, 8, 8, 16>(n, Hp, nk, D, E, st, tune);
-        return launch_panel_t<256, 8, 4, 16>(n, Hp, nk, D, E, st, tune);
+        if (t == 128) return launch_panel_t<128, 8, 8, 16>(n, Hp, nk, D, E, st, tune, n_stop);
+        return launch_panel_t<256, 8, 4, 16>(n, Hp, nk, D, E, st, tune, n_stop);
     }
     if (n <= 256) {
         if (lpr == 32) {
-            if (t == 512) return launch_panel_t<512, 8, 1, 32>(n, Hp, nk, D, E, st, tune);
-            return launch_panel_t<256, 8, 2, 32>(n, Hp, nk, D, E, st, tune);
+            if (t == 512) return launch_panel_t<512, 8, 1, 32>(n, Hp, nk, D, E, st, tune, n_stop);
+            return launch_panel_t<256, 8, 2, 32>(n, Hp, nk, D, E, st, tune, n_stop);
         }
-        return launch_panel_t<256, 16, 2, 16>(n, Hp, nk, D, E, st, tune);
+        return launch_panel_t<256, 16, 2, 16>(n, Hp, nk, D, E, st, tune, n_stop);
     }
-    if (n <= 512) return launch_panel_t<512, 16, 1, 32>(n, Hp, nk, D, E, st, tune);
-    return launch_panel_t<512, 20, 1, 32>(n, Hp, nk, D, E, st, tune);
+    if (n <= 512) return launch_panel_t<512, 16, 1, 32>(n, Hp, nk, D, E, st, tune, n_stop);
+    return launch_panel_t<512, 20, 1, 32>(n, Hp, nk, D, E, st, tune, n_stop);
 }
 
 }  // namespace tbk

@@ -115,6 +115,7 @@ Tuning read_tuning() {
     t.tridiag_stages = env_int("TBK_TRIDIAG_STAGES", t.tridiag_stages);
     t.tridiag_panel_min = env_int("TBK_TRIDIAG_PANEL_MIN", 0);
     t.tridiag_nopanel = getenv("TBK_TRIDIAG_NOPANEL") ? 1 : 0;
+    t.tridiag_panel_stop = env_int("TBK_TRIDIAG_PANEL_STOP", t.tridiag_panel_stop);
     t.tridiag_oldbig = getenv("TBK_TRIDIAG_OLDBIG") ? 1 : 0;
     t.tridiag_reg_min = env_int("TBK_TRIDIAG_REG_MIN", t.tridiag_reg_min);
     t.tridiag_reg_max = env_int("TBK_TRIDIAG_REG_MAX", t.tridiag_reg_max);

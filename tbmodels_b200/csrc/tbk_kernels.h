@@ -28,6 +28,9 @@ struct Tuning {
                                 //   -1 = by size: stages end where one more matrix fits an SM for blocks > 88, else ratio 67
                                 //   -- gpurun_out/r02s_sweep.log, r03f_sweep.log)
     int tridiag_panel_min = 0;  // TBK_TRIDIAG_PANEL_MIN: blocked kernel from this N on (0 = default 120)
+    int tridiag_panel_stop = -1;   // TBK_TRIDIAG_PANEL_STOP: the blocked kernel hands its trailing block to the staged
+                                   //   shared-memory / register kernels once at most this many rows are left (0 = never,
+                                   //   -1 = by size: 112 for N <= 256, 160 above)
     int tridiag_nopanel = 0;    // TBK_TRIDIAG_NOPANEL
     int tridiag_oldbig = 0;     // TBK_TRIDIAG_OLDBIG
     int tridiag_reg_min = 21;   // TBK_TRIDIAG_REG_MIN / _MAX: sizes served by the register-resident kernel
@@ -125,7 +128,11 @@ cudaError_t launch_tridiag_reg(int n, double* Hp, long nk, double* D, double* E,
                                int ldo, int off, int bw, int stop, int mid);
 // Blocked (panel + tensor-core her2k) variant for matrices that live in L2 / HBM (eig_tridiag_panel.cu).
 bool tridiag_panel_fits(int n);
-cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
+// n_stop > 0: staged -- stop at the first panel boundary with at most n_stop rows left (tridiag_panel_handover(n, n_stop)
+// of them), write d / e of the eliminated rows and leave the trailing block packed at the head of each matrix' slot.
+cudaError_t launch_tridiag_panel(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune,
+                                 int n_stop = 0);
+int tridiag_panel_handover(int n, int n_stop);
 // Supercell packing on the device (supercell_pack.cu).  One SupEntry per base hopping matrix that lands in a block of a
 // folded supercell matrix: base matrix index, Hermitian-transposed or not, scale (1/2 for the R' = 0 symmetrisation).
 // table[(q * vol + a) * vol + b] = (first entry, count) of block (a, b) of new lattice vector q.

@@ -34,6 +34,12 @@ VARIANTS = {
     "stop16": {"TBK_TRIDIAG_REG_STOP": "16"},
     "half16": {"TBK_TRIDIAG_REG_MIN": "2"},
     "nopanel": {"TBK_TRIDIAG_NOPANEL": "1"},
+    "pstop0": {"TBK_TRIDIAG_PANEL_STOP": "0"},
+    "pstop128": {"TBK_TRIDIAG_PANEL_STOP": "128"},
+    "pstop112": {"TBK_TRIDIAG_PANEL_STOP": "112"},
+    "pstop144": {"TBK_TRIDIAG_PANEL_STOP": "144"},
+    "pstop80": {"TBK_TRIDIAG_PANEL_STOP": "80"},
+    "pstop96": {"TBK_TRIDIAG_PANEL_STOP": "96"},
     "noovl": {"TBK_QL_OVERLAP": "0"},
     "panel200": {"TBK_TRIDIAG_PANEL_MIN": "200"},
     "panel120": {"TBK_TRIDIAG_PANEL_MIN": "120"},
