@@ -35,4 +35,26 @@ for name, p, nk in cases:
     h = ev.hamilton(k[: min(nk, 20)], convention=1)
     print(name, ev.path, float(e.sum()), float(np.abs(h).sum()), flush=True)
     ev.close()
+# ---- round 2: eigenvectors, construct_kdotp, device-packed supercell, blocked -> staged hand-over, mesh host pipeline ----
+os.environ.pop("TBK_TRIDIAG_PANEL_MIN", None)
+for n_orb, nk in ((5, 9), (36, 7), (64, 3), (90, 2)):
+    p = wl.synthetic(n_orb, 4, seed=n_orb)
+    ev = tbk.Evaluator(p, device=0)
+    w, v = ev.eigh(rng.random((nk, 3)))
+    print("eigh", n_orb, float(w.sum()), float(np.abs(v).sum()), flush=True)
+    ev.close()
+p = wl.synthetic(12, 10, seed=3)
+ev = tbk.Evaluator(p, device=0)
+tc = ev.construct_kdotp((0.1, 0.2, 0.3), 2)
+print("kdotp", len(tc), float(sum(np.abs(m).sum() for m in tc.values())), flush=True)
+print("mesh host", float(ev.eigenval_mesh((3, 4, 16)).sum()), flush=True)
+ev.close()
+sup = tbk.KModel.from_packed(wl.synthetic(5, 6, seed=4)).supercell((2, 1, 2))
+print("supercell", sup.size, float(np.array(sup.eigenval(rng.random((6, 3)))).sum()), flush=True)
+sup.evaluator().close()
+for n_orb in (128, 170, 264):
+    p = wl.synthetic(n_orb, 2, seed=n_orb)
+    ev = tbk.Evaluator(p, device=0)
+    print("hand-over", n_orb, float(ev.eigenval_array(rng.random((3, 3))).sum()), flush=True)
+    ev.close()
 print("sanitize smoke done")
