@@ -235,3 +235,53 @@ def test_sincospi_lean_accuracy_in_ulps():
     assert worst <= 1.5, worst
     assert sc(0.5) == (1.0, 0.0) and sc(1.0)[1] == -1.0 and sc(-0.5)[0] == -1.0 and sc(0.0) == (0.0, 1.0)
     assert sc(2.0 ** 40 + 0.5) == (1.0, 0.0) and abs(sc(0.25)[0] - np.sqrt(0.5)) < 2e-16
+
+
+def test_kdotp_power_tuples_follow_the_reference_order():
+    """Evaluator.construct_kdotp returns its coefficients under the power tuples of the reference's dict
+    (src/tbmodels/_tb_model.py:963-966: itertools.product(range(order + 1), repeat=dim) filtered by sum <= order)."""
+    from tbmodels_b200._evaluator import kdotp_powers
+
+    d = load_golden("construct_kdotp.npz")
+    for name in d["names"]:
+        order = int(d[f"{name}_order"])
+        dim = d[f"{name}_k"].shape[1]
+        assert np.array_equal(kdotp_powers(dim, order), d[f"{name}_powers"]), name
+    assert kdotp_powers(3, 0).tolist() == [[0, 0, 0]]
+    assert kdotp_powers(1, 3).ravel().tolist() == [0, 1, 2, 3]
+
+
+def test_supercell_duck_type_host_side():
+    """SupercellKModel: sizes, positions (reference :1670-1678) and argument errors (:1656-1662) without touching a GPU;
+    pickling drops the device handle."""
+    import pickle
+
+    import tbmodels_b200 as tbk
+    from oracle import workloads as wl
+
+    base = wl.synthetic(3, 4, seed=5)
+    sup = tbk.SupercellKModel(base, (2, 1, 3))
+    big = wl.supercell(base, (2, 1, 3))
+    assert sup.size == big.size == 18 and sup.dim == 3
+    assert np.array_equal(sup.pos, big.pos)
+    clone = pickle.loads(pickle.dumps(sup))
+    assert clone.size == 18 and clone._ev is None and np.array_equal(clone.pos, sup.pos)
+    with pytest.raises(ValueError):
+        tbk.SupercellKModel(base, (2, 2))
+    with pytest.raises(ValueError):
+        tbk.SupercellKModel(base, (2, 0, 1))
+    with pytest.raises(ValueError):
+        sup.hamilton((0, 0, 0), convention=3)  # before any device work
+
+
+def test_new_entry_points_fail_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import tbmodels_b200 as tbk
+    from oracle import workloads as wl
+
+    with pytest.raises(tbk.TbkError) as exc:
+        tbk.Evaluator.from_supercell(wl.synthetic(3, 4, seed=5), (2, 1, 1))
+    assert "no CPU fallback" in str(exc.value)
