@@ -4,8 +4,9 @@ This module is part of the parity oracle: only ``tests/``, ``oracle/make_golden.
 ``cpu_baseline`` leg of ``bench.py`` may use anything under ``oracle/``.  The product package
 ``tbmodels_b200`` never imports it.
 
-``/root/reference`` exists only in the build container; on the GPU box the shim falls back to the byte-identical copy
-of the package that ``oracle/build_ref.py`` places under ``oracle/_ref/`` (git-ignored, shipped like ``libtbk.so``).
+``/root/reference`` exists only in the build container; on the GPU box the shim falls back to the byte-identical, sha256
+verified archive of the package that ``oracle/build_ref.py`` places under ``oracle/_ref/`` (git-ignored, shipped like
+``libtbk.so``; imported straight from the zip).
 
 The reference (v1.4.4) does not import on this image as-is; the hot path itself needs only numpy and
 scipy.  The shims:
@@ -33,12 +34,9 @@ def reference_src() -> str | None:
     """Directory to put on ``sys.path``: the reference tree itself, else the verified copy under ``oracle/_ref``."""
     if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "tbmodels")):
         return os.path.join(REFERENCE_ROOT, "src")
-    if os.path.isdir(os.path.join(_REF_COPY, "tbmodels")):
-        from . import build_ref
+    from . import build_ref
 
-        if build_ref.verify():
-            return _REF_COPY
-    return None
+    return build_ref.package_path()
 
 
 def reference_available() -> bool:
@@ -132,7 +130,7 @@ def import_reference():
         return sys.modules["tbmodels"]
     src = reference_src()
     if src is None:
-        raise ImportError(f"reference package found neither at {REFERENCE_ROOT} nor (verified) under {_REF_COPY}")
+        raise ImportError(f"reference package found neither at {REFERENCE_ROOT} nor (verified archive) under {_REF_COPY}")
     _install_stubs()
     if src not in sys.path:
         sys.path.insert(0, src)

@@ -1,7 +1,8 @@
 """The reference's OWN test-suite, unmodified, run against the GPU methods.
 
-``oracle/build_ref.py`` keeps a verified copy of ``/root/reference/tests`` (python files, samples, regression data) under
-``oracle/_ref/tests`` (git-ignored, shipped to the GPU box like ``libtbk.so``); ``oracle/ref_plugin.py`` makes the
+``oracle/build_ref.py`` keeps a verified archive of ``/root/reference/tests`` (python files, samples, regression data) as
+``oracle/_ref/tests_ref.zip`` (git-ignored, shipped to the GPU box like ``libtbk.so``, unpacked into a temporary directory
+for the run); ``oracle/ref_plugin.py`` makes the
 reference package importable for it (h5py / fsc.hdf5_io stand-ins; the regression data are read with this repository's
 HDF5 reader) and, for the GPU run, calls ``tbmodels_b200.install()`` first.  Every assertion of the reference's tests about
 ``Model.hamilton`` / ``Model.eigenval`` / ``Model.construct_kdotp`` / ``KdotpModel`` -- 96 + 48 + 144 regression goldens,
@@ -35,7 +36,7 @@ def _run(install: bool, timeout: int):
 
     tests_dir = build_ref.tests_dir()
     if tests_dir is None:
-        pytest.skip("the reference's test-suite is neither at /root/reference/tests nor under oracle/_ref/tests "
+        pytest.skip("the reference's test-suite is neither at /root/reference/tests nor archived under oracle/_ref "
                     "(run __graft_entry__.build() in the build container)")
     cmd = [sys.executable, "-m", "pytest", tests_dir, "-p", "oracle.ref_plugin", "-q", "--no-header", "-p", "no:cacheprovider",
            "-W", "error", "-W", "ignore::DeprecationWarning", "-W", "ignore::ImportWarning", "--rootdir", tests_dir, "-c", os.devnull,
