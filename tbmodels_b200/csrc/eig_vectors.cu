@@ -13,10 +13,12 @@
 // Layout: the matrix and Q^T are stored full (both triangles) with thread c owning COLUMN c: every inner loop reads
 // element (j, c) for running j, which is bank-conflict free in shared memory and coalesced in global memory.  The
 // Hermitian product uses A[c][j] = conj(A[j][c]), the rank-2 update touches both triangles.
-// N <= 82 keeps both arrays in shared memory (32 N^2 bytes); larger matrices run the same code on global scratch
-// (L2 / HBM resident, not tuned: the eigenvalue-only path is the benchmarked one).
+// The same code runs with both arrays in shared memory (N <= 12) or on global scratch (L2 resident; faster above because
+// shared memory would cap residency, see eigh_in_smem).  Not tuned further: the eigenvalue-only path is the benchmarked one.
 // Eigenvectors are defined up to a phase (and up to a rotation inside degenerate subspaces); the parity tests check
 // residual, orthonormality and the eigenvalues -- not the phase.
+#include <cstdlib>
+
 #include "tbk_kernels.h"
 #include "tbk_math.cuh"
 
@@ -307,7 +309,19 @@ cudaError_t launch_eigh_t(int n, const double* Hp, long nk, double* eig, double*
 
 }  // namespace
 
-bool eigh_in_smem(int n) { return eigh_fixed_smem(n, 128) + (size_t)2 * n * n * 16 <= 220 * 1024; }
+// Where the matrix and the accumulated unitary live.  Shared memory (32 N^2 bytes per matrix) caps the CTAs an SM
+// holds, and this kernel is latency bound (barriers, one thread's serial QL chain): measured on B200, ms per 1000
+// matrices in shared memory / on L2-resident global scratch (as many CTAs resident as threads allow) -- N = 12: 0.035 /
+// 0.035, 16: 0.063 / 0.058, 24: 0.197 / 0.139, 36: 0.864 / 0.584, 48: 3.23 / 1.25, 64: 10.9 / 3.34, 82: 17.8 / 9.07
+// (gpurun_out/r03y_eigh.log, r03z_eigh.log).  So only the smallest matrices stay in shared memory.
+// TBK_EIGH_SMEM_MAX overrides (tests, A/B runs).
+bool eigh_in_smem(int n) {
+    static const int limit = [] {
+        const char* e = getenv("TBK_EIGH_SMEM_MAX");
+        return e ? atoi(e) : 12;
+    }();
+    return n <= limit && eigh_fixed_smem(n, 128) + (size_t)2 * n * n * 16 <= 220 * 1024;
+}
 
 // Hp: packed Hermitian [nk][n*n] (not modified).  eig [nk][n] ascending, vec [nk][n][n] c128 (column j <-> eig[j]).
 // scratch: 2 * nk * n * n double2 of global memory when !eigh_in_smem(n), else unused (may be null).

@@ -10,6 +10,7 @@ import pytest
 from conftest import assert_eig_close, assert_h_close, h_scale, load_golden, packed_from
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 T_COUNT = 6
 
@@ -609,6 +610,39 @@ def test_eigh_eigenvectors(tbk, shape):
     ev.check()
     assert np.array_equal(wd.cpu().numpy(), w) and np.array_equal(vd.cpu().numpy(), v)
     ev.close()
+
+
+_EIGH_VARIANT_SIZES = (5, 12, 13, 36, 64, 82)
+
+
+def _eigh_variant_case(n_orb):
+    from oracle import workloads as wl
+
+    return wl.synthetic(n_orb, 3, seed=700 + n_orb), np.random.default_rng(n_orb).random((6, 3))
+
+
+@pytest.mark.parametrize("smem_max", ["82", "0"])
+def test_eigh_storage_variants_agree(tbk, tmp_path, smem_max):
+    """The eigenvector kernel with its matrices in shared memory (TBK_EIGH_SMEM_MAX=82, the first version) and on global
+    scratch for every size (=0): same code, bit-identical to the default placement.  The limit is read once per process,
+    so the variant runs in a fresh interpreter."""
+    import subprocess
+    import sys
+
+    out = str(tmp_path / "variant.npz")
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import tbmodels_b200 as tbk; from test_gpu_parity import _eigh_variant_case, _EIGH_VARIANT_SIZES\n"
+            "res = {}\n"
+            "for n in _EIGH_VARIANT_SIZES:\n"
+            "    p, k = _eigh_variant_case(n); w, v = tbk.Evaluator(p).eigh(k); res['w%%d' %% n] = w; res['v%%d' %% n] = v\n"
+            "np.savez(sys.argv[1], **res)\n" % (ROOT_DIR, os.path.join(ROOT_DIR, "tests")))
+    env = dict(os.environ, TBK_EIGH_SMEM_MAX=smem_max)
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=600)
+    with np.load(out) as got:
+        for n_orb in _EIGH_VARIANT_SIZES:
+            p, k = _eigh_variant_case(n_orb)
+            w0, v0 = tbk.Evaluator(p).eigh(k)
+            assert np.array_equal(got["w%d" % n_orb], w0) and np.array_equal(got["v%d" % n_orb], v0), f"N={n_orb}"
 
 
 def test_eigh_degenerate_and_kdotp(tbk):
