@@ -128,6 +128,10 @@ Tuning read_tuning() {
     t.panel_pfd = env_int("TBK_PANEL_PFD", 1);
     t.ql_bisect_min = env_int("TBK_QL_BISECT_MIN", 0);
     t.gemm_dense = getenv("TBK_GEMM_DENSE") ? 1 : 0;
+    t.tridiag_twostage = env_int("TBK_TRIDIAG_TWOSTAGE", t.tridiag_twostage);
+    t.band_t = env_int("TBK_BAND_T", t.band_t);
+    t.band_stage2 = env_int("TBK_BAND_STAGE2", t.band_stage2);
+    t.band_group_mb = env_int("TBK_BAND_GROUP_MB", (int)t.band_group_mb);
     t.ql_global_min = env_int("TBK_QL_GLOBAL_MIN", 0);
     t.ql_overlap = env_int("TBK_QL_OVERLAP", t.ql_overlap);
     return t;
@@ -149,6 +153,12 @@ struct tbk_model {
     // scratch for the device-pointer entry points
     double* wsH = nullptr;  // [chunk][n*n] packed H(k)
     double* wsE = nullptr;  // [chunk][n]   sub-diagonals
+    // two-stage reduction (sizes it serves only): band arrays [band_cap][n][16] complex of up to band_cap matrices -- several
+    // workspace chunks -- and their sub-diagonals; the bulge chasing and the tridiagonal solver run once per group
+    double* wsB = nullptr;
+    double* wsEg = nullptr;
+    long band_cap = 0, band_fill = 0, band_first_row = 0;
+    double* band_D0 = nullptr;
     double* wsQ = nullptr;  // phase tiles of the chunk (GEMM path only)
     // regular k-mesh entry point (tbk_eigenval_mesh)
     int* dRc = nullptr;       // [nRpad] class (last component) of every stored R
@@ -340,12 +350,21 @@ long pick_chunk(const tbk_model* m) {
 
 int ensure_workspace(tbk_model* m, long nk) {
     const long want = std::min(nk, pick_chunk(m));
-    if (want <= m->chunk) return TBK_OK;
+    const bool two = !m->md.small_ok && tridiag_twostage_default(m->md.n, m->md.tune);
+    long group = 0;  // matrices whose band arrays are collected before the second stage runs
+    if (two) {
+        const long per = (long)tridiag_twostage_scratch_bytes(m->md.n, 1);
+        group = std::min(nk, std::max(want, (m->md.tune.band_group_mb << 20) / per));
+    }
+    if (want <= m->chunk && group <= m->band_cap) return TBK_OK;
     if (m->wsH) cudaFree(m->wsH);
     if (m->wsE) cudaFree(m->wsE);
     if (m->wsQ) cudaFree(m->wsQ);
     if (m->wsE2) cudaFree(m->wsE2);
-    m->wsH = m->wsE = m->wsQ = m->wsE2 = nullptr;
+    if (m->wsB) cudaFree(m->wsB);
+    if (m->wsEg) cudaFree(m->wsEg);
+    m->wsH = m->wsE = m->wsQ = m->wsE2 = m->wsB = m->wsEg = nullptr;
+    m->band_cap = m->band_fill = 0;
     m->chunk = 0;
     m->ws_bytes = 0;
     const size_t hb = (size_t)want * m->md.n * m->md.n * 8;
@@ -362,8 +381,15 @@ int ensure_workspace(tbk_model* m, long nk) {
         eb2 = eb;
         CU(cudaMalloc(&m->wsE2, eb2));
     }
+    size_t bb = 0;
+    if (two) {
+        bb = tridiag_twostage_scratch_bytes(m->md.n, group) + (size_t)group * m->md.n * 8;
+        CU(cudaMalloc(&m->wsB, tridiag_twostage_scratch_bytes(m->md.n, group)));
+        CU(cudaMalloc(&m->wsEg, (size_t)group * m->md.n * 8));
+        m->band_cap = group;
+    }
     m->chunk = want;
-    m->ws_bytes = hb + eb + qb + eb2;
+    m->ws_bytes = hb + eb + qb + eb2 + bb;
     return TBK_OK;
 }
 
@@ -389,6 +415,7 @@ int push_chunk(tbk_model* m, const PushPlan& plan, const double* rows, long firs
 // next chunk; two sub-diagonal buffers alternate.  (Opt-in experiment: the step is throughput bound, not latency bound --
 // the background QL slows its co-resident kernels by as much as it saves, see Tuning::ql_overlap.)  eig_begin / eig_drain bracket the chunks of one call.
 int eig_begin(tbk_model* m, long n_chunks) {
+    m->band_fill = 0;
     m->ql_pending[0] = m->ql_pending[1] = false;
     m->eig_chunk_index = 0;
     m->ql_bg_ok = m->md.tune.ql_overlap && n_chunks >= 2 && m->wsE2 != nullptr;
@@ -403,8 +430,34 @@ int eig_begin(tbk_model* m, long n_chunks) {
     return TBK_OK;
 }
 
+// Two-stage sizes: second stage (bulge chasing), tridiagonal solver and peer push of the collected group.
+int band_flush(tbk_model* m, cudaStream_t st, const PushPlan* plan) {
+    const ModelDev& md = m->md;
+    const long cnt = m->band_fill;
+    if (cnt <= 0) return TBK_OK;
+    m->band_fill = 0;
+    if (md.tune.band_stage2) LAUNCH(3, st, launch_band_chase(md.n, m->wsB, cnt, m->band_D0, m->wsEg, st, md.tune));
+    LAUNCH(4, st, launch_ql(md.n, m->band_D0, m->wsEg, cnt, m->dFail, st, md.tune));
+    if (plan)
+        if (int rc = push_chunk(m, *plan, m->band_D0, m->band_first_row, cnt, st)) return rc;
+    return TBK_OK;
+}
+
 int eig_chunk(tbk_model* m, double* D, long cn, bool last, cudaStream_t st, const PushPlan* plan, long first_row) {
     const ModelDev& md = m->md;
+    if (m->wsB != nullptr && tridiag_twostage_default(md.n, md.tune)) {
+        // first stage now (the packed matrices live in the workspace chunk), band arrays collected over several chunks
+        if (m->band_fill > 0 && (D != m->band_D0 + m->band_fill * md.n || m->band_fill + cn > m->band_cap))
+            if (int rc = band_flush(m, st, plan)) return rc;
+        if (m->band_fill == 0) {
+            m->band_D0 = D;
+            m->band_first_row = first_row;
+        }
+        LAUNCH(3, st, launch_band_reduce(md.n, m->wsH, cn, m->wsB + (size_t)m->band_fill * md.n * 32, st, md.tune));
+        m->band_fill += cn;
+        if (last || m->band_fill + m->chunk > m->band_cap) return band_flush(m, st, plan);
+        return TBK_OK;
+    }
     const int b = (int)(m->eig_chunk_index++ & 1);
     double* E = (m->ql_bg_ok && b) ? m->wsE2 : m->wsE;
     if (m->ql_pending[b]) {  // the QL two chunks back still owns this sub-diagonal buffer
@@ -451,6 +504,8 @@ int eig_chunk(tbk_model* m, double* D, long cn, bool last, cudaStream_t st, cons
 }
 
 int eig_drain(tbk_model* m, cudaStream_t st) {
+    if (m->band_fill > 0)  // (the last chunk of a call flushes; kept for callers that stop early)
+        if (int rc = band_flush(m, st, nullptr)) return rc;
     for (int b = 0; b < 2; ++b)
         if (m->ql_pending[b]) {
             CU(cudaStreamWaitEvent(st, m->ev_ql[b], 0));
@@ -1188,6 +1243,8 @@ int tbk_model_destroy(tbk_model* m) {
     }
     if (m->s_ql) cudaStreamDestroy(m->s_ql);
     cudaFree(m->wsE2);
+    cudaFree(m->wsB);
+    cudaFree(m->wsEg);
     cudaFree(m->dCounter);
     if (m->ev_chunk) cudaEventDestroy(m->ev_chunk);
     if (m->ev_push) cudaEventDestroy(m->ev_push);

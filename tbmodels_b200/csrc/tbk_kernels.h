@@ -49,6 +49,11 @@ struct Tuning {
     int ql_overlap = 0;         // TBK_QL_OVERLAP=1: run chunk i's QL in the background of chunk i + 1.  Off by default: measured
                                 //   on B200 the co-resident QL slows the GEMM / tridiagonalisation by what it saves (C3 explicit
                                 //   191.7 vs 189.0 ms per 2^21, k-grid 154.7 vs 128.1 ms; gpurun_out/r02u_*)
+    int tridiag_twostage = -1;  // TBK_TRIDIAG_TWOSTAGE: two-stage reduction (band + bulge chasing, eig_band.cu) from this N on
+                                //   (0 = never, -1 = default)
+    int band_t = 0;             // TBK_BAND_T: threads per matrix of the band reduction (0 = by size)
+    int band_stage2 = 1;        // TBK_BAND_STAGE2=0: timing hook, skip the bulge chasing (results are then meaningless)
+    long band_group_mb = 1024;  // TBK_BAND_GROUP_MB: band arrays collected before one bulge-chasing launch
     int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)
 };
 Tuning read_tuning();
@@ -121,6 +126,14 @@ cudaError_t launch_mesh_kpoints(int dim, const int64_t* dims, const double* shif
 size_t mesh_lines_smem_bytes(int K2);
 // Batched Hermitian -> tridiagonal reduction (Hp is destroyed). D, E: [nk][n].
 cudaError_t launch_tridiag(int n, double* Hp, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
+// Two-stage variant (eig_band.cu): Hermitian -> band (half bandwidth 8) on the tensor cores, band -> tridiagonal by bulge chasing.
+bool tridiag_twostage_fits(int n);
+bool tridiag_twostage_default(int n, const Tuning& tune);  // the size is served by the two-stage reduction
+size_t tridiag_twostage_scratch_bytes(int n, long nk);
+// The two stages are launched separately: the band arrays of several workspace chunks are collected (they are 16 / n of a
+// matrix) and chased in one launch, which gives the latency-bound second stage enough matrices to fill the GPU.
+cudaError_t launch_band_reduce(int n, double* Hp, long nk, double* band_ws, cudaStream_t st, const Tuning& tune);
+cudaError_t launch_band_chase(int n, double* band_ws, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
 // Register-resident warp-per-matrix variant (eig_tridiag_reg.cu), n <= kTridiagRegMaxN.  The matrix of problem k is the
 // packed n x n block at Hp + k * mstride; results go to D / E [k * ldo + off + i] (mstride = 0 -> n * n, ldo = 0 -> n).
 bool tridiag_reg_fits(int n);

@@ -399,14 +399,15 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
 
 
 @pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 36, 37, 40, 41, 48, 49, 64, 65, 96, 97, 112, 113, 119, 120, 121, 128, 129, 144,
-                                   159, 160, 161, 164, 165, 200, 257, 300, 513, 600, 601])
+                                   159, 160, 161, 164, 165, 200, 223, 224, 225, 257, 288, 289, 300, 513, 600, 601, 641, 700, 816, 817])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
-    """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection)."""
+    """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection, one-stage /
+    two-stage reduction from N = 224, its thread configurations, its last size 816)."""
     from oracle import workloads as wl
 
     orc = _oracle()
     p = wl.synthetic(n_orb, 4, seed=n_orb)
-    nk = 37 if n_orb <= 128 else (5 if n_orb <= 300 else 2)
+    nk = 37 if n_orb <= 128 else (5 if n_orb <= 300 else (2 if n_orb <= 601 else 1))
     k = np.random.default_rng(n_orb).uniform(-1, 1, size=(nk, 3))
     _check(tbk, p, k, None, orc.hamilton(p.R, p.hop, p.pos, k[:3], 2), orc.eigenval_array(p.R, p.hop, p.pos, k), f"N={n_orb}")
 
@@ -455,6 +456,75 @@ def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
         p = wl.synthetic(n_orb, 3, seed=1000 + n_orb)
         k = np.random.default_rng(n_orb).uniform(-1, 1, size=(7 if n_orb <= 129 else 3, 3))
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads} LPR={lpr}")
+
+
+@pytest.mark.parametrize("threads", ["256", "257", "512"])
+def test_twostage_tridiag_every_shape(tbk, monkeypatch, threads):
+    """The two-stage reduction (band of half bandwidth 8 on the tensor cores + bulge chasing, eig_band.cu) forced onto
+    small and ragged sizes: sizes that are not multiples of 8, last panels with fewer than 8 rows, a single panel,
+    every thread configuration of the first stage; odd batch sizes leave half a warp of the second stage idle."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_TWOSTAGE", "12")
+    monkeypatch.setenv("TBK_BAND_T", threads)
+    for n_orb in (12, 13, 15, 16, 17, 18, 19, 23, 24, 25, 26, 31, 33, 40, 47, 63, 65, 100, 129, 200, 255, 256):
+        p = wl.synthetic(n_orb, 3, seed=2000 + n_orb)
+        k = np.random.default_rng(n_orb).uniform(-1, 1, size=(7 if n_orb <= 129 else 3, 3))
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"two-stage N={n_orb} T={threads}")
+
+
+def test_twostage_degenerate_and_sparse_matrices(tbk, monkeypatch):
+    """Structured spectra through the two-stage reduction: H = 0, diagonal, block diagonal (zero columns in the panel
+    factorisation: reflectors with tau = 0), a supercell (block-sparse hopping matrices)."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_TWOSTAGE", "12")
+    rng = np.random.default_rng(11)
+    n = 40
+    R = np.zeros((1, 3), dtype=np.int32)
+    pos = np.zeros((n, 3))
+    k = rng.uniform(-1, 1, size=(3, 3))
+    blocks = np.zeros((n, n), dtype=complex)
+    for b0 in range(0, n, 10):
+        a = rng.standard_normal((10, 10)) + 1j * rng.standard_normal((10, 10))
+        blocks[b0:b0 + 10, b0:b0 + 10] = a + a.conj().T
+    from tbmodels_b200._pack import PackedModel
+
+    for name, h in (("zero", np.zeros((n, n), dtype=complex)), ("diagonal", np.diag(rng.standard_normal(n)).astype(complex)),
+                    ("blocks", blocks)):
+        p = PackedModel(R=R, hop=np.ascontiguousarray((0.5 * h)[None]), pos=pos)
+        want = orc.eigenval_array(p.R, p.hop, p.pos, k)
+        got = tbk.Evaluator(p).eigenval_array(k)
+        assert_eig_close(got, want, f"two-stage {name}")
+    sup = wl.supercell(wl.synthetic(8, 6, seed=3), (2, 2, 2))
+    ks = rng.uniform(-1, 1, size=(3, 3))
+    assert_eig_close(tbk.Evaluator(sup).eigenval_array(ks), orc.eigenval_array(sup.R, sup.hop, sup.pos, ks), "two-stage supercell")
+
+
+def test_twostage_groups_and_chunks_bit_equal(tbk, monkeypatch):
+    """The band arrays of several workspace chunks are collected and chased in one launch: neither the chunk size
+    (TBK_WORKSPACE_MB) nor the group size (TBK_BAND_GROUP_MB) may change a bit; the k-mesh entry point takes the same route."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    p = wl.synthetic(230, 3, seed=5)
+    k = np.random.default_rng(5).uniform(-1, 1, size=(75, 3))
+    ref = tbk.Evaluator(p).eigenval_array(k)
+    assert_eig_close(ref, orc.eigenval_array(p.R, p.hop, p.pos, k), "two-stage N=230")
+    for ws, grp in (("8", "1024"), ("8", "1"), ("8", "2"), ("3", "3")):
+        monkeypatch.setenv("TBK_WORKSPACE_MB", ws)
+        monkeypatch.setenv("TBK_BAND_GROUP_MB", grp)
+        ev = tbk.Evaluator(p)
+        assert np.array_equal(ev.eigenval_array(k), ref), f"workspace {ws} MB, group {grp} MB"
+        assert np.array_equal(ev.eigenval_array(k[:31]), ref[:31])
+        mesh = ev.eigenval_mesh((3, 2, 5))
+        ev.close()
+        kk = np.stack(np.meshgrid(np.arange(3) / 3, np.arange(2) / 2, np.arange(5) / 5, indexing="ij"), axis=-1).reshape(-1, 3)
+        assert_eig_close(np.asarray(mesh).reshape(-1, 230), orc.eigenval_array(p.R, p.hop, p.pos, kk), "two-stage mesh")
+    monkeypatch.delenv("TBK_WORKSPACE_MB")
+    monkeypatch.delenv("TBK_BAND_GROUP_MB")
 
 
 @pytest.mark.parametrize("ratio", ["0", "50", "80"])

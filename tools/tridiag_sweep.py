@@ -61,6 +61,11 @@ VARIANTS = {
     "mid0": {"TBK_TRIDIAG_REG_MID": "0"},
     "mid20": {"TBK_TRIDIAG_REG_MID": "20"},
     "mid24": {"TBK_TRIDIAG_REG_MID": "24"},
+    "two": {"TBK_TRIDIAG_TWOSTAGE": "12"},
+    "two256": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "256"},
+    "two512": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "512"},
+    "two257": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "257"},
+    "two_s1": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_STAGE2": "0"},
 }
 KEYS = sorted({k for v in VARIANTS.values() for k in v})
 
