@@ -43,6 +43,11 @@ constexpr int GMW = 8;   // warps that take part in the G / M products
 #define TBK_BAND_PREFETCH 1
 #endif
 
+// Index of element (row i, panel column c) of the V / Z arrays ([rows][8] complex, 128 bytes per row).  The column is
+// swizzled with the row so that "one lane per row, same column" (panel factorisation, Z = Y T + V C2) and "8 rows x 4
+// column pairs" (tensor-core operands of the trailing update) are both free of bank conflicts.
+__device__ __forceinline__ int vz(int i, int c) { return i * BB + (c ^ (i & 7)); }
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
@@ -95,13 +100,13 @@ __device__ __forceinline__ void qr_step(double2* V, int m, double (&acc)[16], do
     }
     const int nw = (m + 31) >> 5;
     cta_sum_n<2 * NC, WARPS>(acc, red, tid, nw < WARPS ? nw : WARPS);
-    const double2 al = V[K * BB + K];
+    const double2 al = V[vz(K, K)];
     double beta, tr, ti, sr, si;
     householder_gen(al.x, al.y, acc[0], beta, tr, ti, sr, si);
     double ur[BB], ui[BB];  // u_c = conj(tau) (E[K][c] + conj(scale) s_c): row K of R is E[K][c] - u_c
 #pragma unroll
     for (int c = K + 1; c < BB; ++c) {
-        const double2 e = V[K * BB + c];
+        const double2 e = V[vz(K, c)];
         const double s_r = acc[2 * (c - K)], s_i = acc[2 * (c - K) + 1];
         const double zr = e.x + sr * s_r + si * s_i;
         const double zi = e.y + sr * s_i - si * s_r;
@@ -123,16 +128,17 @@ __device__ __forceinline__ void qr_step(double2* V, int m, double (&acc)[16], do
     for (int i = tid; i < m; i += THREADS) {
         if (i <= K) continue;
         double2* e = V + i * BB;
-        const double2 x = e[K];
+        const int sw = i & 7;  // (swizzled columns, see vz)
+        const double2 x = e[K ^ sw];
         const double vr = x.x * sr - x.y * si, vi = x.x * si + x.y * sr;
-        e[K] = make_double2(vr, vi);
+        e[K ^ sw] = make_double2(vr, vi);
         double nr[BB], ni[BB];
 #pragma unroll
         for (int c = K + 1; c < BB; ++c) {
-            const double2 ec = e[c];
+            const double2 ec = e[c ^ sw];
             nr[c] = ec.x - (vr * ur[c] - vi * ui[c]);
             ni[c] = ec.y - (vr * ui[c] + vi * ur[c]);
-            e[c] = make_double2(nr[c], ni[c]);
+            e[c ^ sw] = make_double2(nr[c], ni[c]);
         }
         if (K + 1 < BB && i > K + 1) {
             constexpr int K1 = (K + 1 < BB) ? K + 1 : K;
@@ -181,15 +187,29 @@ __device__ __forceinline__ void her2k_update(double* Ar, double* Ai, int N, int 
                 cim[jb][h] = (row_ok && col + h < row) ? pim[col + h] : 0.0;
             }
         }
+        if (TBK_BAND_PREFETCH) {  // the warp's next strip -> L2: lane = (row of the strip, 8 x 8 block), one line per plane
+            int In = I, sn = s + WARPS;
+            int nsn = ((In - I0) >> 2) + 1;
+            while (In < NBk && sn >= nsn) {
+                sn -= nsn;
+                ++In;
+                nsn = ((In - I0) >> 2) + 1;
+            }
+            const int rown = 8 * In + g, coln = 8 * (I0 + 4 * sn + tq);
+            if (In < NBk && rown < N && coln < rown) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Ar + tri((long)rown) + coln));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(Ai + trs((long)rown) + coln));
+            }
+        }
         const int ri = 8 * (I - I0) + g;  // (rows past the end: inside the zero padding of the arrays)
-        const double2 av0 = V[ri * BB + 2 * tq], av1 = V[ri * BB + 2 * tq + 1];
-        const double2 az0 = Z[ri * BB + 2 * tq], az1 = Z[ri * BB + 2 * tq + 1];
+        const double2 av0 = V[vz(ri, 2 * tq)], av1 = V[vz(ri, 2 * tq + 1)];
+        const double2 az0 = Z[vz(ri, 2 * tq)], az1 = Z[vz(ri, 2 * tq + 1)];
 #pragma unroll
         for (int jb = 0; jb < 4; ++jb) {
             if (J0 + jb <= I) {  // warp-uniform
                 const int ci = 8 * (J0 + jb - I0) + g;
-                const double2 bv0 = V[ci * BB + 2 * tq], bv1 = V[ci * BB + 2 * tq + 1];
-                const double2 bz0 = Z[ci * BB + 2 * tq], bz1 = Z[ci * BB + 2 * tq + 1];
+                const double2 bv0 = V[vz(ci, 2 * tq)], bv1 = V[vz(ci, 2 * tq + 1)];
+                const double2 bz0 = Z[vz(ci, 2 * tq)], bz1 = Z[vz(ci, 2 * tq + 1)];
                 dmma884(cre[jb][0], cre[jb][1], -av0.x, bz0.x);
                 dmma884(cim[jb][0], cim[jb][1], -av0.y, bz0.x);
                 dmma884(cre[jb][0], cre[jb][1], -av0.y, bz0.y);
@@ -280,7 +300,7 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
                 e.x = Ar[tri(r) + c0 + c];
                 e.y = Ai[trs(r) + c0 + c];
             }
-            V[idx] = e;
+            V[vz(i, c)] = e;
         }
         if (tid < 128) Rb[tid] = 0.0;
         __syncthreads();
@@ -292,10 +312,10 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
             for (int v = 0; v < 16; ++v) acc[v] = 0.0;
             for (int i = tid; i < m; i += THREADS) {
                 if (i == 0) continue;
-                const double2 x = V[i * BB];
+                const double2 x = V[vz(i, 0)];
 #pragma unroll
                 for (int c = 0; c < BB; ++c) {
-                    const double2 e = V[i * BB + c];
+                    const double2 e = V[vz(i, c)];
                     acc[2 * c] = fma(x.x, e.x, fma(x.y, e.y, acc[2 * c]));
                     acc[2 * c + 1] = fma(x.x, e.y, fma(-x.y, e.x, acc[2 * c + 1]));
                 }
@@ -314,11 +334,11 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
         // unit diagonal / zeros above it; columns without a reflector (m < 8) are zero vectors
         if (tid < 64) {
             const int k = tid >> 3, c = tid & 7;
-            if (k < m && c >= k) V[k * BB + c] = make_double2((c == k) ? 1.0 : 0.0, 0.0);
+            if (k < m && c >= k) V[vz(k, c)] = make_double2((c == k) ? 1.0 : 0.0, 0.0);
         }
         if (m < BB) {
             for (int idx = tid; idx < mp * BB; idx += THREADS)
-                if ((idx & 7) >= m) V[idx] = make_double2(0.0, 0.0);
+                if ((idx & 7) >= m) V[vz(idx >> 3, idx & 7)] = make_double2(0.0, 0.0);
         }
         // band columns c0 .. c0 + 7: diagonal block (d <= 7 - k), R (8 - k <= d <= 8), room for the bulges (zero)
         if (tid < BB * BWD) {
@@ -419,7 +439,7 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
                     const int cc = 8 * Jc + 4 * ks + t;
-                    const double2 bv = V[cc * BB + g];
+                    const double2 bv = V[vz(cc, g)];
                     const double aar = cur[2 * ks], aai = cur[2 * ks + 1];
                     const double abr = cur[4 + 2 * ks], abi = cur[4 + 2 * ks + 1];
                     dmma884(ya[0], ya[1], aar, bv.x);
@@ -434,11 +454,11 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
                 if (++Jc == nbk) {
                     const int ria = 8 * Ic + g, rib = ria + 8;
                     // (rows past the end of the matrix: zeros into the padding rows of Z)
-                    Z[ria * BB + 2 * t] = make_double2(ya[0], ya[2]);
-                    Z[ria * BB + 2 * t + 1] = make_double2(ya[1], ya[3]);
+                    Z[vz(ria, 2 * t)] = make_double2(ya[0], ya[2]);
+                    Z[vz(ria, 2 * t + 1)] = make_double2(ya[1], ya[3]);
                     if (Ic + 1 < nbk) {
-                        Z[rib * BB + 2 * t] = make_double2(yb[0], yb[2]);
-                        Z[rib * BB + 2 * t + 1] = make_double2(yb[1], yb[3]);
+                        Z[vz(rib, 2 * t)] = make_double2(yb[0], yb[2]);
+                        Z[vz(rib, 2 * t + 1)] = make_double2(yb[1], yb[3]);
                     }
 #pragma unroll
                     for (int v = 0; v < 4; ++v) ya[v] = yb[v] = 0.0;
@@ -456,9 +476,9 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
             double gr0 = 0.0, gr1 = 0.0, gi0 = 0.0, gi1 = 0.0, mr0 = 0.0, mr1 = 0.0, mi0 = 0.0, mi1 = 0.0;
             for (int ks = w; ks < (mp >> 2); ks += WGM) {
                 const int i = 4 * ks + t;
-                const double2 a = V[i * BB + g];
+                const double2 a = V[vz(i, g)];
                 double2 y = make_double2(0.0, 0.0);
-                if (i < m) y = Z[i * BB + g];
+                if (i < m) y = Z[vz(i, g)];
                 dmma884(gr0, gr1, a.x, a.x);
                 dmma884(gi0, gi1, a.x, a.y);
                 dmma884(mr0, mr1, a.x, y.x);
@@ -549,8 +569,8 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
             double2 y[BB], v[BB];
 #pragma unroll
             for (int l = 0; l < BB; ++l) {
-                y[l] = Z[i * BB + l];
-                v[l] = V[i * BB + l];
+                y[l] = Z[vz(i, l)];
+                v[l] = V[vz(i, l)];
             }
 #pragma unroll
             for (int j = 0; j < BB; ++j) {
@@ -566,7 +586,7 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
                     zr += v[l].x * cr - v[l].y * ci;
                     zi += v[l].x * ci + v[l].y * cr;
                 }
-                Z[i * BB + j] = make_double2(zr, zi);
+                Z[vz(i, j)] = make_double2(zr, zi);
             }
         }
         __syncthreads();
@@ -594,91 +614,76 @@ band_reduce_kernel(double* __restrict__ Hp, int N, long nk, double2* __restrict_
     }
 }
 
-// Stage 2: band[c][d] = A[c + d, c] (d < 16) -> d, e.  16 lanes per matrix; lane hl holds row R0 + hl of the 16 x 8 panel
-// of columns R0 .. R0 + 7: rows 0 .. 7 the diagonal block (lower triangle), rows 8 .. 15 the block below it.
-// Sum x[c] over the 8-lane group (lanes hl & 7) in a fixed order; lane l of the group ends with the sum of entry l in x[0].
-__device__ __forceinline__ void group8_reduce_scatter(double (&x)[8], int hl) {
-#pragma unroll
-    for (int half = 4, off = 4; half >= 1; half >>= 1, off >>= 1) {
-        const bool up = (hl & off) != 0;
-#pragma unroll
-        for (int v = 0; v < half; ++v) {
-            const double mine = up ? x[half + v] : x[v];
-            const double other = up ? x[v] : x[half + v];
-            x[v] = mine + __shfl_xor_sync(0xffffffffu, other, off);
-        }
-    }
-}
-
+// Stage 2: band[c][d] = A[c + d, c] (d < 16) -> d, e.  Eight lanes per matrix, four matrices per warp; lane gl holds row
+// R0 + gl of the diagonal block (the full Hermitian row: left of the diagonal from the band columns R0 .. R0 + gl, right
+// of it the conjugates of its own column) and row R0 + 8 + gl of the block below, columns R0 .. R0 + 7.  Products along a
+// row are local; the only sums across lanes are (tau p)^H v, the reflector norm and v2^H B.
 template <int WPB>
 __global__ void __launch_bounds__(32 * WPB, 16 / WPB)
 band_chase_kernel(double2* band_all, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
     constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, hl = lane & 15;
-    const long mat = ((long)blockIdx.x * WPB + (threadIdx.x >> 5)) * 2 + (lane >> 4);
+    const int lane = threadIdx.x & 31, gl = lane & 7;
+    const long mat = ((long)blockIdx.x * WPB + (threadIdx.x >> 5)) * 4 + (lane >> 3);
     const bool act = mat < nk;
     double2* band = band_all + (act ? mat : 0) * (long)N * BWD;
-    const bool top = hl < 8;
     for (int j = 0; j < N - 1; ++j) {
         // reflector that annihilates column j below the sub-diagonal (rows j + 1 .. j + 8)
         double xr = 0.0, xi = 0.0;
-        if (act && top && j + 1 + hl < N) {
-            const double2 x = band[(long)j * BWD + 1 + hl];
+        if (act && j + 1 + gl < N) {
+            const double2 x = band[(long)j * BWD + 1 + gl];
             xr = x.x;
             xi = x.y;
         }
-        double xn = (hl >= 1) ? xr * xr + xi * xi : 0.0;
+        double xn = (gl >= 1) ? xr * xr + xi * xi : 0.0;
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) xn += __shfl_xor_sync(FULL, xn, off);
-        const double alr = __shfl_sync(FULL, xr, 0, 16), ali = __shfl_sync(FULL, xi, 0, 16);
+        for (int off = 4; off > 0; off >>= 1) xn += __shfl_xor_sync(FULL, xn, off);
+        const double alr = __shfl_sync(FULL, xr, 0, 8), ali = __shfl_sync(FULL, xi, 0, 8);
         double beta, tr, ti, sr, si;
         householder_gen(alr, ali, xn, beta, tr, ti, sr, si);
-        if (act && hl == 0) {
+        if (act && gl == 0) {
             D[mat * N + j] = band[(long)j * BWD].x;
             E[mat * N + j] = beta;
         }
-        // own element of v (top lanes) and the whole vector
-        double ovr = (hl == 0) ? 1.0 : xr * sr - xi * si;
-        double ovi = (hl == 0) ? 0.0 : xr * si + xi * sr;
+        double ovr = (gl == 0) ? 1.0 : xr * sr - xi * si;  // own element of v, then the whole vector
+        double ovi = (gl == 0) ? 0.0 : xr * si + xi * sr;
         double vr[BB], vi[BB];
 #pragma unroll
         for (int c = 0; c < BB; ++c) {
-            vr[c] = __shfl_sync(FULL, ovr, c, 16);
-            vi[c] = __shfl_sync(FULL, ovi, c, 16);
+            vr[c] = __shfl_sync(FULL, ovr, c, 8);
+            vi[c] = __shfl_sync(FULL, ovi, c, 8);
         }
         for (int R0 = j + 1; R0 < N; R0 += BB) {
-            const bool rowok = act && (R0 + hl < N);
-            double pr[BB], pi[BB];
+            const bool topok = act && (R0 + gl < N);
+            const bool botok = act && (R0 + BB + gl < N);
+            const double2* pcol = band + (long)R0 * BWD + gl;       // + 15 c: element (row R0 + gl, column R0 + c), c <= gl
+            const double2* pown = band + (long)(R0 + gl) * BWD;     // + d: element (row R0 + gl + d, column R0 + gl)
+            double dr[BB], di[BB], br[BB], bi[BB];
 #pragma unroll
             for (int c = 0; c < BB; ++c) {
-                const int dd = hl - c;
                 double2 e = make_double2(0.0, 0.0);
-                if (rowok && dd >= 0) e = band[(long)(R0 + c) * BWD + dd];
-                pr[c] = e.x;
-                pi[c] = (dd == 0) ? 0.0 : e.y;
+                if (topok && c <= gl) e = pcol[15 * c];
+                if (topok && c > gl && R0 + c < N) {  // right of the diagonal: conjugate of the own column
+                    e = pown[c - gl];
+                    e.y = -e.y;
+                }
+                dr[c] = e.x;
+                di[c] = (c == gl) ? 0.0 : e.y;
+                double2 f = make_double2(0.0, 0.0);
+                if (botok) f = pcol[15 * c + BB];
+                br[c] = f.x;
+                bi[c] = f.y;
             }
-            // row sums s = sum_c P[c] v_c : the row part of D v (top) and B v (bottom)
-            double s_r = 0.0, s_i = 0.0;
+            // p = D v (local), tau p, dot = (tau p)^H v, w = tau p - 1/2 tau dot v
+            double p_r = 0.0, p_i = 0.0, y_r = 0.0, y_i = 0.0;
 #pragma unroll
             for (int c = 0; c < BB; ++c) {
-                s_r = fma(pr[c], vr[c], fma(-pi[c], vi[c], s_r));
-                s_i = fma(pr[c], vi[c], fma(pi[c], vr[c], s_i));
+                p_r = fma(dr[c], vr[c], fma(-di[c], vi[c], p_r));
+                p_i = fma(dr[c], vi[c], fma(di[c], vr[c], p_i));
+                y_r = fma(br[c], vr[c], fma(-bi[c], vi[c], y_r));
+                y_i = fma(br[c], vi[c], fma(bi[c], vr[c], y_i));
             }
-            // column part of D v: q_c = sum_{r > c} conj(D[r][c]) v_r (reduce-scatter: top lane c ends with q_c)
-            double q_r[BB], q_i[BB];
-#pragma unroll
-            for (int c = 0; c < BB; ++c) {
-                const bool mk = top && c < hl;
-                q_r[c] = mk ? pr[c] * ovr + pi[c] * ovi : 0.0;
-                q_i[c] = mk ? pr[c] * ovi - pi[c] * ovr : 0.0;
-            }
-            group8_reduce_scatter(q_r, hl);
-            group8_reduce_scatter(q_i, hl);
-            const double myq_r = q_r[0], myq_i = q_i[0];
-            const double p_r = s_r + myq_r, p_i = s_i + myq_i;
             const double tpr = tr * p_r - ti * p_i, tpi = tr * p_i + ti * p_r;
-            double d_r = top ? tpr * ovr + tpi * ovi : 0.0;  // (tau p)^H v
-            double d_i = top ? tpr * ovi - tpi * ovr : 0.0;
+            double d_r = tpr * ovr + tpi * ovi, d_i = tpr * ovi - tpi * ovr;
 #pragma unroll
             for (int off = 4; off > 0; off >>= 1) {
                 d_r += __shfl_xor_sync(FULL, d_r, off);
@@ -686,70 +691,59 @@ band_chase_kernel(double2* band_all, int N, long nk, double* __restrict__ D, dou
             }
             const double al_r = -0.5 * (tr * d_r - ti * d_i), al_i = -0.5 * (tr * d_i + ti * d_r);
             const double owr = tpr + al_r * ovr - al_i * ovi, owi = tpi + al_r * ovi + al_i * ovr;
-            const double tyr = tr * s_r - ti * s_i, tyi = tr * s_i + ti * s_r;  // bottom rows: tau (B v)
+            const double tyr = tr * y_r - ti * y_i, tyi = tr * y_i + ti * y_r;  // tau (B v)
 #pragma unroll
             for (int c = 0; c < BB; ++c) {
-                const double wr = __shfl_sync(FULL, owr, c, 16), wi = __shfl_sync(FULL, owi, c, 16);
-                if (top) {
-                    if (c <= hl) {  // D -= v w^H + w v^H (lower triangle)
-                        pr[c] -= ovr * wr + ovi * wi + owr * vr[c] + owi * vi[c];
-                        pi[c] -= ovi * wr - ovr * wi + owi * vr[c] - owr * vi[c];
-                    }
-                } else {  // B -= tau (B v) v^H
-                    pr[c] -= tyr * vr[c] + tyi * vi[c];
-                    pi[c] -= tyi * vr[c] - tyr * vi[c];
-                }
+                const double wr = __shfl_sync(FULL, owr, c, 8), wi = __shfl_sync(FULL, owi, c, 8);
+                // D -= v w^H + w v^H (only the stored part, c <= gl, is needed);  B -= tau (B v) v^H
+                dr[c] -= ovr * wr + ovi * wi + owr * vr[c] + owi * vi[c];
+                di[c] -= ovi * wr - ovr * wi + owi * vr[c] - owr * vi[c];
+                br[c] -= tyr * vr[c] + tyi * vi[c];
+                bi[c] -= tyi * vr[c] - tyr * vi[c];
             }
-            // next reflector: annihilates column 0 of the block below (rows 9 .. 15 of the panel)
-            const double x2r = top ? 0.0 : pr[0], x2i = top ? 0.0 : pi[0];
-            double xn2 = (hl >= 9) ? x2r * x2r + x2i * x2i : 0.0;
+            // next reflector: annihilates column 0 of the block below under its first row
+            double xn2 = (gl >= 1) ? br[0] * br[0] + bi[0] * bi[0] : 0.0;
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1) xn2 += __shfl_xor_sync(FULL, xn2, off);
-            const double a2r = __shfl_sync(FULL, x2r, 8, 16), a2i = __shfl_sync(FULL, x2i, 8, 16);
+            for (int off = 4; off > 0; off >>= 1) xn2 += __shfl_xor_sync(FULL, xn2, off);
+            const double a2r = __shfl_sync(FULL, br[0], 0, 8), a2i = __shfl_sync(FULL, bi[0], 0, 8);
             double beta2, t2r, t2i, s2r, s2i;
             householder_gen(a2r, a2i, xn2, beta2, t2r, t2i, s2r, s2i);
-            const double mv2r = (hl == 8) ? 1.0 : x2r * s2r - x2i * s2i;  // (top lanes: 0)
-            const double mv2i = (hl == 8) ? 0.0 : x2r * s2i + x2i * s2r;
+            const double mv2r = (gl == 0) ? 1.0 : br[0] * s2r - bi[0] * s2i;
+            const double mv2i = (gl == 0) ? 0.0 : br[0] * s2i + bi[0] * s2r;
             const double cvr = t2r * mv2r + t2i * mv2i, cvi = t2r * mv2i - t2i * mv2r;  // conj(tau2) v2_own
-            // z_c = v2^H B[:, c] (reduce-scatter: bottom lane 8 + c ends with z_c);  B -= conj(tau2) v2 z
-            double z_r[BB], z_i[BB];
 #pragma unroll
-            for (int c = 0; c < BB; ++c) {
-                z_r[c] = top ? 0.0 : mv2r * pr[c] + mv2i * pi[c];
-                z_i[c] = top ? 0.0 : mv2r * pi[c] - mv2i * pr[c];
-            }
-            group8_reduce_scatter(z_r, hl);
-            group8_reduce_scatter(z_i, hl);
+            for (int c = 0; c < BB; ++c) {  // z_c = v2^H B[:, c];  B -= conj(tau2) v2 z
+                double z_r = mv2r * br[c] + mv2i * bi[c];
+                double z_i = mv2r * bi[c] - mv2i * br[c];
 #pragma unroll
-            for (int c = 0; c < BB; ++c) {
-                const double zr = __shfl_sync(FULL, z_r[0], 8 + c, 16), zi = __shfl_sync(FULL, z_i[0], 8 + c, 16);
-                if (!top) {
-                    pr[c] -= cvr * zr - cvi * zi;
-                    pi[c] -= cvr * zi + cvi * zr;
+                for (int off = 4; off > 0; off >>= 1) {
+                    z_r += __shfl_xor_sync(FULL, z_r, off);
+                    z_i += __shfl_xor_sync(FULL, z_i, off);
                 }
+                br[c] -= cvr * z_r - cvi * z_i;
+                bi[c] -= cvr * z_i + cvi * z_r;
             }
-            if (!top) {
-                pr[0] = (hl == 8) ? beta2 : 0.0;
-                pi[0] = 0.0;
-            }
+            br[0] = (gl == 0) ? beta2 : 0.0;
+            bi[0] = 0.0;
+            double2* qcol = band + (long)R0 * BWD + gl;
 #pragma unroll
             for (int c = 0; c < BB; ++c) {
-                const int dd = hl - c;
-                if (rowok && dd >= 0) band[(long)(R0 + c) * BWD + dd] = make_double2(pr[c], (dd == 0) ? 0.0 : pi[c]);
+                if (topok && c <= gl) qcol[15 * c] = make_double2(dr[c], (c == gl) ? 0.0 : di[c]);
+                if (botok) qcol[15 * c + BB] = make_double2(br[c], bi[c]);
             }
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < BB; ++c) {
-                vr[c] = __shfl_sync(FULL, mv2r, 8 + c, 16);
-                vi[c] = __shfl_sync(FULL, mv2i, 8 + c, 16);
+                vr[c] = __shfl_sync(FULL, mv2r, c, 8);
+                vi[c] = __shfl_sync(FULL, mv2i, c, 8);
             }
-            ovr = __shfl_sync(FULL, mv2r, 8 + (hl & 7), 16);
-            ovi = __shfl_sync(FULL, mv2i, 8 + (hl & 7), 16);
+            ovr = mv2r;
+            ovi = mv2i;
             tr = t2r;
             ti = t2i;
         }
     }
-    if (act && hl == 0) {
+    if (act && gl == 0) {
         D[mat * N + N - 1] = band[(long)(N - 1) * BWD].x;
         E[mat * N + N - 1] = 0.0;
     }
@@ -786,13 +780,23 @@ cudaError_t launch_band_reduce(int n, double* Hp, long nk, double* band_ws, cuda
     return launch_band_reduce_t<512, 1>(n, Hp, nk, band, st);
 }
 
+long band_chase_wave_matrices(const Tuning& tune) {
+    if (tune.band_wave > 0) return tune.band_wave;
+    static const long wave = [] {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        return (long)sms * 16 * 4;  // 16 warps per SM (128 registers), 4 matrices per warp
+    }();
+    return wave;
+}
+
 // Stage 2 of nk matrices: band -> D, E [nk][n].
 cudaError_t launch_band_chase(int n, double* band_ws, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
     if (nk <= 0) return cudaSuccess;
     if (band_ws == nullptr) return cudaErrorInvalidConfiguration;
     (void)tune;
     constexpr int WPB = 4;
-    const long ctas = (nk + 2 * WPB - 1) / (2 * WPB);
+    const long ctas = (nk + 4 * WPB - 1) / (4 * WPB);
     if (ctas > 2147483647L) return cudaErrorInvalidConfiguration;
     band_chase_kernel<WPB><<<(unsigned)ctas, 32 * WPB, 0, st>>>(reinterpret_cast<double2*>(band_ws), n, nk, D, E);
     return cudaGetLastError();

@@ -132,6 +132,7 @@ Tuning read_tuning() {
     t.band_t = env_int("TBK_BAND_T", t.band_t);
     t.band_stage2 = env_int("TBK_BAND_STAGE2", t.band_stage2);
     t.band_group_mb = env_int("TBK_BAND_GROUP_MB", (int)t.band_group_mb);
+    t.band_wave = env_int("TBK_BAND_WAVE", t.band_wave);
     t.ql_global_min = env_int("TBK_QL_GLOBAL_MIN", 0);
     t.ql_overlap = env_int("TBK_QL_OVERLAP", t.ql_overlap);
     return t;
@@ -436,7 +437,18 @@ int band_flush(tbk_model* m, cudaStream_t st, const PushPlan* plan) {
     const long cnt = m->band_fill;
     if (cnt <= 0) return TBK_OK;
     m->band_fill = 0;
-    if (md.tune.band_stage2) LAUNCH(3, st, launch_band_chase(md.n, m->wsB, cnt, m->band_D0, m->wsEg, st, md.tune));
+    if (md.tune.band_stage2) {
+        // balanced launches of at most one resident wave of the bulge-chasing kernel (its warps all run equally long: a
+        // launch of 1.3 waves takes as long as one of 2)
+        const long wave = std::max<long>(1, band_chase_wave_matrices(md.tune));
+        const long parts = (cnt + wave - 1) / wave;
+        const long per = (cnt + parts - 1) / parts;
+        for (long c0 = 0; c0 < cnt; c0 += per) {
+            const long cn = std::min(per, cnt - c0);
+            LAUNCH(3, st, launch_band_chase(md.n, m->wsB + (size_t)c0 * md.n * 32, cn, m->band_D0 + c0 * md.n,
+                                            m->wsEg + c0 * md.n, st, md.tune));
+        }
+    }
     LAUNCH(4, st, launch_ql(md.n, m->band_D0, m->wsEg, cnt, m->dFail, st, md.tune));
     if (plan)
         if (int rc = push_chunk(m, *plan, m->band_D0, m->band_first_row, cnt, st)) return rc;

@@ -53,7 +53,8 @@ struct Tuning {
                                 //   (0 = never, -1 = default)
     int band_t = 0;             // TBK_BAND_T: threads per matrix of the band reduction (0 = by size)
     int band_stage2 = 1;        // TBK_BAND_STAGE2=0: timing hook, skip the bulge chasing (results are then meaningless)
-    long band_group_mb = 1024;  // TBK_BAND_GROUP_MB: band arrays collected before one bulge-chasing launch
+    int band_wave = 0;          // TBK_BAND_WAVE: matrices per launch of the bulge chasing (0 = one resident wave)
+    long band_group_mb = 2048;  // TBK_BAND_GROUP_MB: band arrays collected before one bulge-chasing launch
     int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)
 };
 Tuning read_tuning();
@@ -133,6 +134,7 @@ size_t tridiag_twostage_scratch_bytes(int n, long nk);
 // The two stages are launched separately: the band arrays of several workspace chunks are collected (they are 16 / n of a
 // matrix) and chased in one launch, which gives the latency-bound second stage enough matrices to fill the GPU.
 cudaError_t launch_band_reduce(int n, double* Hp, long nk, double* band_ws, cudaStream_t st, const Tuning& tune);
+long band_chase_wave_matrices(const Tuning& tune);  // matrices one resident wave of the second stage holds
 cudaError_t launch_band_chase(int n, double* band_ws, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune);
 // Register-resident warp-per-matrix variant (eig_tridiag_reg.cu), n <= kTridiagRegMaxN.  The matrix of problem k is the
 // packed n x n block at Hp + k * mstride; results go to D / E [k * ldo + off + i] (mstride = 0 -> n * n, ldo = 0 -> n).

@@ -1,0 +1,6 @@
+#!/bin/bash
+set +e
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+OUT=gpurun_out; mkdir -p $OUT
+PYTHONPATH=. timeout 1200 ncu --set full --clock-control none --import-source on -k regex:band_ -c 2 -f -o $OUT/${TAG:-r04n}_band python tools/tridiag_sweep.py --variants default 512:4736 > $OUT/${TAG:-r04n}_ncu.log 2>&1
+echo "ncu rc=$?"; tail -3 $OUT/${TAG:-r04n}_ncu.log

@@ -64,6 +64,16 @@ VARIANTS = {
     "two": {"TBK_TRIDIAG_TWOSTAGE": "12"},
     "two256": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "256"},
     "two512": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "512"},
+    "w4736": {"TBK_BAND_WAVE": "4736"},
+    "w7104": {"TBK_BAND_WAVE": "7104"},
+    "w8192": {"TBK_BAND_WAVE": "8192"},
+    "w100000": {"TBK_BAND_WAVE": "100000"},
+    "g256": {"TBK_BAND_GROUP_MB": "256"},
+    "g512": {"TBK_BAND_GROUP_MB": "512"},
+    "g768": {"TBK_BAND_GROUP_MB": "768"},
+    "g1024": {"TBK_BAND_GROUP_MB": "1024"},
+    "g1280": {"TBK_BAND_GROUP_MB": "1280"},
+    "g2048": {"TBK_BAND_GROUP_MB": "2048"},
     "two257": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "257"},
     "two_s1": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_STAGE2": "0"},
 }
