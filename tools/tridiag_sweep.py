@@ -61,6 +61,7 @@ VARIANTS = {
     "mid0": {"TBK_TRIDIAG_REG_MID": "0"},
     "mid20": {"TBK_TRIDIAG_REG_MID": "20"},
     "mid24": {"TBK_TRIDIAG_REG_MID": "24"},
+    "one": {"TBK_TRIDIAG_TWOSTAGE": "0"},
     "two": {"TBK_TRIDIAG_TWOSTAGE": "12"},
     "two256": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "256"},
     "two512": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "512"},
