@@ -749,6 +749,185 @@ band_chase_kernel(double2* band_all, int N, long nk, double* __restrict__ D, dou
     }
 }
 
+// Stage 2, pipelined form: ONE matrix per warp, its four 8-lane groups run four consecutive sweeps at once.  Sweep s may
+// perform its step k once sweep s - 1 has finished step k + 1 (their column ranges are disjoint from then on), so in
+// warp lockstep group g trails group g - 1 by two steps; a group starts its next sweep (s + 4) when it is free and that
+// sweep's predecessor is two steps ahead.  The start times follow a data-independent recurrence every lane evaluates for
+// itself.  Per-sweep arithmetic is exactly that of band_chase_kernel (bit-identical results); what changes is that the
+// four sweeps touch the same part of the band within a few steps -- the band is streamed from HBM once per FOUR sweeps
+// -- and that a small batch exposes four times as many warps.
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB)
+band_chase_pipe_kernel(double2* band_all, int N, long nk, double* __restrict__ D, double* __restrict__ E) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, gl = lane & 7, grp = lane >> 3;
+    const long mat = (long)blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (mat >= nk) return;  // (warp-uniform)
+    double2* band = band_all + mat * (long)N * BWD;
+    const int nsweeps = N - 1;
+    // start times of the four most recent sweeps of the schedule, indexed by sweep & 3
+    int st0 = 0, st1 = 2, st2 = 4, st3 = 6, ns = 4;
+    int s = grp, k = 0, tstart = 2 * grp;
+    bool alive = s < nsweeps;
+    double vr[BB], vi[BB], ovr = 0.0, ovi = 0.0, tr = 0.0, ti = 0.0;
+#pragma unroll
+    for (int c = 0; c < BB; ++c) vr[c] = vi[c] = 0.0;
+    for (int t = 0; __any_sync(FULL, alive); ++t) {
+        const bool run = alive && t >= tstart;
+        if (__any_sync(FULL, run && k == 0)) {
+            // groups that start a sweep: the reflector that annihilates column s below the sub-diagonal
+            const bool first = run && k == 0;
+            double xr = 0.0, xi = 0.0;
+            if (first && s + 1 + gl < N) {
+                const double2 x = band[(long)s * BWD + 1 + gl];
+                xr = x.x;
+                xi = x.y;
+            }
+            double xn = (gl >= 1) ? xr * xr + xi * xi : 0.0;
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) xn += __shfl_xor_sync(FULL, xn, off);
+            const double alr = __shfl_sync(FULL, xr, 0, 8), ali = __shfl_sync(FULL, xi, 0, 8);
+            double beta, ntr, nti, sr, si;
+            householder_gen(alr, ali, xn, beta, ntr, nti, sr, si);
+            if (first && gl == 0) {
+                D[mat * N + s] = band[(long)s * BWD].x;
+                E[mat * N + s] = beta;
+            }
+            const double novr = (gl == 0) ? 1.0 : xr * sr - xi * si;
+            const double novi = (gl == 0) ? 0.0 : xr * si + xi * sr;
+#pragma unroll
+            for (int c = 0; c < BB; ++c) {
+                const double a = __shfl_sync(FULL, novr, c, 8), b = __shfl_sync(FULL, novi, c, 8);
+                if (first) {
+                    vr[c] = a;
+                    vi[c] = b;
+                }
+            }
+            if (first) {
+                ovr = novr;
+                ovi = novi;
+                tr = ntr;
+                ti = nti;
+            }
+        }
+        const int R0 = s + 1 + BB * k;
+        const bool topok = run && (R0 + gl < N);
+        const bool botok = run && (R0 + BB + gl < N);
+        const double2* pcol = band + (long)R0 * BWD + gl;    // + 15 c: element (row R0 + gl, column R0 + c), c <= gl
+        const double2* pown = band + (long)(R0 + gl) * BWD;  // + d: element (row R0 + gl + d, column R0 + gl)
+        double dr[BB], di[BB], br[BB], bi[BB];
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            double2 e = make_double2(0.0, 0.0);
+            if (topok && c <= gl) e = pcol[15 * c];
+            if (topok && c > gl && R0 + c < N) {  // right of the diagonal: conjugate of the own column
+                e = pown[c - gl];
+                e.y = -e.y;
+            }
+            dr[c] = e.x;
+            di[c] = (c == gl) ? 0.0 : e.y;
+            double2 f = make_double2(0.0, 0.0);
+            if (botok) f = pcol[15 * c + BB];
+            br[c] = f.x;
+            bi[c] = f.y;
+        }
+        double p_r = 0.0, p_i = 0.0, y_r = 0.0, y_i = 0.0;
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            p_r = fma(dr[c], vr[c], fma(-di[c], vi[c], p_r));
+            p_i = fma(dr[c], vi[c], fma(di[c], vr[c], p_i));
+            y_r = fma(br[c], vr[c], fma(-bi[c], vi[c], y_r));
+            y_i = fma(br[c], vi[c], fma(bi[c], vr[c], y_i));
+        }
+        const double tpr = tr * p_r - ti * p_i, tpi = tr * p_i + ti * p_r;
+        double d_r = tpr * ovr + tpi * ovi, d_i = tpr * ovi - tpi * ovr;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            d_r += __shfl_xor_sync(FULL, d_r, off);
+            d_i += __shfl_xor_sync(FULL, d_i, off);
+        }
+        const double al_r = -0.5 * (tr * d_r - ti * d_i), al_i = -0.5 * (tr * d_i + ti * d_r);
+        const double owr = tpr + al_r * ovr - al_i * ovi, owi = tpi + al_r * ovi + al_i * ovr;
+        const double tyr = tr * y_r - ti * y_i, tyi = tr * y_i + ti * y_r;
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            const double wr = __shfl_sync(FULL, owr, c, 8), wi = __shfl_sync(FULL, owi, c, 8);
+            dr[c] -= ovr * wr + ovi * wi + owr * vr[c] + owi * vi[c];
+            di[c] -= ovi * wr - ovr * wi + owi * vr[c] - owr * vi[c];
+            br[c] -= tyr * vr[c] + tyi * vi[c];
+            bi[c] -= tyi * vr[c] - tyr * vi[c];
+        }
+        double xn2 = (gl >= 1) ? br[0] * br[0] + bi[0] * bi[0] : 0.0;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) xn2 += __shfl_xor_sync(FULL, xn2, off);
+        const double a2r = __shfl_sync(FULL, br[0], 0, 8), a2i = __shfl_sync(FULL, bi[0], 0, 8);
+        double beta2, t2r, t2i, s2r, s2i;
+        householder_gen(a2r, a2i, xn2, beta2, t2r, t2i, s2r, s2i);
+        const double mv2r = (gl == 0) ? 1.0 : br[0] * s2r - bi[0] * s2i;
+        const double mv2i = (gl == 0) ? 0.0 : br[0] * s2i + bi[0] * s2r;
+        const double cvr = t2r * mv2r + t2i * mv2i, cvi = t2r * mv2i - t2i * mv2r;
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            double z_r = mv2r * br[c] + mv2i * bi[c];
+            double z_i = mv2r * bi[c] - mv2i * br[c];
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {
+                z_r += __shfl_xor_sync(FULL, z_r, off);
+                z_i += __shfl_xor_sync(FULL, z_i, off);
+            }
+            br[c] -= cvr * z_r - cvi * z_i;
+            bi[c] -= cvr * z_i + cvi * z_r;
+        }
+        br[0] = (gl == 0) ? beta2 : 0.0;
+        bi[0] = 0.0;
+        double2* qcol = band + (long)R0 * BWD + gl;
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            if (topok && c <= gl) qcol[15 * c] = make_double2(dr[c], (c == gl) ? 0.0 : di[c]);
+            if (botok) qcol[15 * c + BB] = make_double2(br[c], bi[c]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < BB; ++c) {
+            const double a = __shfl_sync(FULL, mv2r, c, 8), b = __shfl_sync(FULL, mv2i, c, 8);
+            if (run) {
+                vr[c] = a;
+                vi[c] = b;
+            }
+        }
+        if (run) {
+            ovr = mv2r;
+            ovi = mv2i;
+            tr = t2r;
+            ti = t2i;
+            const int L = (N + 6 - s) >> 3;  // steps of sweep s
+            if (++k >= L) {
+                s += 4;
+                k = 0;
+                alive = s < nsweeps;
+                if (alive) {
+                    while (ns <= s) {  // start(ns) = max(start(ns - 1) + 2, start(ns - 4) + steps(ns - 4))
+                        const int i = ns & 3, ip = (ns - 1) & 3;
+                        const int prev = ip == 0 ? st0 : ip == 1 ? st1 : ip == 2 ? st2 : st3;
+                        const int own = i == 0 ? st0 : i == 1 ? st1 : i == 2 ? st2 : st3;
+                        const int a = prev + 2, b = own + ((N + 6 - (ns - 4)) >> 3);
+                        const int v = a > b ? a : b;
+                        if (i == 0) st0 = v; else if (i == 1) st1 = v; else if (i == 2) st2 = v; else st3 = v;
+                        ++ns;
+                    }
+                    const int i = s & 3;
+                    tstart = i == 0 ? st0 : i == 1 ? st1 : i == 2 ? st2 : st3;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        D[mat * N + N - 1] = band[(long)(N - 1) * BWD].x;
+        E[mat * N + N - 1] = 0.0;
+    }
+}
+
 template <int THREADS, int MINB>
 cudaError_t launch_band_reduce_t(int n, double* Hp, long nk, double2* band, cudaStream_t st) {
     const size_t smem = band_smem_doubles(n, THREADS / 32) * 8;
@@ -785,7 +964,7 @@ long band_chase_wave_matrices(const Tuning& tune) {
     static const long wave = [] {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        return (long)sms * 16 * 4;  // 16 warps per SM (128 registers), 4 matrices per warp
+        return (long)sms * 12;  // 12 warps per SM (168 registers), one matrix per warp
     }();
     return wave;
 }
@@ -794,11 +973,22 @@ long band_chase_wave_matrices(const Tuning& tune) {
 cudaError_t launch_band_chase(int n, double* band_ws, long nk, double* D, double* E, cudaStream_t st, const Tuning& tune) {
     if (nk <= 0) return cudaSuccess;
     if (band_ws == nullptr) return cudaErrorInvalidConfiguration;
-    (void)tune;
     constexpr int WPB = 4;
-    const long ctas = (nk + 4 * WPB - 1) / (4 * WPB);
+    if (tune.band_chase == 1) {  // (first form: four matrices per warp, one sweep at a time)
+        const long ctas = (nk + 4 * WPB - 1) / (4 * WPB);
+        if (ctas > 2147483647L) return cudaErrorInvalidConfiguration;
+        band_chase_kernel<WPB><<<(unsigned)ctas, 32 * WPB, 0, st>>>(reinterpret_cast<double2*>(band_ws), n, nk, D, E);
+        return cudaGetLastError();
+    }
+    const long ctas = (nk + WPB - 1) / WPB;
     if (ctas > 2147483647L) return cudaErrorInvalidConfiguration;
-    band_chase_kernel<WPB><<<(unsigned)ctas, 32 * WPB, 0, st>>>(reinterpret_cast<double2*>(band_ws), n, nk, D, E);
+    // 12 warps per SM (168 registers, no spills).  Measured against 16 warps at 128 registers with 136 bytes of spills
+    // (TBK_BAND_CHASE=4), both stages, ms per 1000 matrices: N = 256: 9.54 / 10.74 (18 944 matrices), 14.6 / 20.1 (296);
+    // N = 512: 62.3 / 65.7 (9 472), 81.9 / 104.0 (296) -- gpurun_out/r04y_sweep.log
+    if (tune.band_chase == 4)
+        band_chase_pipe_kernel<WPB, 4><<<(unsigned)ctas, 32 * WPB, 0, st>>>(reinterpret_cast<double2*>(band_ws), n, nk, D, E);
+    else
+        band_chase_pipe_kernel<WPB, 3><<<(unsigned)ctas, 32 * WPB, 0, st>>>(reinterpret_cast<double2*>(band_ws), n, nk, D, E);
     return cudaGetLastError();
 }
 

@@ -961,17 +961,18 @@ int smem_residency(int n) {
     return best;
 }
 
-constexpr int kTwoStageMinN = 224;  // two-stage reduction (eig_band.cu) from this size on, see tridiag_twostage_default
+constexpr int kTwoStageMinN = 128;  // two-stage reduction (eig_band.cu) from this size on, see tridiag_twostage_default
 constexpr int kPanelMinN = 161;   // blocked kernel from this size on (re-measured in round 2, see below)
 constexpr int kStagedMaxN = 160;  // staged shared-memory reduction while the packed matrix + work vectors fit 227 KB
 
 // Sizes the two-stage reduction (eig_band.cu) serves: TBK_TRIDIAG_TWOSTAGE = first such N (0 = never).  The hooks that force
-// one of the one-stage kernels win.  Measured on B200, ms per 1000 matrices, one-stage (blocked kernel + staged tail) /
-// two-stage, batches that fill the second stage (profiles/r04l_twostage_sweep.log): N = 161: 4.60 / 4.38, 200: 8.02 / 7.49,
-// 224: 11.2 / 9.72, 256: 16.6 / 13.3, 320: 34.5 / 26.9, 384: 57.0 / 43.5, 512: 118.8 / 85.0, 640: 553 / 186, 700: 2572 / 328
-// (the blocked kernel ends at N = 640).  Batches of a few hundred matrices leave the warp-per-two-matrices second stage
-// under-occupied (N = 512, 296 matrices: 117 / 214), and the choice may depend on N only (results must not depend on the
-// batch): the two-stage reduction serves the sizes where it wins by more than 15 % on large batches.
+// one of the one-stage kernels win.  Measured on B200, ms per 1000 matrices, one-stage (staged shared-memory kernels up to
+// 160, blocked kernel + staged tail above) / two-stage, batches of 9 472 - 37 888 matrices (profiles/r05a_twostage_small_n_sweep.log,
+// r04z_twostage_threshold_sweep.log, r04w_onestage_vs_twostage_sweep.log): N = 96: 1.05 / 1.25, 112: 1.54 / 1.63,
+// 128: 2.38 / 2.05, 144: 3.59 / 2.57, 160: 4.99 / 3.20, 200: 7.97 / 5.35, 224: 11.1 / 6.82, 256: 16.4 / 9.54, 320: 34.9 / 21.2,
+// 512: 117.2 / 62.9, 640: 561 / 154, 700: 2328 / 202 (the blocked kernel ends at N = 640).  Batches of a few hundred matrices
+// (296): N = 128: 3.03 / 3.73, 160: 5.52 / 5.58, 224: 11.8 / 10.9, 256: 16.9 / 14.6, 512: 117 / 81.9.  The choice may depend
+// on N only (results must not depend on the batch): the two-stage reduction serves every size where it wins on large batches.
 bool tridiag_twostage_default(int n, const Tuning& tune) {
     const int from = tune.tridiag_twostage >= 0 ? tune.tridiag_twostage : kTwoStageMinN;
     return from > 0 && n >= from && tune.tridiag_g == 0 && tune.tridiag_panel_min == 0 && !tune.tridiag_nopanel &&

@@ -133,6 +133,7 @@ Tuning read_tuning() {
     t.band_stage2 = env_int("TBK_BAND_STAGE2", t.band_stage2);
     t.band_group_mb = env_int("TBK_BAND_GROUP_MB", (int)t.band_group_mb);
     t.band_wave = env_int("TBK_BAND_WAVE", t.band_wave);
+    t.band_chase = env_int("TBK_BAND_CHASE", t.band_chase);
     t.ql_global_min = env_int("TBK_QL_GLOBAL_MIN", 0);
     t.ql_overlap = env_int("TBK_QL_OVERLAP", t.ql_overlap);
     return t;

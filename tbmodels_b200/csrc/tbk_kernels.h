@@ -53,6 +53,8 @@ struct Tuning {
                                 //   (0 = never, -1 = default)
     int band_t = 0;             // TBK_BAND_T: threads per matrix of the band reduction (0 = by size)
     int band_stage2 = 1;        // TBK_BAND_STAGE2=0: timing hook, skip the bulge chasing (results are then meaningless)
+    int band_chase = 0;         // TBK_BAND_CHASE: 1 = first form of the bulge chasing (four matrices per warp, one sweep
+                                //   each), 4 = pipelined form at 16 warps per SM (128 registers, spills)
     int band_wave = 0;          // TBK_BAND_WAVE: matrices per launch of the bulge chasing (0 = one resident wave)
     long band_group_mb = 2048;  // TBK_BAND_GROUP_MB: band arrays collected before one bulge-chasing launch
     int gemm_dense = 0;         // TBK_GEMM_DENSE: never skip all-zero weight stages (block-sparse models; A/B tests)

@@ -399,10 +399,10 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
 
 
 @pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 36, 37, 40, 41, 48, 49, 64, 65, 96, 97, 112, 113, 119, 120, 121, 128, 129, 144,
-                                   159, 160, 161, 164, 165, 200, 223, 224, 225, 257, 288, 289, 300, 513, 600, 601, 641, 700, 816, 817])
+                                   127, 159, 160, 161, 164, 165, 200, 223, 224, 225, 257, 288, 289, 300, 513, 600, 601, 641, 700, 808, 809])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
     """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection, one-stage /
-    two-stage reduction from N = 224, its thread configurations, its last size 816)."""
+    two-stage reduction from N = 128, its thread configurations, its last size 808)."""
     from oracle import workloads as wl
 
     orc = _oracle()
@@ -456,6 +456,33 @@ def test_blocked_tridiag_every_shape(tbk, monkeypatch, threads, lpr):
         p = wl.synthetic(n_orb, 3, seed=1000 + n_orb)
         k = np.random.default_rng(n_orb).uniform(-1, 1, size=(7 if n_orb <= 129 else 3, 3))
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"blocked N={n_orb} T={threads} LPR={lpr}")
+
+
+@pytest.mark.parametrize("n_orb", [128, 129, 144, 160, 161, 164, 165, 200, 257, 300, 513, 600, 601])
+def test_one_stage_kernels_still_agree(tbk, monkeypatch, n_orb):
+    """The one-stage path the two-stage reduction replaced by default for N >= 128 (staged shared-memory kernels, the
+    blocked kernel and its hand-over to the staged tail) stays reachable through TBK_TRIDIAG_TWOSTAGE=0."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_TRIDIAG_TWOSTAGE", "0")
+    p = wl.synthetic(n_orb, 4, seed=n_orb)
+    k = np.random.default_rng(n_orb).uniform(-1, 1, size=(5 if n_orb <= 300 else 2, 3))
+    _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"one-stage N={n_orb}")
+
+
+@pytest.mark.parametrize("chase", ["1", "4"])
+def test_twostage_bulge_chasing_variants(tbk, monkeypatch, chase):
+    """The first form of the second stage (four matrices per warp, one sweep at a time) and the 16-warp build of the
+    pipelined form stay reachable and agree with the oracle."""
+    from oracle import workloads as wl
+
+    orc = _oracle()
+    monkeypatch.setenv("TBK_BAND_CHASE", chase)
+    for n_orb in (128, 131, 200, 230):
+        p = wl.synthetic(n_orb, 3, seed=3000 + n_orb)
+        k = np.random.default_rng(n_orb).uniform(-1, 1, size=(5, 3))
+        _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"two-stage chase={chase} N={n_orb}")
 
 
 @pytest.mark.parametrize("threads", ["256", "257", "512"])

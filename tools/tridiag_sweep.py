@@ -62,6 +62,9 @@ VARIANTS = {
     "mid20": {"TBK_TRIDIAG_REG_MID": "20"},
     "mid24": {"TBK_TRIDIAG_REG_MID": "24"},
     "one": {"TBK_TRIDIAG_TWOSTAGE": "0"},
+    "chase1": {"TBK_BAND_CHASE": "1"},
+    "chase4": {"TBK_BAND_CHASE": "4"},
+    "two_chase1": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_CHASE": "1"},
     "two": {"TBK_TRIDIAG_TWOSTAGE": "12"},
     "two256": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "256"},
     "two512": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "512"},
