@@ -1,6 +1,6 @@
-// eig_band.cu -- two-stage Hermitian -> tridiagonal reduction for matrices that live in L2 / HBM (N > 160).
+// eig_band.cu -- two-stage Hermitian -> tridiagonal reduction (N >= 128).
 //
-// Same role as eig_tridiag_panel.cu (first half of the replacement for the per-k scipy.linalg.eigvalsh loop of
+// Same role as eig_tridiag.cu / eig_tridiag_panel.cu (first half of the replacement for the per-k scipy.linalg.eigvalsh loop of
 // Model.eigenval, reference src/tbmodels/_tb_model.py:1148-1149; LAPACK zheevr JOBZ='N', UPLO='L'), different
 // formulation.  The one-stage reduction needs one Hermitian matrix-vector product with the whole trailing matrix per
 // column -- half of its flops are BLAS-2 and stream the matrix from L2 / HBM once per column (394 MB per 512 x 512
@@ -16,11 +16,13 @@
 //       A22   -= V Z^H + Z V^H                         (tensor cores, the her2k of the blocked kernel)
 //     R and the diagonal block go to the band array band[c][d] = A[c + d, c], d = 0 .. 15 (8 diagonals of room for the
 //     bulges of stage 2).  The matrix is read twice and written once per EIGHT columns instead of once per column.
-//   stage 2, band_chase_kernel (16 lanes per matrix, two matrices per warp): band -> tridiagonal by bulge chasing with
-//     length-8 reflectors (the Householder form of the Schwarz / Murata-Horikoshi algorithm): sweep j annihilates
-//     column j below the sub-diagonal, the 8 x 8 bulge this opens one block further down is chased off the end of the
-//     band block by block.  A lane owns one row of the 16 x 8 panel [diagonal block; block below]; every product is a
-//     few shuffles inside the 16-lane group.
+//   stage 2, band_chase_pipe_kernel (one matrix per warp): band -> tridiagonal by bulge chasing with length-8 reflectors
+//     (the Householder form of the Schwarz / Murata-Horikoshi algorithm): sweep j annihilates column j below the
+//     sub-diagonal, the 8 x 8 bulge this opens one block further down is chased off the end of the band block by block.
+//     An 8-lane group runs one sweep: lane l owns row l of the diagonal block (the full Hermitian row) and row l of the
+//     block below, every product along a row is local, the few sums across lanes are 3-level shuffles.  The warp's four
+//     groups run four consecutive sweeps two steps apart, so the band is streamed from HBM once per four sweeps.
+//     (band_chase_kernel: the first form, four matrices per warp and one sweep at a time, kept behind TBK_BAND_CHASE=1.)
 //
 // Both stages use fixed-order reductions only: results do not depend on the batch.  tools/twostage_proto.py is a numpy
 // walk-through of exactly these steps and index conventions.
