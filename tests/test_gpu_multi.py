@@ -19,6 +19,8 @@ def _free_port():
 def _model(kind):
     from oracle import workloads as wl
 
+    if kind == "syn130":  # two-stage tridiagonalisation: band arrays collected over several chunks before the peer push
+        return wl.synthetic(130, 3, seed=9)
     return wl.haldane() if kind == "haldane" else wl.synthetic(12, 10)
 
 
@@ -53,7 +55,7 @@ def _worker(rank, world, port, n_k, out_dir, kind="syn12"):
 
 
 @pytest.mark.parametrize("n_k,ws_mb,kind", [(4096, None, "syn12"), (5001, None, "syn12"), (30001, "1", "syn12"),
-                                           (2_500_001, None, "haldane")])
+                                           (2_500_001, None, "haldane"), (301, "1", "syn130")])
 def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb, kind):
     import torch
     import torch.multiprocessing as mp
@@ -65,8 +67,11 @@ def test_two_gpu_nccl_sharding(tmp_path, monkeypatch, n_k, ws_mb, kind):
 
     if ws_mb:  # tiny workspace: many chunks per rank, so the peer stores of the fused gather interleave with compute
         monkeypatch.setenv("TBK_WORKSPACE_MB", ws_mb)
+    if kind == "syn130":  # groups of four chunks, several groups per rank
+        monkeypatch.setenv("TBK_BAND_GROUP_MB", "1")
     mp.spawn(_worker, args=(2, _free_port(), n_k, str(tmp_path), kind), nprocs=2, join=True)
     monkeypatch.delenv("TBK_WORKSPACE_MB", raising=False)
+    monkeypatch.delenv("TBK_BAND_GROUP_MB", raising=False)
     d0 = np.load(tmp_path / "r0.npz")
     d1 = np.load(tmp_path / "r1.npz")
     want = tbk.Evaluator(_model(kind), device=0).eigenval_array(d0["k"])

@@ -485,7 +485,7 @@ def test_twostage_bulge_chasing_variants(tbk, monkeypatch, chase):
         _check(tbk, p, k, None, None, orc.eigenval_array(p.R, p.hop, p.pos, k), f"two-stage chase={chase} N={n_orb}")
 
 
-@pytest.mark.parametrize("threads", ["256", "257", "512"])
+@pytest.mark.parametrize("threads", ["128", "256", "257", "512"])
 def test_twostage_tridiag_every_shape(tbk, monkeypatch, threads):
     """The two-stage reduction (band of half bandwidth 8 on the tensor cores + bulge chasing, eig_band.cu) forced onto
     small and ragged sizes: sizes that are not multiples of 8, last panels with fewer than 8 rows, a single panel,

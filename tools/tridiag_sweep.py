@@ -66,6 +66,7 @@ VARIANTS = {
     "chase4": {"TBK_BAND_CHASE": "4"},
     "two_chase1": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_CHASE": "1"},
     "two": {"TBK_TRIDIAG_TWOSTAGE": "12"},
+    "t128": {"TBK_BAND_T": "128"},
     "two256": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "256"},
     "two512": {"TBK_TRIDIAG_TWOSTAGE": "12", "TBK_BAND_T": "512"},
     "w4736": {"TBK_BAND_WAVE": "4736"},
