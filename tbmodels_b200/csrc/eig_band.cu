@@ -24,8 +24,8 @@
 //     groups run four consecutive sweeps two steps apart, so the band is streamed from HBM once per four sweeps.
 //     (band_chase_kernel: the first form, four matrices per warp and one sweep at a time, kept behind TBK_BAND_CHASE=1.)
 //
-// Both stages use fixed-order reductions only: results do not depend on the batch.  tools/twostage_proto.py is a numpy
-// walk-through of exactly these steps and index conventions.
+// Both stages use fixed-order reductions only: results do not depend on the batch.  oracle/twostage_hetrd.py is a numpy
+// walk-through of exactly these steps, index conventions and the pipelined schedule (pinned against LAPACK in the CPU suite).
 #include <cstdio>
 #include <cstdlib>
 
