@@ -954,10 +954,11 @@ cudaError_t launch_band_reduce(int n, double* Hp, long nk, double* band_ws, cuda
     // threads per matrix (tuning hook TBK_BAND_T).  Measured on B200, both stages, ms per 1000 matrices (r04k_sweep2.log):
     // N = 200: 256 threads 9.30, 2 x 256 per SM 7.90, 512 threads 9.54;  N = 256: 16.0 / 14.0 / 15.9 -- two independent
     // CTAs per SM overlap one matrix' barrier-bound panel factorisation with the other's tensor-core passes while both
-    // fit in shared memory; at N = 368 one 512-thread CTA is ahead again (47.1 against 53.4).  Four 128-thread CTAs per SM
+    // fit in shared memory; the final kernels cross over near N = 340 (two 256-thread CTAs / one 512-thread CTA: N = 288:
+    // 13.0 / 14.6, 304: 16.6 / 17.1, 320: 19.4 / 19.8, 352: 24.4 / 24.1; r05h_sweep2.log).  Four 128-thread CTAs per SM
     // help only the smallest sizes, where the barriers of the panel factorisation dominate (N = 128: 1.88 against 2.05,
     // 144: 2.53 / 2.57, 160: 3.22 / 3.20, 200: 5.65 / 5.34; r05e_sweep.log).
-    const int t = tune.band_t > 0 ? tune.band_t : (n <= 136 ? 128 : n <= 288 ? 257 : 512);
+    const int t = tune.band_t > 0 ? tune.band_t : (n <= 136 ? 128 : n <= 336 ? 257 : 512);
     if (t == 128) return launch_band_reduce_t<128, 4>(n, Hp, nk, band, st);  // (four CTAs per SM)
     if (t == 256) return launch_band_reduce_t<256, 1>(n, Hp, nk, band, st);
     if (t == 257) return launch_band_reduce_t<256, 2>(n, Hp, nk, band, st);  // (two CTAs per SM: 128 registers)

@@ -399,7 +399,7 @@ def test_tridiag_variants_agree(tbk, monkeypatch, g):
 
 
 @pytest.mark.parametrize("n_orb", [9, 10, 11, 20, 21, 32, 33, 36, 37, 40, 41, 48, 49, 64, 65, 96, 97, 112, 113, 119, 120, 121, 128, 129, 144,
-                                   127, 159, 160, 161, 164, 165, 200, 223, 224, 225, 257, 288, 289, 300, 513, 600, 601, 641, 700, 808, 809])
+                                   127, 136, 137, 159, 160, 161, 164, 165, 200, 223, 224, 225, 257, 288, 289, 300, 336, 337, 513, 600, 601, 641, 700, 808, 809])
 def test_size_boundaries_vs_oracle(tbk, n_orb):
     """Every dispatch boundary of the eigensolver (thread-group sizes, smem / global, QL / bisection, one-stage /
     two-stage reduction from N = 128, its thread configurations, its last size 808)."""
