@@ -43,6 +43,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
     e = fma(-x, y, 1.0);
     return fma(y, e, y);
 }
+// Two Newton steps: rcp.approx.ftz.f64 reads the upper 20 mantissa bits of its operand (relative error ~ 2^-20), so the
+// error after two steps (~ 2^-80) is already far below one ulp.  Used where the reciprocal sits in a long dependent chain
+// and a last-bit rounding difference is immaterial (the Sturm recurrence of the bisection: 50 N^2 of them per matrix).
+__device__ __forceinline__ double fast_rcp2(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 __device__ __forceinline__ double fast_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
@@ -291,7 +302,7 @@ TBK_HD int sturm_count(int n, const double* d, const double* e2, double x, doubl
     int cnt = q < 0.0 ? 1 : 0;
     for (int i = 1; i < n; ++i) {
 #if defined(__CUDA_ARCH__)
-        q = fma(-e2[i - 1], fast_rcp(q), d[i] - x);
+        q = fma(-e2[i - 1], fast_rcp2(q), d[i] - x);
 #else
         q = d[i] - x - e2[i - 1] / q;
 #endif
