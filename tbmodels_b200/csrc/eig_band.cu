@@ -10,12 +10,14 @@
 //       E      = A[r0:, c0:c0+8]                       (the block below the band, r0 = c0 + 8) -> shared memory
 //       E      = Q [R; 0],  Q = H_0 .. H_7 = I - V T V^H   (Householder QR in shared memory, ONE block reduction per
 //                                                           column: norm and the 7 - k dot products together)
-//       Y      = A22 V                                 (A22 = A[r0:, r0:], read ONCE per panel, FP64 tensor cores)
+//       Y      = A22 V                                 (A22 = A[r0:, r0:]; FP64 tensor cores; the stored triangle is read
+//                                                        as is and as its conjugate transpose)
 //       G, M   = V^H V, V^H Y                          (8 x 8, tensor cores) ;  T from G and tau (zlarft recurrence)
 //       Z      = Y T - 1/2 V (T^H M T)
 //       A22   -= V Z^H + Z V^H                         (tensor cores, the her2k of the blocked kernel)
 //     R and the diagonal block go to the band array band[c][d] = A[c + d, c], d = 0 .. 15 (8 diagonals of room for the
-//     bulges of stage 2).  The matrix is read twice and written once per EIGHT columns instead of once per column.
+//     bulges of stage 2).  The stored triangle is read three times and written once per EIGHT columns instead of once
+//     per column.
 //   stage 2, band_chase_pipe_kernel (one matrix per warp): band -> tridiagonal by bulge chasing with length-8 reflectors
 //     (the Householder form of the Schwarz / Murata-Horikoshi algorithm): sweep j annihilates column j below the
 //     sub-diagonal, the 8 x 8 bulge this opens one block further down is chased off the end of the band block by block.
